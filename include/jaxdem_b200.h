@@ -1,0 +1,222 @@
+/* jaxdem_b200 — C ABI of the B200-native DEM step engine (libjaxdem_b200.so).
+ *
+ * Drop-in boundary for the per-timestep hot path of cdelv/JaxDEM
+ * (System.step / _step_once, jaxdem/system.py:60-98).  Each entry point below
+ * replaces one plugin hook of the reference; the hook it replaces is cited as
+ * reference file:line.  INTEGRATION.md shows the jax.ffi binding a JaxDEM
+ * maintainer would add on top of these symbols.
+ *
+ * Rules every entry point obeys:
+ *  - stream-ordered and asynchronous: work is enqueued on `stream`, the call
+ *    never synchronises with the host, never allocates, never throws, and
+ *    touches no global mutable state => legal inside jit / lax.scan /
+ *    lax.fori_loop and CUDA-graph capture, re-entrant across threads;
+ *  - all buffers are caller-owned DEVICE pointers, dense row-major, exactly
+ *    the State / System pytree leaves of the reference (jaxdem/state.py:103-228),
+ *    with an optional leading batch axis of size `params.batch` (vmap);
+ *  - everything the reference treats as a traced leaf (dt, box, anchor,
+ *    cell_size, material tables, ...) is read from device memory; only shapes,
+ *    dtypes and type names are host-side (`jdb200_params`);
+ *  - scratch comes from a caller-provided workspace sized by
+ *    jdb200_workspace_bytes();
+ *  - return value: 0 on success, negative JDB200_E* for ARGUMENT errors only.
+ *    Data-dependent failures (hash overflow, neighbour-list overflow) are
+ *    written to device flags, mirroring Collider.overflow
+ *    (jaxdem/colliders/__init__.py:51-54);
+ *  - State buffers are updated IN PLACE (bind with operand/result aliasing
+ *    under XLA FFI).
+ *
+ * dtype pairs: JDB200_F32 = <float, int32_t>, JDB200_F64 = <double, int64_t>
+ * (jax_enable_x64 off / on).  `fixed` and boolean flags are uint8.
+ */
+#ifndef JAXDEM_B200_H
+#define JAXDEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JDB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define JDB200_API __attribute__((visibility("default")))
+#else
+#define JDB200_API
+#endif
+
+/* error codes */
+#define JDB200_OK 0
+#define JDB200_EINVAL (-1)    /* bad params (dim, dtype, law, ...) */
+#define JDB200_ENULL (-2)     /* a required pointer is NULL */
+#define JDB200_EWORKSPACE (-3) /* workspace too small */
+#define JDB200_ECUDA (-4)     /* kernel launch failed (cudaGetLastError) */
+
+enum { JDB200_F32 = 0, JDB200_F64 = 1 };
+enum { JDB200_DOMAIN_FREE = 0, JDB200_DOMAIN_PERIODIC = 1, JDB200_DOMAIN_REFLECT = 2 };
+enum { JDB200_LAW_SPRING = 0, JDB200_LAW_HERTZ = 1, JDB200_LAW_CUNDALLSTRACK = 2 };
+enum { JDB200_LIN_NONE = 0, JDB200_LIN_VERLET = 1, JDB200_LIN_EULER = 2 };
+enum { JDB200_ROT_NONE = 0, JDB200_ROT_VERLETSPIRAL = 1, JDB200_ROT_SPIRAL = 2 };
+enum { JDB200_COLLIDER_NONE = 0, JDB200_COLLIDER_CELLLIST = 1, JDB200_COLLIDER_NAIVE = 2 };
+/* cell-table strategy.  AUTO picks, per system and per call, ON THE DEVICE:
+ * DENSE (counting sort into a dense cell table) when every cell hash lies in
+ * [0, max_cells) and no cell holds more than JDB200_DENSE_MAX_OCC particles,
+ * else SORTED (stable LSD radix sort + binary search; any hash values).
+ * Both produce bit-identical perm / sorted hashes / neighbour lists. */
+enum { JDB200_GRID_AUTO = 0, JDB200_GRID_DENSE = 1, JDB200_GRID_SORTED = 2 };
+#define JDB200_DENSE_MAX_OCC 64
+
+/* Trace-time-static values only (shapes, dtypes, type names). */
+typedef struct jdb200_params {
+  int64_t batch;          /* leading vmap axis, >= 1 */
+  int64_t n;              /* particles per system */
+  int64_t max_cells;      /* dense cell-table capacity per system (0 => SORTED) */
+  int32_t dim;            /* 2 or 3 */
+  int32_t dtype;          /* JDB200_F32 / JDB200_F64 */
+  int32_t domain;         /* JDB200_DOMAIN_* (periodic <=> Domain.periodic) */
+  int32_t law;            /* JDB200_LAW_* (ForceModel type_name) */
+  int32_t collider;       /* JDB200_COLLIDER_* */
+  int32_t linear_integrator;   /* JDB200_LIN_* */
+  int32_t rotation_integrator; /* JDB200_ROT_* */
+  int32_t stencil_m;      /* rows of neighbor_mask */
+  int32_t bond_width;     /* W of bond_id (N, W) */
+  int32_t n_materials;    /* M of the material tables */
+  int32_t max_neighbors;  /* K of create_neighbor_list */
+  int32_t grid_mode;      /* JDB200_GRID_* */
+  int32_t clumps;         /* 0: caller promises clump_id == arange(N) (spheres only; the
+                             clump reductions are identities), 1: general clump ids */
+} jdb200_params;
+
+/* State leaves (jaxdem/state.py:103-228).  F = float/double, I = int32/int64.
+ * A = 3 in 3D, 1 in 2D.  NULL is allowed for leaves an entry point does not use. */
+typedef struct jdb200_state {
+  void* pos_c;     /* (B,N,D) F */
+  void* pos_p;     /* (B,N,D) F */
+  void* vel;       /* (B,N,D) F */
+  void* force;     /* (B,N,D) F */
+  void* q_w;       /* (B,N,1) F */
+  void* q_xyz;     /* (B,N,3) F */
+  void* ang_vel;   /* (B,N,A) F */
+  void* torque;    /* (B,N,A) F */
+  void* inertia;   /* (B,N,A) F */
+  void* rad;       /* (B,N) F */
+  void* mass;      /* (B,N) F */
+  void* clump_id;  /* (B,N) I */
+  void* mat_id;    /* (B,N) I */
+  void* bond_id;   /* (B,N,W) I, -1 padded */
+  void* fixed;     /* (B,N) uint8 */
+  void* pos_p_rot; /* (B,N,D) F  cache R(q)·pos_p (State._pos_p_rot) */
+} jdb200_state;
+
+/* System leaves (jaxdem/system.py:123-228 and the components it holds). */
+typedef struct jdb200_system {
+  void* dt;                    /* (B,) F */
+  void* box_size;              /* (B,D) F   Domain.box_size */
+  void* inv_box_size;          /* (B,D) F   Domain.inv_box_size */
+  void* anchor;                /* (B,D) F   Domain.anchor */
+  void* restitution;           /* (B,) F    ReflectDomain.restitution_coefficient */
+  void* cell_size;             /* (B,) F    DynamicCellList.cell_size */
+  void* neighbor_mask;         /* (B,M,D) I DynamicCellList.neighbor_mask */
+  void* collider_overflow;     /* (B,) uint8 out: Collider.overflow */
+  void* interact_same_bond_id; /* (B,) uint8 */
+  void* gravity;               /* (B,D) F   ForceManager.gravity */
+  void* external_force;        /* (B,N,D) F ForceManager.external_force (cleared by apply) */
+  void* external_force_com;    /* (B,N,D) F */
+  void* external_torque;       /* (B,N,A) F */
+  void* mat_young;             /* (B,Mt) F  MaterialTable.young */
+  void* mat_poisson;           /* (B,Mt) F */
+  void* mat_e;                 /* (B,Mt) F */
+  void* mat_mu;                /* (B,Mt) F */
+  void* mat_mu_r;              /* (B,Mt) F */
+  void* mat_young_eff;         /* (B,Mt,Mt) F MaterialTable.young_eff */
+} jdb200_system;
+
+JDB200_API int jdb200_abi_version(void);
+
+/* Bytes of scratch any entry point below needs for these params. */
+JDB200_API size_t jdb200_workspace_bytes(const jdb200_params* p);
+
+/* ---- collider: DynamicCellList ("CellList") ------------------------------ */
+
+/* _get_spatial_partition (jaxdem/colliders/cell_list.py:35-87) +
+ * _grid_params (_partition.py:54-99).  Optional outputs (NULL to skip), for
+ * parity checks and for callers that want the partition itself:
+ *   perm        (B,N) I   stable-sort permutation
+ *   sorted_hash (B,N) I   sorted cell hashes
+ *   nbr_hash    (B,N,M) I neighbour-cell hashes after the periodic de-dup
+ *                         (_dedup_stencil_hashes, cell_list.py:90-96)
+ *   used_dense  (B,) uint8  which cell-table strategy ran */
+JDB200_API int jdb200_celllist_partition(void* stream, const jdb200_params* p, const jdb200_state* st,
+                              const jdb200_system* sys, void* ws, size_t ws_bytes, void* perm,
+                              void* sorted_hash, void* nbr_hash, void* used_dense);
+
+/* DynamicCellList.compute_force (cell_list.py:434-464): writes st->force,
+ * st->torque (= sum T + cross(pos_p_rot, sum F)) and sys->collider_overflow. */
+JDB200_API int jdb200_celllist_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                  const jdb200_system* sys, void* ws, size_t ws_bytes);
+
+/* DynamicCellList.compute_potential_energy (cell_list.py:466-496):
+ * energy (B,) F. */
+JDB200_API int jdb200_celllist_compute_potential_energy(void* stream, const jdb200_params* p,
+                                             const jdb200_state* st, const jdb200_system* sys,
+                                             void* ws, size_t ws_bytes, void* energy);
+
+/* DynamicCellList.create_neighbor_list (cell_list.py:498-595): cutoff (B,) F
+ * on device; neighbor_list (B,N,K) I padded with -1; overflow (B,) uint8. */
+JDB200_API int jdb200_celllist_create_neighbor_list(void* stream, const jdb200_params* p,
+                                         const jdb200_state* st, const jdb200_system* sys,
+                                         void* ws, size_t ws_bytes, const void* cutoff,
+                                         void* neighbor_list, void* overflow);
+
+/* NaiveSimulator.compute_force / compute_potential_energy
+ * (jaxdem/colliders/naive.py:187-235, 73-113): O(N^2), the reference's default
+ * collider (README config). */
+JDB200_API int jdb200_naive_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                               const jdb200_system* sys, void* ws, size_t ws_bytes);
+JDB200_API int jdb200_naive_compute_potential_energy(void* stream, const jdb200_params* p,
+                                          const jdb200_state* st, const jdb200_system* sys,
+                                          void* ws, size_t ws_bytes, void* energy);
+
+/* ---- ForceManager.apply (jaxdem/forces/force_manager.py:338-425) --------- */
+JDB200_API int jdb200_force_manager_apply(void* stream, const jdb200_params* p, const jdb200_state* st,
+                               const jdb200_system* sys, void* ws, size_t ws_bytes);
+
+/* ---- integrators ---------------------------------------------------------- */
+/* p->linear_integrator selects VelocityVerlet (velocity_verlet.py:57-61,92-95)
+ * or DirectEuler (direct_euler.py:62-66). */
+JDB200_API int jdb200_linear_step_before_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                    const jdb200_system* sys);
+JDB200_API int jdb200_linear_step_after_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                   const jdb200_system* sys);
+/* p->rotation_integrator selects VelocityVerletSpiral
+ * (velocity_verlet_spiral.py:83-116,156-180) or Spiral (spiral.py:104-141);
+ * both refresh st->pos_p_rot when q changes (State.__setattr__, state.py:264-273). */
+JDB200_API int jdb200_rotation_step_before_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                      const jdb200_system* sys);
+JDB200_API int jdb200_rotation_step_after_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                     const jdb200_system* sys);
+
+/* ---- domains --------------------------------------------------------------- */
+/* Domain.apply for p->domain: periodic = no-op (domains/__init__.py:156-189),
+ * reflect = ReflectDomain.apply (domains/reflect.py:99-299, _toc.py:11-94),
+ * free = FreeDomain.apply (domains/free.py:42-64; rewrites box_size/anchor). */
+JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const jdb200_state* st,
+                        const jdb200_system* sys, void* ws, size_t ws_bytes);
+
+/* ---- fused driver: n x _step_once (jaxdem/system.py:60-98) ---------------- */
+/* Runs domain.apply -> inv_box refresh -> linear/rotation before -> collider ->
+ * force manager -> linear/rotation after, `n_steps` times, all on `stream`, with
+ * no host round trip.  Identity user pre/post hooks only. */
+JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
+                       const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps);
+
+/* Number of kernels the library has launched since load (diagnostic counter for
+ * bench.py's `gpu_launches`; relaxed atomic, not part of the data path). */
+JDB200_API int64_t jdb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXDEM_B200_H */

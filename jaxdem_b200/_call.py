@@ -1,0 +1,120 @@
+"""Marshalling between the Python plugin objects and the C ABI structs."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_WORKSPACES: dict = {}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(state) -> None:
+    if state.pos_c.device.type != "cuda":
+        raise RuntimeError(
+            "jaxdem_b200 runs on CUDA devices only (sm_100a kernels, no CPU fallback): "
+            f"state is on {state.pos_c.device}."
+        )
+
+
+def params_for(state, system, *, max_neighbors: int = 0) -> L.Params:
+    col = system.collider
+    batched = state.pos_c.ndim == 3
+    p = L.Params()
+    p.batch = state.pos_c.shape[0] if batched else 1
+    p.n = state.N
+    p.dim = state.dim
+    p.dtype = L.JDB200_F32 if state.dtype == torch.float32 else L.JDB200_F64
+    p.domain = L.DOMAIN[system.domain.native_kind]
+    p.law = L.LAW[system.force_model.native_kind]
+    p.collider = L.COLLIDER.get(getattr(col, "native_kind", None), 0)
+    p.linear_integrator = L.LIN[system.linear_integrator.native_kind]
+    p.rotation_integrator = L.ROT[system.rotation_integrator.native_kind]
+    mask = getattr(col, "neighbor_mask", None)
+    p.stencil_m = 0 if mask is None else mask.shape[-2]
+    p.bond_width = state.bond_id.shape[-1]
+    p.n_materials = len(system.mat_table)
+    p.max_neighbors = int(max_neighbors)
+    p.grid_mode = L.GRID[getattr(col, "grid_mode", "auto")]
+    p.max_cells = int(getattr(col, "max_cells", 0) or 0)
+    p.clumps = 1 if state.has_clumps else 0
+    return p
+
+
+def workspace(p: L.Params, device) -> torch.Tensor:
+    nbytes = L.lib().jdb200_workspace_bytes(C.byref(p))
+    if nbytes == 0:
+        raise RuntimeError("jdb200_workspace_bytes rejected the parameters (JDB200_EINVAL)")
+    key = (str(device), nbytes)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        _WORKSPACES.clear()  # one live workspace per process is enough; sizes rarely change
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def state_view(state) -> L.StateView:
+    v = L.StateView()
+    for k in ("pos_c", "pos_p", "vel", "force", "ang_vel", "torque", "inertia", "rad", "mass",
+              "clump_id", "mat_id", "bond_id", "fixed"):
+        t = getattr(state, k)
+        if not t.is_contiguous():
+            raise RuntimeError(f"State.{k} must be contiguous")
+        setattr(v, k, t.data_ptr())
+    v.q_w = state.q.w.data_ptr()
+    v.q_xyz = state.q.xyz.data_ptr()
+    v.pos_p_rot = state._pos_p_rot.data_ptr()
+    return v
+
+
+def system_view(system) -> L.SystemView:
+    v = L.SystemView()
+    dom, fm, mt, col = system.domain, system.force_manager, system.mat_table, system.collider
+    v.dt = system.dt.data_ptr()
+    v.box_size = dom.box_size.data_ptr()
+    v.inv_box_size = dom.inv_box_size.data_ptr()
+    v.anchor = dom.anchor.data_ptr()
+    rc = getattr(dom, "restitution_coefficient", None)
+    v.restitution = None if rc is None else rc.data_ptr()
+    cs = getattr(col, "cell_size", None)
+    v.cell_size = None if cs is None else cs.data_ptr()
+    nm = getattr(col, "neighbor_mask", None)
+    v.neighbor_mask = None if nm is None else nm.data_ptr()
+    v.collider_overflow = col.overflow.data_ptr()
+    v.interact_same_bond_id = system.interact_same_bond_id.data_ptr()
+    v.gravity = fm.gravity.data_ptr()
+    v.external_force = fm.external_force.data_ptr()
+    v.external_force_com = fm.external_force_com.data_ptr()
+    v.external_torque = fm.external_torque.data_ptr()
+    v.mat_young = mt.young.data_ptr()
+    v.mat_poisson = mt.poisson.data_ptr()
+    v.mat_e = mt.e.data_ptr()
+    v.mat_mu = mt.mu.data_ptr()
+    v.mat_mu_r = mt.mu_r.data_ptr()
+    v.mat_young_eff = mt.young_eff.data_ptr()
+    return v
+
+
+def stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def call(name: str, state, system, *extra, needs_ws: bool = True, max_neighbors: int = 0):
+    """Invoke one C-ABI entry point on the current CUDA stream (asynchronous)."""
+    require_cuda(state)
+    lib = L.lib()
+    p = params_for(state, system, max_neighbors=max_neighbors)
+    sv, yv = state_view(state), system_view(system)
+    args = [stream_ptr(state.device), C.byref(p), C.byref(sv), C.byref(yv)]
+    if needs_ws:
+        ws = workspace(p, state.device)
+        args += [C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())]
+    args += [(_ptr(e) if isinstance(e, torch.Tensor) or e is None else e) for e in extra]
+    L.check(getattr(lib, name)(*args), name)

@@ -1,0 +1,98 @@
+"""ctypes binding of libjaxdem_b200.so (C ABI declared in include/jaxdem_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+returns an error code, a RuntimeError is raised.  Nothing under ``oracle/`` is
+ever imported from here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjaxdem_b200.so")
+
+JDB200_F32, JDB200_F64 = 0, 1
+DOMAIN = {"free": 0, "periodic": 1, "reflect": 2}
+LAW = {"spring": 0, "hertz": 1, "cundallstrack": 2}
+LIN = {"": 0, "verlet": 1, "euler": 2}
+ROT = {"": 0, "verletspiral": 1, "spiral": 2}
+COLLIDER = {"": 0, "celllist": 1, "naive": 2}
+GRID = {"auto": 0, "dense": 1, "sorted": 2}
+ERRORS = {-1: "JDB200_EINVAL (bad params)", -2: "JDB200_ENULL (NULL pointer)",
+          -3: "JDB200_EWORKSPACE (workspace too small)", -4: "JDB200_ECUDA (kernel launch failed)"}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int64), ("n", C.c_int64), ("max_cells", C.c_int64),
+        ("dim", C.c_int32), ("dtype", C.c_int32), ("domain", C.c_int32), ("law", C.c_int32),
+        ("collider", C.c_int32), ("linear_integrator", C.c_int32), ("rotation_integrator", C.c_int32),
+        ("stencil_m", C.c_int32), ("bond_width", C.c_int32), ("n_materials", C.c_int32),
+        ("max_neighbors", C.c_int32), ("grid_mode", C.c_int32), ("clumps", C.c_int32),
+    ]
+
+
+STATE_FIELDS = ("pos_c", "pos_p", "vel", "force", "q_w", "q_xyz", "ang_vel", "torque", "inertia",
+                "rad", "mass", "clump_id", "mat_id", "bond_id", "fixed", "pos_p_rot")
+SYSTEM_FIELDS = ("dt", "box_size", "inv_box_size", "anchor", "restitution", "cell_size",
+                 "neighbor_mask", "collider_overflow", "interact_same_bond_id", "gravity",
+                 "external_force", "external_force_com", "external_torque", "mat_young",
+                 "mat_poisson", "mat_e", "mat_mu", "mat_mu_r", "mat_young_eff")
+
+
+class StateView(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS]
+
+
+class SystemView(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in SYSTEM_FIELDS]
+
+
+_PP, _PS, _PY = C.POINTER(Params), C.POINTER(StateView), C.POINTER(SystemView)
+_V, _SZ = C.c_void_p, C.c_size_t
+
+# symbol -> (restype, argtypes); every symbol include/jaxdem_b200.h declares
+SYMBOLS = {
+    "jdb200_abi_version": (C.c_int, []),
+    "jdb200_launch_count": (C.c_int64, []),
+    "jdb200_workspace_bytes": (_SZ, [_PP]),
+    "jdb200_celllist_partition": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V, _V, _V, _V]),
+    "jdb200_celllist_compute_force": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_celllist_compute_potential_energy": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V]),
+    "jdb200_celllist_create_neighbor_list": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V, _V, _V]),
+    "jdb200_naive_compute_force": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_naive_compute_potential_energy": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V]),
+    "jdb200_force_manager_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_linear_step_before_force": (C.c_int, [_V, _PP, _PS, _PY]),
+    "jdb200_linear_step_after_force": (C.c_int, [_V, _PP, _PS, _PY]),
+    "jdb200_rotation_step_before_force": (C.c_int, [_V, _PP, _PS, _PY]),
+    "jdb200_rotation_step_after_force": (C.c_int, [_V, _PP, _PS, _PY]),
+    "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; loud failure if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C jaxdem_b200/csrc`.  jaxdem_b200 has no CPU fallback."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if a declared symbol is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {ERRORS.get(rc, rc)}")

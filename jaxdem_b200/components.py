@@ -1,0 +1,406 @@
+"""Plugin components mirroring JaxDEM's Factory roots for the step path:
+Domain, ForceModel, Collider, LinearIntegrator, RotationIntegrator, ForceManager.
+
+Every hook has the reference's name and argument meaning, ``(state, system) ->
+(state, system)``; the work is done by one C-ABI entry point of
+libjaxdem_b200.so on the current CUDA stream.  Buffers are updated IN PLACE and
+the same objects are returned (the reference returns fresh pytrees).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+
+from . import _call
+from .factory import Factory
+from .state import State, int_dtype_for
+
+
+def _leaf(x, dtype, device, batch, shape):
+    """System leaf as a dense tensor with an optional leading batch axis."""
+    t = torch.as_tensor(x, dtype=dtype).to(device)
+    full = (batch, *shape) if batch is not None else tuple(shape)
+    return t.expand(full).contiguous().clone()
+
+
+# ---------------------------------------------------------------------------
+# Domain (reference jaxdem/domains/__init__.py:26-215)
+# ---------------------------------------------------------------------------
+class Domain(Factory):
+    native_kind = "free"
+
+    def __init__(self, box_size, inv_box_size, anchor, **kw: Any):
+        self.box_size, self.inv_box_size, self.anchor = box_size, inv_box_size, anchor
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def periodic(self) -> bool:
+        return False
+
+    @classmethod
+    def Create(cls, dim: int, box_size=None, anchor=None, *, dtype=torch.float32, device="cpu",
+               batch=None, **kw: Any):
+        box = torch.ones(dim) if box_size is None else torch.as_tensor(box_size, dtype=torch.float64)
+        if box.shape[-1:] != (dim,):
+            raise ValueError(f"box_size must have shape ({dim},), got shape {tuple(box.shape)}.")
+        anc = torch.zeros(dim) if anchor is None else torch.as_tensor(anchor, dtype=torch.float64)
+        if anc.shape[-1:] != (dim,):
+            raise ValueError(f"anchor must have shape ({dim},), got shape {tuple(anc.shape)}.")
+        box = _leaf(box, dtype, device, batch, (dim,))
+        anc = _leaf(anc, dtype, device, batch, (dim,))
+        extra = {k: _leaf(v, dtype, device, batch, ()) for k, v in kw.items()}
+        return cls(box_size=box, inv_box_size=1.0 / box, anchor=anc, **extra)
+
+    @staticmethod
+    def displacement(ri, rj, system):
+        return ri - rj
+
+    @staticmethod
+    def apply(state: State, system: "Any"):
+        """Domain.apply -> jdb200_domain_apply (free: bbox; reflect: impulses; periodic: no-op)."""
+        if system.domain.native_kind != "periodic":
+            _call.call("jdb200_domain_apply", state, system)
+        return state, system
+
+    @staticmethod
+    def shift(state: State, system: "Any"):
+        return state, system
+
+
+@Domain.register("free")
+class FreeDomain(Domain):
+    """reference jaxdem/domains/free.py:42-64."""
+    native_kind = "free"
+
+
+@Domain.register("periodic")
+class PeriodicDomain(Domain):
+    """reference jaxdem/domains/periodic.py:31-116."""
+    native_kind = "periodic"
+
+    @property
+    def periodic(self) -> bool:
+        return True
+
+    @staticmethod
+    def displacement(ri, rj, system):
+        rij = ri - rj
+        return rij - system.domain.box_size * torch.round(rij / system.domain.box_size)
+
+    @staticmethod
+    def shift(state, system):
+        """Wrap pos_c into the primary box (periodic.py:84-116); writer-side, not on the step path."""
+        box, anc = system.domain.box_size[..., None, :], system.domain.anchor[..., None, :]
+        state.pos_c -= box * torch.floor((state.pos_c - anc) / box)
+        return state, system
+
+
+@Domain.register("reflect")
+class ReflectDomain(Domain):
+    """reference jaxdem/domains/reflect.py:99-299."""
+    native_kind = "reflect"
+
+    @classmethod
+    def Create(cls, dim, box_size=None, anchor=None, restitution_coefficient=1.0, **kw):
+        return super().Create(dim, box_size=box_size, anchor=anchor,
+                              restitution_coefficient=restitution_coefficient, **kw)
+
+
+# ---------------------------------------------------------------------------
+# ForceModel (reference jaxdem/forces/__init__.py:55-150): the law is selected by
+# name; its arithmetic lives in csrc/laws.cuh.
+# ---------------------------------------------------------------------------
+class ForceModel(Factory):
+    native_kind = "spring"
+    required_material_properties: tuple = ()
+    requires_history = False
+
+
+@ForceModel.register("spring")
+class SpringForce(ForceModel):
+    """reference jaxdem/forces/spring.py:69-147."""
+    native_kind = "spring"
+    required_material_properties = ("young_eff",)
+
+
+@ForceModel.register("hertz")
+class HertzianForce(ForceModel):
+    """reference jaxdem/forces/hertz.py:69-162."""
+    native_kind = "hertz"
+    required_material_properties = ("young", "poisson")
+
+
+@ForceModel.register("cundallstrack")
+class CundallStrackForce(ForceModel):
+    """reference jaxdem/forces/cundall_strack.py:99-235."""
+    native_kind = "cundallstrack"
+    required_material_properties = ("young", "poisson", "e", "mu", "mu_r")
+
+
+# ---------------------------------------------------------------------------
+# Collider (reference jaxdem/colliders/__init__.py:22-222)
+# ---------------------------------------------------------------------------
+class Collider(Factory):
+    native_kind = ""
+
+    def __init__(self, overflow=None):
+        self.overflow = overflow
+
+    def _bind(self, dtype, device, batch):
+        """Allocate device leaves once the owning System knows dtype/device/batch."""
+        shape = (batch,) if batch is not None else ()
+        self.overflow = torch.zeros(shape, dtype=torch.bool, device=device)
+        return self
+
+    @staticmethod
+    def compute_force(state, system):
+        """No-op collider "": zero force and torque (colliders/__init__.py:56-88)."""
+        state.force.zero_()
+        state.torque.zero_()
+        return state, system
+
+    @staticmethod
+    def compute_potential_energy(state, system):
+        shape = state.pos_c.shape[:-2]
+        return state, system, torch.zeros(shape, dtype=state.dtype, device=state.device)
+
+
+Collider.register("")(Collider)
+
+
+@Collider.register("naive")
+class NaiveSimulator(Collider):
+    """O(N^2) collider, the reference's default (jaxdem/colliders/naive.py:73-235)."""
+    native_kind = "naive"
+
+    @staticmethod
+    def compute_force(state, system):
+        _call.call("jdb200_naive_compute_force", state, system)
+        return state, system
+
+    @staticmethod
+    def compute_potential_energy(state, system):
+        e = torch.empty(state.pos_c.shape[:-2], dtype=state.dtype, device=state.device)
+        _call.call("jdb200_naive_compute_potential_energy", state, system, e)
+        return state, system, e
+
+
+@Collider.register("CellList")
+class DynamicCellList(Collider):
+    """Cell-list collider (reference jaxdem/colliders/cell_list.py:264-595).
+
+    Extra static knobs of this implementation: ``max_cells`` (capacity of the dense
+    cell table per system, default 4 N + 1024) and ``grid_mode`` ("auto" | "dense" |
+    "sorted", see include/jaxdem_b200.h)."""
+    native_kind = "celllist"
+
+    def __init__(self, neighbor_mask, cell_size, max_cells=None, grid_mode="auto", overflow=None):
+        super().__init__(overflow)
+        self.neighbor_mask, self.cell_size = neighbor_mask, cell_size
+        self.max_cells, self.grid_mode = max_cells, grid_mode
+
+    @classmethod
+    def Create(cls, state: State, cell_size=None, search_range=None, box_size=None, max_cells=None,
+               grid_mode="auto"):
+        """DynamicCellList.Create (cell_list.py:374-432); host-side, once."""
+        F = state.dtype
+        rad = state._rad.detach().cpu().to(F)
+        min_rad, max_rad = rad.min(), rad.max()
+        alpha = max_rad / min_rad
+        if cell_size is None:
+            cell_size = 2.0 * max_rad if bool(alpha < 2.5) else 0.5 * max_rad
+        cell_size = torch.as_tensor(cell_size, dtype=F)
+        if box_size is not None:
+            box = torch.as_tensor(box_size, dtype=F)
+            for _ in range(2):
+                sr = max(1, int(torch.ceil(2 * max_rad / cell_size))) if search_range is None else int(search_range)
+                gd = torch.clamp(torch.floor(box / cell_size).to(torch.int64), min=2 * sr + 1)
+                cell_size = torch.min(box / gd.to(F))
+        if search_range is None:
+            search_range = max(1, int(torch.ceil(2 * max_rad / cell_size)))
+        r = torch.arange(-int(search_range), int(search_range) + 1)
+        mesh = torch.meshgrid(*([r] * state.dim), indexing="ij")
+        mask = torch.stack([m.reshape(-1) for m in mesh], dim=1).to(int_dtype_for(F))
+        if max_cells is None:
+            max_cells = 4 * state.N + 1024
+        return cls(neighbor_mask=mask, cell_size=cell_size, max_cells=int(max_cells), grid_mode=grid_mode)
+
+    def _bind(self, dtype, device, batch):
+        super()._bind(dtype, device, batch)
+        I = int_dtype_for(dtype)
+        self.cell_size = _leaf(self.cell_size, dtype, device, batch, ())
+        m = torch.as_tensor(self.neighbor_mask)
+        self.neighbor_mask = _leaf(m, I, device, batch, tuple(m.shape[-2:]))
+        return self
+
+    @staticmethod
+    def compute_force(state, system):
+        """-> jdb200_celllist_compute_force (cell_list.py:434-464)."""
+        _call.call("jdb200_celllist_compute_force", state, system)
+        return state, system
+
+    @staticmethod
+    def compute_potential_energy(state, system):
+        """-> jdb200_celllist_compute_potential_energy (cell_list.py:466-496)."""
+        e = torch.empty(state.pos_c.shape[:-2], dtype=state.dtype, device=state.device)
+        _call.call("jdb200_celllist_compute_potential_energy", state, system, e)
+        return state, system, e
+
+    @staticmethod
+    def create_neighbor_list(state, system, cutoff, max_neighbors: int):
+        """-> jdb200_celllist_create_neighbor_list (cell_list.py:498-595).
+        Returns (state, system, (.., N, K) int list padded with -1, overflow flag)."""
+        lead = state.pos_c.shape[:-2]
+        I = int_dtype_for(state.dtype)
+        nl = torch.empty((*lead, state.N, max_neighbors), dtype=I, device=state.device)
+        ovf = torch.zeros(lead, dtype=torch.bool, device=state.device)
+        cut = torch.as_tensor(cutoff, dtype=state.dtype).to(state.device).expand(lead).contiguous()
+        if max_neighbors > 0 and state.N > 0:
+            _call.call("jdb200_celllist_create_neighbor_list", state, system, cut, nl, ovf,
+                       max_neighbors=max_neighbors)
+        return state, system, nl, ovf
+
+    @staticmethod
+    def partition(state, system):
+        """Cell permutation, sorted hashes, de-duplicated neighbour-cell hashes and the
+        strategy used (-> jdb200_celllist_partition; _get_spatial_partition,
+        cell_list.py:35-96)."""
+        lead = state.pos_c.shape[:-2]
+        I = int_dtype_for(state.dtype)
+        M = system.collider.neighbor_mask.shape[-2]
+        perm = torch.empty((*lead, state.N), dtype=I, device=state.device)
+        sh = torch.empty_like(perm)
+        nh = torch.empty((*lead, state.N, M), dtype=I, device=state.device)
+        dense = torch.zeros(lead, dtype=torch.bool, device=state.device)
+        _call.call("jdb200_celllist_partition", state, system, perm, sh, nh, dense)
+        return perm, sh, nh, dense
+
+
+Collider.register("b200celllist")(DynamicCellList)
+
+
+# ---------------------------------------------------------------------------
+# Integrators (reference jaxdem/integrators/__init__.py:21-149)
+# ---------------------------------------------------------------------------
+class Integrator(Factory):
+    native_kind = ""
+
+    @staticmethod
+    def step_before_force(state, system):
+        return state, system
+
+    @staticmethod
+    def step_after_force(state, system):
+        return state, system
+
+    @staticmethod
+    def initialize(state, system):
+        return state, system
+
+
+class LinearIntegrator(Integrator):
+    _registry: dict = {}
+
+    @staticmethod
+    def step_before_force(state, system):
+        if system.linear_integrator.native_kind:
+            _call.call("jdb200_linear_step_before_force", state, system, needs_ws=False)
+        return state, system
+
+    @staticmethod
+    def step_after_force(state, system):
+        if system.linear_integrator.native_kind:
+            _call.call("jdb200_linear_step_after_force", state, system, needs_ws=False)
+        return state, system
+
+
+class RotationIntegrator(Integrator):
+    _registry: dict = {}
+
+    @staticmethod
+    def step_before_force(state, system):
+        if system.rotation_integrator.native_kind:
+            _call.call("jdb200_rotation_step_before_force", state, system, needs_ws=False)
+        return state, system
+
+    @staticmethod
+    def step_after_force(state, system):
+        if system.rotation_integrator.native_kind:
+            _call.call("jdb200_rotation_step_after_force", state, system, needs_ws=False)
+        return state, system
+
+
+LinearIntegrator.register("")(LinearIntegrator)
+RotationIntegrator.register("")(RotationIntegrator)
+
+
+@LinearIntegrator.register("verlet")
+class VelocityVerlet(LinearIntegrator):
+    """reference jaxdem/integrators/velocity_verlet.py:57-95."""
+    native_kind = "verlet"
+
+
+@LinearIntegrator.register("euler")
+class DirectEuler(LinearIntegrator):
+    """reference jaxdem/integrators/direct_euler.py:62-66."""
+    native_kind = "euler"
+
+
+@RotationIntegrator.register("verletspiral")
+class VelocityVerletSpiral(RotationIntegrator):
+    """reference jaxdem/integrators/velocity_verlet_spiral.py:83-180."""
+    native_kind = "verletspiral"
+
+
+@RotationIntegrator.register("spiral")
+class Spiral(RotationIntegrator):
+    """reference jaxdem/integrators/spiral.py:104-141."""
+    native_kind = "spiral"
+
+
+for _k, _c in (("b200verlet", VelocityVerlet), ("b200euler", DirectEuler)):
+    LinearIntegrator.register(_k)(_c)
+for _k, _c in (("b200verletspiral", VelocityVerletSpiral), ("b200spiral", Spiral)):
+    RotationIntegrator.register(_k)(_c)
+
+
+# ---------------------------------------------------------------------------
+# ForceManager (reference jaxdem/forces/force_manager.py:31-479; not a Factory)
+# ---------------------------------------------------------------------------
+class ForceManager:
+    def __init__(self, gravity, external_force, external_force_com, external_torque):
+        self.gravity = gravity
+        self.external_force = external_force
+        self.external_force_com = external_force_com
+        self.external_torque = external_torque
+
+    @staticmethod
+    def create(state_shape, *, gravity=None, dtype=torch.float32, device="cpu") -> "ForceManager":
+        dim = state_shape[-1]
+        A = 1 if dim == 2 else 3
+        batch = state_shape[0] if len(state_shape) == 3 else None
+        g = torch.zeros(dim) if gravity is None else gravity
+        z = lambda *s: torch.zeros(s, dtype=dtype, device=device)
+        return ForceManager(_leaf(g, dtype, device, batch, (dim,)), z(*state_shape), z(*state_shape),
+                            z(*state_shape[:-1], A))
+
+    @staticmethod
+    def add_force(state, system, force, *, is_com=False):
+        fm = system.force_manager
+        (fm.external_force_com if is_com else fm.external_force).add_(force)
+        return system
+
+    @staticmethod
+    def add_torque(state, system, torque):
+        system.force_manager.external_torque.add_(torque)
+        return system
+
+    @staticmethod
+    def apply(state, system):
+        """-> jdb200_force_manager_apply (force_manager.py:338-425)."""
+        _call.call("jdb200_force_manager_apply", state, system)
+        return state, system

@@ -1,0 +1,243 @@
+// jaxdem_b200 — extern "C" entry points (include/jaxdem_b200.h) and the fused
+// n-step driver replacing _step_once / System.step (jaxdem/system.py:60-98,701-748).
+#include "ctx.cuh"
+#include "launch.cuh"
+
+namespace jdb {
+
+std::atomic<unsigned long long> g_launches{0};
+
+template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*);
+template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, bool);
+template <typename F> int celllist_energy(cudaStream_t, Ctx<F>&, F*);
+template <typename F> int celllist_neighbor_list(cudaStream_t, Ctx<F>&, const F*, typename RT<F>::I*, uint8_t*);
+template <typename F> int naive_force(cudaStream_t, Ctx<F>&);
+template <typename F> int naive_energy(cudaStream_t, Ctx<F>&, F*);
+template <typename F> int force_manager_apply(cudaStream_t, Ctx<F>&);
+template <typename F> int domain_apply(cudaStream_t, Ctx<F>&);
+template <typename F> int refresh_inv_box(cudaStream_t, Ctx<F>&);
+template <typename F> int linear_before(cudaStream_t, Ctx<F>&);
+template <typename F> int linear_after(cudaStream_t, Ctx<F>&);
+template <typename F> int rotation_before(cudaStream_t, Ctx<F>&);
+template <typename F> int rotation_after(cudaStream_t, Ctx<F>&);
+
+// ---- partition outputs for parity checks -------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_export_partition(Ctx<F> c, typename RT<F>::I* perm,
+                                                           typename RT<F>::I* sorted_hash,
+                                                           typename RT<F>::I* nbr_hash, uint8_t* used_dense) {
+  using I = typename RT<F>::I;
+  const int b = blockIdx.y;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n) return;
+  const size_t off = (size_t)b * c.n;
+  const GridInfo<I> g = c.gi[b];
+  if (perm) perm[off + k] = (I)c.perm[off + k];
+  if (sorted_hash) sorted_hash[off + k] = c.skey[off + k];
+  if (k == 0 && used_dense) used_dense[b] = (uint8_t)(g.dense && !g.dense_fail);
+  if (nbr_hash) {
+    // row k here is ORIGINAL particle k (the reference builds the table from unsorted coords)
+    const F* pc = c.pos_c + (off + k) * c.dim;
+    const F* pr = c.pos_p_rot + (off + k) * c.dim;
+    I cc[3] = {0, 0, 0};
+    for (int d = 0; d < c.dim; ++d)
+      cc[d] = cell_coord<F, I>(RT<F>::add(pc[d], pr[d]), c.anchor[b * c.dim + d], c.box[b * c.dim + d],
+                               c.cell_size[b], g.gd[d], c.periodic);
+    const I* mask = c.mask + (size_t)b * c.M * c.dim;
+    I* row = nbr_hash + (off + k) * c.M;
+    for (int m = 0; m < c.M; ++m) {
+      I h = neighbor_hash<F, I>(cc, mask + m * c.dim, g.gd, g.stride, c.dim, c.periodic);
+      if (c.periodic)  // _dedup_stencil_hashes: later duplicates -> -1
+        for (int m2 = 0; m2 < m; ++m2)
+          if (neighbor_hash<F, I>(cc, mask + m2 * c.dim, g.gd, g.stride, c.dim, c.periodic) == h) {
+            h = I(-1);
+            break;
+          }
+      row[m] = h;
+    }
+  }
+}
+
+template <typename F>
+int partition_entry(cudaStream_t s, Ctx<F>& c, void* perm, void* sorted_hash, void* nbr_hash,
+                    void* used_dense) {
+  using I = typename RT<F>::I;
+  int rc = build_partition<F>(s, c, nullptr);
+  if (rc || c.n == 0) return rc;
+  JDB_LAUNCH(k_export_partition<F>, dim3(cdiv(c.n, 256), c.batch), 256, s, c, (I*)perm, (I*)sorted_hash,
+             (I*)nbr_hash, (uint8_t*)used_dense);
+  return 0;
+}
+
+template <typename F>
+int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
+  if (collider == JDB200_COLLIDER_CELLLIST) return celllist_force<F>(s, c, true);
+  if (collider == JDB200_COLLIDER_NAIVE) return naive_force<F>(s, c);
+  // "" no-op collider zeroes force and torque (colliders/__init__.py:56-88)
+  if (c.n == 0) return 0;
+  if (cudaMemsetAsync(c.force, 0, sizeof(F) * c.batch * c.n * c.dim, s) != cudaSuccess) return JDB200_ECUDA;
+  if (cudaMemsetAsync(c.torque, 0, sizeof(F) * c.batch * c.n * c.A, s) != cudaSuccess) return JDB200_ECUDA;
+  return 0;
+}
+
+// _step_once (system.py:60-82), identity user hooks.  time/step_count are host-side
+// bookkeeping of the caller.
+template <typename F>
+int system_step(cudaStream_t s, Ctx<F>& c, int collider, long long n_steps) {
+  int rc = 0;
+  if (c.domain != JDB200_DOMAIN_FREE && n_steps > 0) rc = refresh_inv_box<F>(s, c);  // box is constant
+  for (long long it = 0; it < n_steps && !rc; ++it) {
+    if ((rc = domain_apply<F>(s, c))) break;  // free: also refreshes inv_box_size
+    if ((rc = linear_before<F>(s, c))) break;
+    if ((rc = rotation_before<F>(s, c))) break;
+    if ((rc = collider_force<F>(s, c, collider))) break;
+    if ((rc = force_manager_apply<F>(s, c))) break;
+    if ((rc = linear_after<F>(s, c))) break;
+    if ((rc = rotation_after<F>(s, c))) break;
+  }
+  return rc;
+}
+
+}  // namespace jdb
+
+using namespace jdb;
+
+#define JDB_ENTER(NEED_WS)                                               \
+  int rc_ = check_params(p);                                             \
+  if (rc_) return rc_;                                                   \
+  if (!st || !sys) return JDB200_ENULL;                                  \
+  if (NEED_WS) {                                                         \
+    if (!ws) return JDB200_ENULL;                                        \
+    if (ws_bytes < jdb200_workspace_bytes(p)) return JDB200_EWORKSPACE;  \
+  }                                                                      \
+  cudaStream_t s = (cudaStream_t)stream;
+
+#define JDB_DISPATCH(EXPR)                         \
+  if (p->dtype == JDB200_F32) {                    \
+    using F = float;                               \
+    Ctx<F> c;                                      \
+    make_ctx<F>(c, p, st, sys, ws);                \
+    return EXPR;                                   \
+  } else {                                         \
+    using F = double;                              \
+    Ctx<F> c;                                      \
+    make_ctx<F>(c, p, st, sys, ws);                \
+    return EXPR;                                   \
+  }
+
+extern "C" {
+
+JDB200_API int jdb200_abi_version(void) { return JDB200_ABI_VERSION; }
+
+JDB200_API int64_t jdb200_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+JDB200_API size_t jdb200_workspace_bytes(const jdb200_params* p) {
+  if (check_params(p)) return 0;
+  if (p->dtype == JDB200_F32) {
+    Ctx<float> c;
+    make_ctx<float>(c, p, nullptr, nullptr, nullptr);
+    return carve(c, nullptr);
+  }
+  Ctx<double> c;
+  make_ctx<double>(c, p, nullptr, nullptr, nullptr);
+  return carve(c, nullptr);
+}
+
+JDB200_API int jdb200_celllist_partition(void* stream, const jdb200_params* p, const jdb200_state* st,
+                              const jdb200_system* sys, void* ws, size_t ws_bytes, void* perm,
+                              void* sorted_hash, void* nbr_hash, void* used_dense) {
+  JDB_ENTER(true)
+  JDB_DISPATCH(partition_entry<F>(s, c, perm, sorted_hash, nbr_hash, used_dense))
+}
+
+JDB200_API int jdb200_celllist_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                  const jdb200_system* sys, void* ws, size_t ws_bytes) {
+  JDB_ENTER(true)
+  JDB_DISPATCH(celllist_force<F>(s, c, true))
+}
+
+JDB200_API int jdb200_celllist_compute_potential_energy(void* stream, const jdb200_params* p,
+                                             const jdb200_state* st, const jdb200_system* sys,
+                                             void* ws, size_t ws_bytes, void* energy) {
+  JDB_ENTER(true)
+  if (!energy) return JDB200_ENULL;
+  JDB_DISPATCH(celllist_energy<F>(s, c, (F*)energy))
+}
+
+JDB200_API int jdb200_celllist_create_neighbor_list(void* stream, const jdb200_params* p,
+                                         const jdb200_state* st, const jdb200_system* sys,
+                                         void* ws, size_t ws_bytes, const void* cutoff,
+                                         void* neighbor_list, void* overflow) {
+  JDB_ENTER(true)
+  if (!cutoff || !overflow || (!neighbor_list && p->max_neighbors > 0 && p->n > 0)) return JDB200_ENULL;
+  JDB_DISPATCH(celllist_neighbor_list<F>(s, c, (const F*)cutoff, (RT<F>::I*)neighbor_list,
+                                         (uint8_t*)overflow))
+}
+
+JDB200_API int jdb200_naive_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                               const jdb200_system* sys, void* ws, size_t ws_bytes) {
+  JDB_ENTER(true)
+  JDB_DISPATCH(naive_force<F>(s, c))
+}
+
+JDB200_API int jdb200_naive_compute_potential_energy(void* stream, const jdb200_params* p,
+                                          const jdb200_state* st, const jdb200_system* sys,
+                                          void* ws, size_t ws_bytes, void* energy) {
+  JDB_ENTER(true)
+  if (!energy) return JDB200_ENULL;
+  JDB_DISPATCH(naive_energy<F>(s, c, (F*)energy))
+}
+
+JDB200_API int jdb200_force_manager_apply(void* stream, const jdb200_params* p, const jdb200_state* st,
+                               const jdb200_system* sys, void* ws, size_t ws_bytes) {
+  JDB_ENTER(true)
+  JDB_DISPATCH(force_manager_apply<F>(s, c))
+}
+
+JDB200_API int jdb200_linear_step_before_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                    const jdb200_system* sys) {
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  JDB_ENTER(false)
+  (void)ws_bytes;
+  JDB_DISPATCH(linear_before<F>(s, c))
+}
+JDB200_API int jdb200_linear_step_after_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                   const jdb200_system* sys) {
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  JDB_ENTER(false)
+  (void)ws_bytes;
+  JDB_DISPATCH(linear_after<F>(s, c))
+}
+JDB200_API int jdb200_rotation_step_before_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                      const jdb200_system* sys) {
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  JDB_ENTER(false)
+  (void)ws_bytes;
+  JDB_DISPATCH(rotation_before<F>(s, c))
+}
+JDB200_API int jdb200_rotation_step_after_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                     const jdb200_system* sys) {
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  JDB_ENTER(false)
+  (void)ws_bytes;
+  JDB_DISPATCH(rotation_after<F>(s, c))
+}
+
+JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const jdb200_state* st,
+                        const jdb200_system* sys, void* ws, size_t ws_bytes) {
+  JDB_ENTER(true)
+  JDB_DISPATCH(domain_apply<F>(s, c))
+}
+
+JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
+                       const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps) {
+  JDB_ENTER(true)
+  if (n_steps < 0) return JDB200_EINVAL;
+  JDB_DISPATCH(system_step<F>(s, c, p->collider, (long long)n_steps))
+}
+
+}  // extern "C"

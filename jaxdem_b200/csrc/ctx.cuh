@@ -1,0 +1,146 @@
+// jaxdem_b200 — kernel argument bundle built from the C-ABI structs.
+#pragma once
+#include "common.cuh"
+
+namespace jdb {
+
+template <typename F>
+struct Ctx {
+  using I = typename RT<F>::I;
+  // static
+  long long n;
+  long long max_cells;
+  int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
+  // state (in place)
+  F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;
+  I *clump_id, *mat_id, *bond_id;
+  uint8_t* fixed;
+  // system
+  F *dt, *box, *inv_box, *anchor, *restitution, *cell_size, *gravity;
+  F *ext_force, *ext_force_com, *ext_torque;
+  F *young, *poisson, *e, *mu, *mu_r, *young_eff;
+  I* mask;
+  uint8_t *overflow, *interact;
+  // workspace
+  GridInfo<I>* gi;            // [B]
+  I *key, *key_b, *key_c;      // [B*N] unsorted hashes + radix ping-pong
+  I* skey;                     // [B*N] sorted hashes
+  int *perm, *perm_b, *perm_c; // [B*N] final perm + scratch
+  int* rank;                   // [B*N] arrival rank inside the cell (dense)
+  int* cell_start;             // [B*(max_cells+1)] counts -> exclusive starts (dense)
+  unsigned long long* tile_state;  // [B*scan_tiles] decoupled look-back descriptors
+  int* tile_counter;           // [B]
+  int* radix_counts;           // [B*256*radix_blocks]
+  int* radix_skip;             // [B]
+  Vec4<F>* spos;               // [B*N] sorted (x, y, z, rad)
+  Vec4<F>* svel;               // [B*N] sorted (vx, vy, vz, mass)       (cundallstrack)
+  Vec4<F>* sang;               // [B*N] sorted (wx, wy, wz, 0)          (cundallstrack)
+  int* sclump;                 // [B*N] sorted clump id | has_bond << 31
+  int* smat;                   // [B*N] sorted material id
+  F* partial;                  // [B*reduce_blocks] reduction partials
+  int* seg;                    // [B*N] clump arrival ranks (force manager / reflect)
+  F *segf, *segf2;             // [B*N*8] per-sphere scratch of the clump reductions
+  int* cell_start_clump;       // [B*(N+1)] clump CSR starts
+  unsigned long long* tile_state_clump;  // [B*tiles(N+1)]
+  int* tile_counter_clump;     // [B]
+  int scan_tiles, radix_blocks, reduce_blocks;
+};
+
+constexpr int kScanTile = 4096;    // cells per look-back tile (512 threads x 8)
+constexpr int kRadixTile = 2048;   // keys per radix block (256 threads x 8)
+constexpr int kReduceBlock = 256;
+
+template <typename F>
+inline size_t carve(Ctx<F>& c, void* ws) {
+  using I = typename RT<F>::I;
+  Bump b(ws);
+  const size_t B = (size_t)c.batch, N = (size_t)c.n, BN = B * N;
+  c.scan_tiles = cdiv(c.max_cells + 1, kScanTile);
+  c.radix_blocks = cdiv(c.n, kRadixTile);
+  c.reduce_blocks = cdiv(c.n, kReduceBlock);
+  c.gi = b.take<GridInfo<I>>(B);
+  c.key = b.take<I>(BN);
+  c.key_b = b.take<I>(BN);
+  c.key_c = b.take<I>(BN);
+  c.skey = b.take<I>(BN);
+  c.perm = b.take<int>(BN);
+  c.perm_b = b.take<int>(BN);
+  c.perm_c = b.take<int>(BN);
+  c.rank = b.take<int>(BN);
+  c.cell_start = b.take<int>(B * (size_t)(c.max_cells + 1));
+  c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);
+  c.tile_counter = b.take<int>(B);
+  c.radix_counts = b.take<int>(B * 256 * (size_t)c.radix_blocks);
+  c.radix_skip = b.take<int>(B);
+  c.spos = b.take<Vec4<F>>(BN);
+  c.svel = b.take<Vec4<F>>(BN);
+  c.sang = b.take<Vec4<F>>(BN);
+  c.sclump = b.take<int>(BN);
+  c.smat = b.take<int>(BN);
+  c.partial = b.take<F>(B * (size_t)c.reduce_blocks);
+  c.seg = b.take<int>(BN);
+  c.segf = b.take<F>(BN * 8 + 64);
+  c.segf2 = b.take<F>(BN * 8 + 64);
+  c.cell_start_clump = b.take<int>(B * (N + 1));
+  c.tile_state_clump = b.take<unsigned long long>(B * (size_t)cdiv(c.n + 1, kScanTile));
+  c.tile_counter_clump = b.take<int>(B);
+  return b.off + 256;
+}
+
+template <typename F>
+inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
+                    const jdb200_system* sys, void* ws) {
+  using I = typename RT<F>::I;
+  c = Ctx<F>{};
+  c.n = p->n;
+  c.max_cells = p->grid_mode == JDB200_GRID_SORTED ? 0 : p->max_cells;
+  c.batch = (int)p->batch;
+  c.dim = p->dim;
+  c.A = p->dim == 2 ? 1 : 3;
+  c.domain = p->domain;
+  c.periodic = p->domain == JDB200_DOMAIN_PERIODIC;
+  c.law = p->law;
+  c.M = p->stencil_m;
+  c.W = p->bond_width;
+  c.nmat = p->n_materials;
+  c.K = p->max_neighbors;
+  c.grid_mode = p->grid_mode;
+  c.clumps = p->clumps;
+  c.lin = p->linear_integrator;
+  c.rot = p->rotation_integrator;
+  if (st) {
+    c.pos_c = (F*)st->pos_c; c.pos_p = (F*)st->pos_p; c.vel = (F*)st->vel; c.force = (F*)st->force;
+    c.q_w = (F*)st->q_w; c.q_xyz = (F*)st->q_xyz; c.ang_vel = (F*)st->ang_vel;
+    c.torque = (F*)st->torque; c.inertia = (F*)st->inertia; c.rad = (F*)st->rad;
+    c.mass = (F*)st->mass; c.pos_p_rot = (F*)st->pos_p_rot;
+    c.clump_id = (I*)st->clump_id; c.mat_id = (I*)st->mat_id; c.bond_id = (I*)st->bond_id;
+    c.fixed = (uint8_t*)st->fixed;
+  }
+  if (sys) {
+    c.dt = (F*)sys->dt; c.box = (F*)sys->box_size; c.inv_box = (F*)sys->inv_box_size;
+    c.anchor = (F*)sys->anchor; c.restitution = (F*)sys->restitution;
+    c.cell_size = (F*)sys->cell_size; c.gravity = (F*)sys->gravity;
+    c.ext_force = (F*)sys->external_force; c.ext_force_com = (F*)sys->external_force_com;
+    c.ext_torque = (F*)sys->external_torque;
+    c.young = (F*)sys->mat_young; c.poisson = (F*)sys->mat_poisson; c.e = (F*)sys->mat_e;
+    c.mu = (F*)sys->mat_mu; c.mu_r = (F*)sys->mat_mu_r; c.young_eff = (F*)sys->mat_young_eff;
+    c.mask = (I*)sys->neighbor_mask;
+    c.overflow = (uint8_t*)sys->collider_overflow; c.interact = (uint8_t*)sys->interact_same_bond_id;
+  }
+  carve(c, ws);
+  return 0;
+}
+
+inline int check_params(const jdb200_params* p) {
+  if (!p) return JDB200_ENULL;
+  if (p->dim != 2 && p->dim != 3) return JDB200_EINVAL;
+  if (p->dtype != JDB200_F32 && p->dtype != JDB200_F64) return JDB200_EINVAL;
+  if (p->batch < 1 || p->n < 0 || p->n > 0x7fffffffLL) return JDB200_EINVAL;
+  if (p->domain < 0 || p->domain > 2 || p->law < 0 || p->law > 2) return JDB200_EINVAL;
+  if (p->grid_mode < 0 || p->grid_mode > 2 || p->max_cells < 0) return JDB200_EINVAL;
+  if (p->bond_width < 0 || p->n_materials < 0 || p->stencil_m < 0 || p->max_neighbors < 0)
+    return JDB200_EINVAL;
+  return 0;
+}
+
+}  // namespace jdb

@@ -1,0 +1,909 @@
+// jaxdem_b200 — streaming kernels of the step: linear / rotation integrators (K8, K9),
+// ForceManager.apply (K7), domain apply (K10 reflect, K11 free).
+//
+// All arithmetic that the numpy/JAX expressions perform as separate roundings is
+// written with non-contracting intrinsics (RT<F>::add/mul/...) so the kernels agree
+// with the reference expressions op for op; these kernels are HBM-bound, the extra
+// instructions are free.
+#include "ctx.cuh"
+#include "launch.cuh"
+#include "scan.cuh"
+
+namespace jdb {
+
+template <typename F>
+using T_ = RT<F>;
+
+// ---------------------------------------------------------------------------
+// K8  linear integrators
+// ---------------------------------------------------------------------------
+// VelocityVerlet.step_before_force (velocity_verlet.py:57-61) [kick + drift],
+// VelocityVerlet.step_after_force (:92-95) [kick], DirectEuler.step_after_force
+// (direct_euler.py:62-66) [full kick + drift].
+template <typename F, bool HALF, bool DRIFT>
+__global__ void __launch_bounds__(256) k_linear(Ctx<F> c) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // element of (N, D)
+  const long long total = c.n * c.dim;
+  if (e >= total) return;
+  const long long i = e / c.dim;
+  const size_t gi = (size_t)b * c.n + i, ge = (size_t)b * total + e;
+  const F dt = c.dt[b];
+  const F h = HALF ? T::mul(dt, F(0.5)) : dt;
+  const F s = T::div(h, c.mass[gi]);  // (dt * 0.5 / mass)
+  const F free = c.fixed[gi] ? F(0) : F(1);
+  const F v = T::add(c.vel[ge], T::mul(T::mul(c.force[ge], s), free));
+  c.vel[ge] = v;
+  if (DRIFT) c.pos_c[ge] = T::add(c.pos_c[ge], T::mul(dt, v));
+}
+
+// ---------------------------------------------------------------------------
+// K9  rotation integrators (SPIRAL)
+// ---------------------------------------------------------------------------
+template <typename F>
+struct Q4 {
+  F w, x, y, z;
+};
+
+template <typename F>
+__device__ __forceinline__ V3<F> xcross(const V3<F>& a, const V3<F>& b) {  // unfused cross
+  using T = RT<F>;
+  return {T::sub(T::mul(a.y, b.z), T::mul(a.z, b.y)), T::sub(T::mul(a.z, b.x), T::mul(a.x, b.z)),
+          T::sub(T::mul(a.x, b.y), T::mul(a.y, b.x))};
+}
+template <typename F>
+__device__ __forceinline__ F xdot(const V3<F>& a, const V3<F>& b) {
+  using T = RT<F>;
+  return T::add(T::add(T::mul(a.x, b.x), T::mul(a.y, b.y)), T::mul(a.z, b.z));
+}
+// Quaternion.rotate 3D (quaternion.py:236-238): t = 2 q x v; v + w t + q x t
+template <typename F>
+__device__ __forceinline__ V3<F> xrotate(const Q4<F>& q, const V3<F>& v) {
+  using T = RT<F>;
+  const V3<F> qv = {q.x, q.y, q.z};
+  V3<F> t = xcross(qv, v);
+  t = {T::mul(F(2), t.x), T::mul(F(2), t.y), T::mul(F(2), t.z)};
+  const V3<F> u = xcross(qv, t);
+  return {T::add(T::add(v.x, T::mul(q.w, t.x)), u.x), T::add(T::add(v.y, T::mul(q.w, t.y)), u.y),
+          T::add(T::add(v.z, T::mul(q.w, t.z)), u.z)};
+}
+template <typename F>
+__device__ __forceinline__ V3<F> xrotate_back(const Q4<F>& q, const V3<F>& v) {
+  return xrotate(Q4<F>{q.w, -q.x, -q.y, -q.z}, v);
+}
+// 2D rotate (quaternion.py:224-234)
+template <typename F>
+__device__ __forceinline__ void xrotate2(const Q4<F>& q, F vx, F vy, F& rx, F& ry) {
+  using T = RT<F>;
+  const F cth = T::sub(T::mul(q.w, q.w), T::mul(q.z, q.z));
+  const F sth = T::mul(T::mul(F(2), q.w), q.z);
+  rx = T::sub(T::mul(cth, vx), T::mul(sth, vy));
+  ry = T::add(T::mul(sth, vx), T::mul(cth, vy));
+}
+// Hamilton product (quaternion.py:345-367)
+template <typename F>
+__device__ __forceinline__ Q4<F> xqmul(const Q4<F>& a, const Q4<F>& b) {
+  using T = RT<F>;
+  const V3<F> av = {a.x, a.y, a.z}, bv = {b.x, b.y, b.z};
+  const V3<F> cr = xcross(av, bv);
+  Q4<F> r;
+  r.w = T::sub(T::mul(a.w, b.w), xdot(av, bv));
+  r.x = T::add(T::add(T::mul(a.w, b.x), T::mul(b.w, a.x)), cr.x);
+  r.y = T::add(T::add(T::mul(a.w, b.y), T::mul(b.w, a.y)), cr.y);
+  r.z = T::add(T::add(T::mul(a.w, b.z), T::mul(b.w, a.z)), cr.z);
+  return r;
+}
+// Quaternion.unit (quaternion.py:72-94)
+template <typename F>
+__device__ __forceinline__ Q4<F> xqunit(const Q4<F>& q) {
+  using T = RT<F>;
+  const V3<F> v = {q.x, q.y, q.z};
+  const F n2 = T::add(T::mul(q.w, q.w), xdot(v, v));
+  const F inv = T::div(F(1), T::sqrt(n2 == F(0) ? F(1) : n2));
+  return {T::mul(q.w, inv), T::mul(q.x, inv), T::mul(q.y, inv), T::mul(q.z, inv)};
+}
+// Quaternion.from_small_rotvec (quaternion.py:129-141)
+template <typename F>
+__device__ __forceinline__ Q4<F> xsmall(const V3<F>& rv) {
+  using T = RT<F>;
+  const F n2 = xdot(rv, rv);
+  const F ch = T::sub(F(1), T::div(n2, F(8)));
+  const F sc = T::sub(F(0.5), T::div(n2, F(48)));
+  return {ch, T::mul(rv.x, sc), T::mul(rv.y, sc), T::mul(rv.z, sc)};
+}
+// omega_dot (spiral.py:22-40), 3D diagonal inertia
+template <typename F>
+__device__ __forceinline__ V3<F> xomega_dot(const V3<F>& w, const V3<F>& tq, const V3<F>& I,
+                                            const V3<F>& invI) {
+  using T = RT<F>;
+  const F cx = T::sub(T::mul(w.y, T::mul(I.z, w.z)), T::mul(w.z, T::mul(I.y, w.y)));
+  const F cy = T::sub(T::mul(w.z, T::mul(I.x, w.x)), T::mul(w.x, T::mul(I.z, w.z)));
+  const F cz = T::sub(T::mul(w.x, T::mul(I.y, w.y)), T::mul(w.y, T::mul(I.x, w.x)));
+  return {T::mul(T::sub(tq.x, cx), invI.x), T::mul(T::sub(tq.y, cy), invI.y),
+          T::mul(T::sub(tq.z, cz), invI.z)};
+}
+template <typename F>
+__device__ __forceinline__ V3<F> xaxpy(F a, const V3<F>& x, const V3<F>& y) {  // a*x + y, unfused
+  using T = RT<F>;
+  return {T::add(T::mul(a, x.x), y.x), T::add(T::mul(a, x.y), y.y), T::add(T::mul(a, x.z), y.z)};
+}
+template <typename F>
+__device__ __forceinline__ V3<F> xscale(F a, const V3<F>& x) {
+  using T = RT<F>;
+  return {T::mul(a, x.x), T::mul(a, x.y), T::mul(a, x.z)};
+}
+template <typename F>
+__device__ __forceinline__ V3<F> xadd(const V3<F>& x, const V3<F>& y) {
+  using T = RT<F>;
+  return {T::add(x.x, y.x), T::add(x.y, y.y), T::add(x.z, y.z)};
+}
+
+// SSPRK3 update of the body-frame angular velocity with step h
+// (velocity_verlet_spiral.py:93-99 / spiral.py:129-134): w + free*(k1+k2+4k3)/6.
+// `k1_out` returns omega_dot(w) for Spiral's quaternion update.
+template <typename F>
+__device__ __forceinline__ V3<F> ssprk3(F h, const V3<F>& w, const V3<F>& tq, const V3<F>& I,
+                                        const V3<F>& invI, F free, V3<F>* wdot_out) {
+  using T = RT<F>;
+  const V3<F> wd = xomega_dot(w, tq, I, invI);
+  if (wdot_out) *wdot_out = wd;
+  const V3<F> k1 = xscale(h, wd);
+  const V3<F> k2 = xscale(h, xomega_dot(xadd(w, k1), tq, I, invI));
+  const V3<F> k3 = xscale(h, xomega_dot(xadd(w, xscale(F(0.25), xadd(k1, k2))), tq, I, invI));
+  const V3<F> s = xadd(xadd(k1, k2), xscale(F(4), k3));
+  return {T::add(w.x, T::div(T::mul(free, s.x), F(6))), T::add(w.y, T::div(T::mul(free, s.y), F(6))),
+          T::add(w.z, T::div(T::mul(free, s.z), F(6)))};
+}
+
+template <typename F>
+__device__ __forceinline__ Q4<F> load_q(const Ctx<F>& c, size_t gi) {
+  return {c.q_w[gi], c.q_xyz[gi * 3 + 0], c.q_xyz[gi * 3 + 1], c.q_xyz[gi * 3 + 2]};
+}
+template <typename F>
+__device__ __forceinline__ void store_q_and_cache(const Ctx<F>& c, size_t gi, const Q4<F>& q) {
+  c.q_w[gi] = q.w;
+  c.q_xyz[gi * 3 + 0] = q.x;
+  c.q_xyz[gi * 3 + 1] = q.y;
+  c.q_xyz[gi * 3 + 2] = q.z;
+  // State.__setattr__("q") refreshes _pos_p_rot = rotate(q, pos_p) (state.py:264-273)
+  if (c.dim == 3) {
+    const V3<F> p = {c.pos_p[gi * 3], c.pos_p[gi * 3 + 1], c.pos_p[gi * 3 + 2]};
+    const V3<F> r = xrotate(q, p);
+    c.pos_p_rot[gi * 3] = r.x;
+    c.pos_p_rot[gi * 3 + 1] = r.y;
+    c.pos_p_rot[gi * 3 + 2] = r.z;
+  } else {
+    F rx, ry;
+    xrotate2(q, c.pos_p[gi * 2], c.pos_p[gi * 2 + 1], rx, ry);
+    c.pos_p_rot[gi * 2] = rx;
+    c.pos_p_rot[gi * 2 + 1] = ry;
+  }
+}
+
+// MODE 0: VelocityVerletSpiral.step_before_force (velocity_verlet_spiral.py:83-116)
+// MODE 1: VelocityVerletSpiral.step_after_force  (:156-180)
+// MODE 2: Spiral.step_after_force                (spiral.py:104-141)
+template <typename F, int MODE>
+__global__ void __launch_bounds__(256) k_rotation(Ctx<F> c) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  const F dt = c.dt[b];
+  const F dt_2 = T::div(dt, F(2));
+  const F free = c.fixed[gi] ? F(0) : F(1);
+  const F h = MODE == 2 ? dt : dt_2;
+  Q4<F> q = load_q(c, gi);
+  if (c.dim == 3) {
+    const V3<F> I = {c.inertia[gi * 3], c.inertia[gi * 3 + 1], c.inertia[gi * 3 + 2]};
+    const V3<F> invI = {T::div(F(1), I.x), T::div(F(1), I.y), T::div(F(1), I.z)};
+    const V3<F> wl = {c.ang_vel[gi * 3], c.ang_vel[gi * 3 + 1], c.ang_vel[gi * 3 + 2]};
+    const V3<F> tl = {c.torque[gi * 3], c.torque[gi * 3 + 1], c.torque[gi * 3 + 2]};
+    const V3<F> w0 = xrotate_back(q, wl);
+    const V3<F> tq = xrotate_back(q, tl);
+    V3<F> wdot;
+    const V3<F> w = ssprk3(h, w0, tq, I, invI, free, &wdot);
+    if (MODE == 0) {
+      const Q4<F> dq = xsmall(xscale(T::mul(F(2), dt_2), w));
+      q = xqunit(xqmul(q, dq));
+      store_q_and_cache(c, gi, q);
+    } else if (MODE == 2) {
+      const Q4<F> a = xsmall(xscale(T::mul(F(2), dt_2), w0));
+      const Q4<F> bq = xsmall(xscale(T::mul(T::mul(F(2), dt_2), dt_2), wdot));
+      q = xqunit(xqmul(q, xqmul(a, bq)));
+      store_q_and_cache(c, gi, q);
+    }
+    const V3<F> wn = xrotate(q, w);
+    c.ang_vel[gi * 3] = wn.x;
+    c.ang_vel[gi * 3 + 1] = wn.y;
+    c.ang_vel[gi * 3 + 2] = wn.z;
+  } else {
+    const F I = c.inertia[gi], invI = T::div(F(1), I);
+    const F w0 = c.ang_vel[gi], tq = c.torque[gi];
+    const F wd = T::mul(tq, invI);  // omega_dot 2D: torque * inv_inertia (independent of w)
+    const F k = T::mul(h, wd);
+    const F s = T::add(T::add(k, k), T::mul(F(4), k));
+    const F w = T::add(w0, T::div(T::mul(free, s), F(6)));
+    if (MODE == 0) {
+      const Q4<F> dq = xsmall(V3<F>{T::mul(F(0), T::mul(T::mul(F(2), dt_2), w)),
+                                    T::mul(F(0), T::mul(T::mul(F(2), dt_2), w)),
+                                    T::mul(F(1), T::mul(T::mul(F(2), dt_2), w))});
+      q = xqunit(xqmul(q, dq));
+      store_q_and_cache(c, gi, q);
+    } else if (MODE == 2) {
+      const F r1 = T::mul(T::mul(F(2), dt_2), w0);
+      const F r2 = T::mul(T::mul(T::mul(F(2), dt_2), dt_2), wd);
+      const Q4<F> a = xsmall(V3<F>{T::mul(F(0), r1), T::mul(F(0), r1), r1});
+      const Q4<F> bq = xsmall(V3<F>{T::mul(F(0), r2), T::mul(F(0), r2), r2});
+      q = xqunit(xqmul(q, xqmul(a, bq)));
+      store_q_and_cache(c, gi, q);
+    }
+    c.ang_vel[gi] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// clump CSR (members of every clump in index order): counting sort on clump_id
+// ---------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_clump_zero(Ctx<F> c, int* cl_start, unsigned long long* ts,
+                                                     int* tc, int tiles) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= c.n) cl_start[(size_t)b * (c.n + 1) + i] = 0;
+  if (i < tiles) ts[(size_t)b * tiles + i] = 0ull;
+  if (i == 0) tc[b] = 0;
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_clump_count(Ctx<F> c, int* cl_start, int* cl_rank) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  long long cid = (long long)c.clump_id[gi];
+  cid = cid < 0 ? 0 : (cid >= c.n ? c.n - 1 : cid);  // out-of-range ids clamp like XLA gathers
+  cl_rank[gi] = atomicAdd(&cl_start[(size_t)b * (c.n + 1) + cid], 1);
+}
+template <typename F>
+__global__ void __launch_bounds__(512) k_clump_scan(Ctx<F> c, int* cl_start, unsigned long long* ts,
+                                                     int* tc, int tiles) {
+  const int b = blockIdx.y;
+  scan_tile(cl_start + (size_t)b * (c.n + 1), c.n + 1, ts + (size_t)b * tiles, &tc[b], 0x7fffffff);
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_clump_scatter(Ctx<F> c, const int* cl_start, const int* cl_rank,
+                                                        int* tmp) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  long long cid = (long long)c.clump_id[gi];
+  cid = cid < 0 ? 0 : (cid >= c.n ? c.n - 1 : cid);
+  tmp[(size_t)b * c.n + cl_start[(size_t)b * (c.n + 1) + cid] + cl_rank[gi]] = (int)i;
+}
+// members[s + (#members with smaller index)] = i  => ascending index order per clump
+template <typename F>
+__global__ void __launch_bounds__(256) k_clump_order(Ctx<F> c, const int* cl_start, const int* tmp,
+                                                      int* members) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n;
+  long long cid = (long long)c.clump_id[off + i];
+  cid = cid < 0 ? 0 : (cid >= c.n ? c.n - 1 : cid);
+  const int s = cl_start[(size_t)b * (c.n + 1) + cid], e = cl_start[(size_t)b * (c.n + 1) + cid + 1];
+  int r = 0;
+  for (int k = s; k < e; ++k) r += tmp[off + k] < (int)i;
+  members[off + s + r] = (int)i;
+}
+
+template <typename F>
+struct ClumpCsr {
+  int* start;    // [B*(N+1)]
+  int* members;  // [B*N]
+};
+
+template <typename F>
+int build_clump_csr(cudaStream_t s, Ctx<F>& c, ClumpCsr<F>* out) {
+  // scratch: reuse the partition's integer buffers that are dead outside the collider
+  int* cl_start = c.cell_start_clump;
+  int* cl_rank = c.seg;
+  int* tmp = c.perm_b;
+  int* members = c.perm_c;
+  const int tiles = cdiv(c.n + 1, kScanTile);
+  const dim3 g1(cdiv(c.n + 1, 256), c.batch), gp(cdiv(c.n, 256), c.batch);
+  JDB_LAUNCH(k_clump_zero<F>, g1, 256, s, c, cl_start, c.tile_state_clump, c.tile_counter_clump, tiles);
+  JDB_LAUNCH(k_clump_count<F>, gp, 256, s, c, cl_start, cl_rank);
+  JDB_LAUNCH(k_clump_scan<F>, dim3(tiles, c.batch), 512, s, c, cl_start, c.tile_state_clump,
+             c.tile_counter_clump, tiles);
+  JDB_LAUNCH(k_clump_scatter<F>, gp, 256, s, c, cl_start, cl_rank, tmp);
+  JDB_LAUNCH(k_clump_order<F>, gp, 256, s, c, cl_start, tmp, members);
+  out->start = cl_start;
+  out->members = members;
+  return 0;
+}
+
+template <typename F>
+__device__ __forceinline__ void clump_range(const Ctx<F>& c, const ClumpCsr<F>& csr, int b, size_t gi,
+                                            int& s, int& e) {
+  long long cid = (long long)c.clump_id[gi];
+  cid = cid < 0 ? 0 : (cid >= c.n ? c.n - 1 : cid);
+  s = csr.start[(size_t)b * (c.n + 1) + cid];
+  e = csr.start[(size_t)b * (c.n + 1) + cid + 1];
+}
+
+// ---------------------------------------------------------------------------
+// K7  ForceManager.apply (force_manager.py:359-423)
+// ---------------------------------------------------------------------------
+// per-particle totals: F_total = F_contact + F_part + F_com, T_total = T_contact + T_part
+template <typename F>
+__device__ __forceinline__ void fm_totals(const Ctx<F>& c, int b, size_t gi, F count, F* Ft, F* Tt) {
+  using T = RT<F>;
+  const int D = c.dim, A = c.A;
+  const F mc = T::div(c.mass[gi], count);
+  F fp[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+  for (int d = 0; d < D; ++d) {
+    fp[d] = c.ext_force[gi * D + d];
+    r[d] = c.pos_p_rot[gi * D + d];
+    const F fcom = T::add(c.ext_force_com[gi * D + d], T::mul(c.gravity[b * D + d], mc));
+    Ft[d] = T::add(T::add(c.force[gi * D + d], fp[d]), fcom);
+  }
+  if (D == 3) {
+    const V3<F> cr = xcross(V3<F>{r[0], r[1], r[2]}, V3<F>{fp[0], fp[1], fp[2]});
+    const F crv[3] = {cr.x, cr.y, cr.z};
+    for (int a = 0; a < 3; ++a)
+      Tt[a] = T::add(c.torque[gi * 3 + a], T::add(c.ext_torque[gi * 3 + a], crv[a]));
+  } else {
+    const F cr = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
+    Tt[0] = T::add(c.torque[gi * A], T::add(c.ext_torque[gi * A], cr));
+  }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256) k_fm_spheres(Ctx<F> c) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  F Ft[3], Tt[3];
+  fm_totals(c, b, gi, F(1), Ft, Tt);
+  for (int d = 0; d < c.dim; ++d) {
+    c.force[gi * c.dim + d] = Ft[d];
+    c.ext_force[gi * c.dim + d] = F(0);
+    c.ext_force_com[gi * c.dim + d] = F(0);
+  }
+  for (int a = 0; a < c.A; ++a) {
+    c.torque[gi * c.A + a] = Tt[a];
+    c.ext_torque[gi * c.A + a] = F(0);
+  }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256) k_fm_totals(Ctx<F> c, ClumpCsr<F> csr) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  int s, e;
+  clump_range(c, csr, b, gi, s, e);
+  F Ft[3] = {0, 0, 0}, Tt[3] = {0, 0, 0};
+  fm_totals(c, b, gi, RT<F>::from_int((typename RT<F>::I)(e - s)), Ft, Tt);
+  F* o = c.segf + gi * 8;
+  o[0] = Ft[0]; o[1] = Ft[1]; o[2] = Ft[2];
+  o[3] = Tt[0]; o[4] = Tt[1]; o[5] = Tt[2];
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n, gi = off + i;
+  int s, e;
+  clump_range(c, csr, b, gi, s, e);
+  F acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = s; k < e; ++k) {  // members in ascending index order: fixed summation order
+    const F* o = c.segf + (off + csr.members[off + k]) * 8;
+    for (int q = 0; q < 6; ++q) acc[q] = T::add(acc[q], o[q]);
+  }
+  for (int d = 0; d < c.dim; ++d) {
+    c.force[gi * c.dim + d] = acc[d];
+    c.ext_force[gi * c.dim + d] = F(0);
+    c.ext_force_com[gi * c.dim + d] = F(0);
+  }
+  for (int a = 0; a < c.A; ++a) {
+    c.torque[gi * c.A + a] = acc[3 + a];
+    c.ext_torque[gi * c.A + a] = F(0);
+  }
+}
+
+template <typename F>
+int force_manager_apply(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0) return 0;
+  const dim3 gp(cdiv(c.n, 256), c.batch);
+  if (!c.clumps) {
+    JDB_LAUNCH(k_fm_spheres<F>, gp, 256, s, c);
+    return 0;
+  }
+  ClumpCsr<F> csr;
+  int rc = build_clump_csr<F>(s, c, &csr);
+  if (rc) return rc;
+  JDB_LAUNCH(k_fm_totals<F>, gp, 256, s, c, csr);
+  JDB_LAUNCH(k_fm_reduce<F>, gp, 256, s, c, csr);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K11  FreeDomain.apply (free.py:59-63): bounding box of all spheres
+// ---------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_free_partial(Ctx<F> c, F* part) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const F inf = F(1) / F(0);
+  F lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  if (i < c.n) {
+    const size_t gi = (size_t)b * c.n + i;
+    F n2 = F(0);
+    for (int d = 0; d < c.dim; ++d) n2 = T::add(n2, T::mul(c.pos_p[gi * c.dim + d], c.pos_p[gi * c.dim + d]));
+    const F nrm = n2 == F(0) ? F(0) : T::sqrt(T::fmax(n2, F(1e-16)));  // linalg.norm
+    const F br = T::add(nrm, c.rad[gi]);
+    for (int d = 0; d < c.dim; ++d) {
+      lo[d] = T::sub(c.pos_c[gi * c.dim + d], br);
+      hi[d] = T::add(c.pos_c[gi * c.dim + d], br);
+    }
+  }
+  __shared__ F sm[6][256];
+  for (int d = 0; d < 3; ++d) {
+    sm[d][threadIdx.x] = lo[d];
+    sm[3 + d][threadIdx.x] = hi[d];
+  }
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st)
+      for (int d = 0; d < 3; ++d) {
+        sm[d][threadIdx.x] = T::fmin(sm[d][threadIdx.x], sm[d][threadIdx.x + st]);
+        sm[3 + d][threadIdx.x] = T::fmax(sm[3 + d][threadIdx.x], sm[3 + d][threadIdx.x + st]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) part[((size_t)b * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = sm[threadIdx.x][0];
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_free_final(Ctx<F> c, const F* part, int nblocks) {
+  using T = RT<F>;
+  const int b = blockIdx.x;
+  const F inf = F(1) / F(0);
+  F lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  for (int k = threadIdx.x; k < nblocks; k += 256)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = T::fmin(lo[d], part[((size_t)b * nblocks + k) * 6 + d]);
+      hi[d] = T::fmax(hi[d], part[((size_t)b * nblocks + k) * 6 + 3 + d]);
+    }
+  __shared__ F sm[6][256];
+  for (int d = 0; d < 3; ++d) {
+    sm[d][threadIdx.x] = lo[d];
+    sm[3 + d][threadIdx.x] = hi[d];
+  }
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st)
+      for (int d = 0; d < 3; ++d) {
+        sm[d][threadIdx.x] = T::fmin(sm[d][threadIdx.x], sm[d][threadIdx.x + st]);
+        sm[3 + d][threadIdx.x] = T::fmax(sm[3 + d][threadIdx.x], sm[3 + d][threadIdx.x + st]);
+      }
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < c.dim) {
+    const int d = threadIdx.x;
+    const F box = T::sub(sm[3 + d][0], sm[d][0]);
+    c.box[b * c.dim + d] = box;
+    c.anchor[b * c.dim + d] = sm[d][0];
+    c.inv_box[b * c.dim + d] = T::div(F(1), box);  // _step_once refresh (system.py:69-74)
+  }
+}
+
+template <typename F>
+__global__ void k_inv_box(Ctx<F> c) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < c.batch * c.dim) c.inv_box[e] = RT<F>::div(F(1), c.box[e]);
+}
+
+// ---------------------------------------------------------------------------
+// K10  ReflectDomain.apply (reflect.py:165-299, _toc.py:68-94)
+// ---------------------------------------------------------------------------
+// verlet_collision_fraction for one coordinate
+template <typename F>
+__device__ __forceinline__ F toc_alpha(F v_end, F acc, F delta, F wall_sign, F dt) {
+  using T = RT<F>;
+  const F v0 = T::sub(v_end, T::mul(dt, acc));
+  const F vmid = T::sub(v_end, T::mul(T::mul(F(0.5), dt), acc));
+  const F v0n = T::mul(v0, wall_sign), vmn = T::mul(vmid, wall_sign), an = T::mul(acc, wall_sign);
+  const F A = T::mul(T::mul(T::mul(F(0.5), an), dt), dt);
+  const F B = T::mul(v0n, dt);
+  const F dw = T::add(delta, T::mul(vmn, dt));
+  F disc = T::add(T::mul(B, B), T::mul(T::mul(F(4), A), dw));
+  disc = T::fmax(F(0), disc);
+  const F sq = disc > F(0) ? T::sqrt(disc) : F(0);
+  F alpha;
+  if (B < F(0)) {
+    const F den = T::sub(B, sq) < F(-1e-10) ? T::sub(B, sq) : F(-1);
+    alpha = T::div(T::mul(F(2), dw), den);
+  } else {
+    const F twoA = T::mul(F(2), A);
+    const F den = T::abs(twoA) > F(1e-10) ? twoA : F(1);
+    alpha = T::div(T::sub(-B, sq), den);
+  }
+  return T::fmin(T::fmax(alpha, F(0)), F(1));  // jnp.clip
+}
+
+// spheres only (clump_id == iota): every segment op is an identity.
+// pos_p is NOT assumed zero: lever arms and the rotational terms are kept.
+template <typename F>
+struct ReflectLocal {
+  F over_lo[3], over_hi[3];
+  F denom[3], vcs[3], accc[3];
+};
+
+template <typename F>
+__device__ __forceinline__ void reflect_local(const Ctx<F>& c, int b, size_t gi, ReflectLocal<F>& L,
+                                              F* Rm /*3x3 rows = n_prime*/) {
+  // per-sphere quantities that do not depend on clump reductions (reflect.py:165-226)
+  using T = RT<F>;
+  const int D = c.dim;
+  const F rad = c.rad[gi];
+  F ppl[3] = {0, 0, 0}, pp[3] = {0, 0, 0};
+  for (int d = 0; d < D; ++d) {
+    ppl[d] = c.pos_p_rot[gi * D + d];
+    pp[d] = c.pos_p[gi * D + d];
+    const F pos = T::add(c.pos_c[gi * D + d], ppl[d]);
+    const F lo = T::add(c.anchor[b * D + d], rad);
+    const F hi = T::sub(T::add(c.anchor[b * D + d], c.box[b * D + d]), rad);
+    L.over_lo[d] = T::fmax(F(0), T::sub(lo, pos));
+    L.over_hi[d] = T::fmax(F(0), T::sub(pos, hi));
+  }
+  const F inv_mass = T::div(F(1), c.mass[gi]);
+  const Q4<F> q = load_q(c, gi);
+  if (D == 3) {
+    const V3<F> invI = {T::div(F(1), c.inertia[gi * 3]), T::div(F(1), c.inertia[gi * 3 + 1]),
+                        T::div(F(1), c.inertia[gi * 3 + 2])};
+    const V3<F> ppv = {pp[0], pp[1], pp[2]};
+    for (int a = 0; a < 3; ++a) {
+      const V3<F> ea = {a == 0 ? F(1) : F(0), a == 1 ? F(1) : F(0), a == 2 ? F(1) : F(0)};
+      const V3<F> np = xrotate_back(q, ea);  // n_prime[a, :]
+      Rm[a * 3 + 0] = np.x; Rm[a * 3 + 1] = np.y; Rm[a * 3 + 2] = np.z;
+      const V3<F> cr = xcross(ppv, np);
+      const F dr = T::add(T::add(T::mul(invI.x, T::mul(cr.x, cr.x)), T::mul(invI.y, T::mul(cr.y, cr.y))),
+                          T::mul(invI.z, T::mul(cr.z, cr.z)));
+      const F dn = T::add(inv_mass, dr);
+      L.denom[a] = dn == F(0) ? F(1) : dn;
+    }
+    const V3<F> w = {c.ang_vel[gi * 3], c.ang_vel[gi * 3 + 1], c.ang_vel[gi * 3 + 2]};
+    const V3<F> tq = {c.torque[gi * 3], c.torque[gi * 3 + 1], c.torque[gi * 3 + 2]};
+    const V3<F> I = {c.inertia[gi * 3], c.inertia[gi * 3 + 1], c.inertia[gi * 3 + 2]};
+    const V3<F> pl = {ppl[0], ppl[1], ppl[2]};
+    const V3<F> wxr = xcross(w, pl);
+    // body-frame torque / angular velocity through R^T (einsum "ij,j->i" with R_T = n_prime^T)
+    auto matT = [&](const V3<F>& v) {  // R_T v : (R_T)_{ij} = Rm[j][i]
+      return V3<F>{T::add(T::add(T::mul(Rm[0], v.x), T::mul(Rm[3], v.y)), T::mul(Rm[6], v.z)),
+                   T::add(T::add(T::mul(Rm[1], v.x), T::mul(Rm[4], v.y)), T::mul(Rm[7], v.z)),
+                   T::add(T::add(T::mul(Rm[2], v.x), T::mul(Rm[5], v.y)), T::mul(Rm[8], v.z))};
+    };
+    auto mat = [&](const V3<F>& v) {  // R v
+      return V3<F>{T::add(T::add(T::mul(Rm[0], v.x), T::mul(Rm[1], v.y)), T::mul(Rm[2], v.z)),
+                   T::add(T::add(T::mul(Rm[3], v.x), T::mul(Rm[4], v.y)), T::mul(Rm[5], v.z)),
+                   T::add(T::add(T::mul(Rm[6], v.x), T::mul(Rm[7], v.y)), T::mul(Rm[8], v.z))};
+    };
+    const V3<F> tb = matT(tq), wb = matT(w);
+    const V3<F> Iw = {T::mul(I.x, wb.x), T::mul(I.y, wb.y), T::mul(I.z, wb.z)};
+    const V3<F> cwi = xcross(wb, Iw);
+    const V3<F> ab = {T::mul(T::sub(tb.x, cwi.x), invI.x), T::mul(T::sub(tb.y, cwi.y), invI.y),
+                      T::mul(T::sub(tb.z, cwi.z), invI.z)};
+    const V3<F> ar = mat(ab);
+    const V3<F> axr = xcross(ar, pl);
+    const F wx[3] = {wxr.x, wxr.y, wxr.z}, ax[3] = {axr.x, axr.y, axr.z};
+    for (int d = 0; d < 3; ++d) {
+      L.vcs[d] = T::add(c.vel[gi * 3 + d], wx[d]);
+      L.accc[d] = T::add(T::mul(c.force[gi * 3 + d], inv_mass), ax[d]);
+    }
+  } else {
+    const F invI = T::div(F(1), c.inertia[gi]);
+    for (int a = 0; a < 2; ++a) {
+      F nx, ny;  // rotate_back(q, e_a) in 2D
+      xrotate2(Q4<F>{q.w, -q.x, -q.y, -q.z}, a == 0 ? F(1) : F(0), a == 1 ? F(1) : F(0), nx, ny);
+      Rm[a * 3 + 0] = nx; Rm[a * 3 + 1] = ny; Rm[a * 3 + 2] = F(0);
+      const F cr = T::sub(T::mul(pp[0], ny), T::mul(pp[1], nx));
+      const F dn = T::add(inv_mass, T::mul(invI, T::mul(cr, cr)));
+      L.denom[a] = dn == F(0) ? F(1) : dn;
+    }
+    const F w = c.ang_vel[gi], tq = c.torque[gi];
+    const F ar = T::mul(tq, invI);
+    const F wx[2] = {T::mul(-w, ppl[1]), T::mul(w, ppl[0])};
+    const F ax[2] = {T::mul(-ar, ppl[1]), T::mul(ar, ppl[0])};
+    for (int d = 0; d < 2; ++d) {
+      L.vcs[d] = T::add(c.vel[gi * 2 + d], wx[d]);
+      L.accc[d] = T::add(T::mul(c.force[gi * 2 + d], inv_mass), ax[d]);
+    }
+  }
+}
+
+// Impulse of one sphere given clump-level maxima / alpha / active counts; returns the
+// per-sphere contributions j*inv_mass (dv) and d_omega_lab (reflect.py:239-276).
+template <typename F>
+__device__ __forceinline__ void reflect_impulse(const Ctx<F>& c, int b, size_t gi,
+                                                const ReflectLocal<F>& L, const F* Rm,
+                                                const F* active, const F* wall_sign,
+                                                const F* count_active, F alpha_clump, F* dv, F* dom) {
+  using T = RT<F>;
+  const int D = c.dim;
+  const F dt = c.dt[b], e = c.restitution[b];
+  const F inv_mass = T::div(F(1), c.mass[gi]);
+  const F dt_factor = T::mul(T::sub(alpha_clump, F(1)), dt);
+  F jm[3] = {0, 0, 0};
+  for (int d = 0; d < D; ++d) {
+    const F vc = T::add(L.vcs[d], T::mul(dt_factor, L.accc[d]));
+    F j = T::div(T::mul(-T::add(F(1), e), vc), L.denom[d]);
+    const F closing = T::mul(vc, wall_sign[d]) < F(0) ? F(1) : F(0);
+    const F weight = T::div(active[d], T::fmax(count_active[d], F(1)));
+    j = T::mul(j, T::mul(weight, closing));
+    jm[d] = j;
+    dv[d] = T::mul(j, inv_mass);
+  }
+  if (D == 3) {
+    // j_body = R_T j ; moment = pos_p x j_body ; d_omega_lab = R (moment * inv_inertia)
+    const V3<F> jb = {T::add(T::add(T::mul(Rm[0], jm[0]), T::mul(Rm[3], jm[1])), T::mul(Rm[6], jm[2])),
+                      T::add(T::add(T::mul(Rm[1], jm[0]), T::mul(Rm[4], jm[1])), T::mul(Rm[7], jm[2])),
+                      T::add(T::add(T::mul(Rm[2], jm[0]), T::mul(Rm[5], jm[1])), T::mul(Rm[8], jm[2]))};
+    const V3<F> pp = {c.pos_p[gi * 3], c.pos_p[gi * 3 + 1], c.pos_p[gi * 3 + 2]};
+    const V3<F> mo = xcross(pp, jb);
+    const V3<F> ob = {T::mul(mo.x, T::div(F(1), c.inertia[gi * 3])),
+                      T::mul(mo.y, T::div(F(1), c.inertia[gi * 3 + 1])),
+                      T::mul(mo.z, T::div(F(1), c.inertia[gi * 3 + 2]))};
+    dom[0] = T::add(T::add(T::mul(Rm[0], ob.x), T::mul(Rm[1], ob.y)), T::mul(Rm[2], ob.z));
+    dom[1] = T::add(T::add(T::mul(Rm[3], ob.x), T::mul(Rm[4], ob.y)), T::mul(Rm[5], ob.z));
+    dom[2] = T::add(T::add(T::mul(Rm[6], ob.x), T::mul(Rm[7], ob.y)), T::mul(Rm[8], ob.z));
+  } else {
+    // einsum("...ji,...j->...i", n_prime, j): j_body_i = sum_j n_prime[j][i] * jm[j]
+    const F jbx = T::add(T::mul(Rm[0], jm[0]), T::mul(Rm[3], jm[1]));
+    const F jby = T::add(T::mul(Rm[1], jm[0]), T::mul(Rm[4], jm[1]));
+    const F mo = T::sub(T::mul(c.pos_p[gi * 2], jby), T::mul(c.pos_p[gi * 2 + 1], jbx));
+    dom[0] = T::mul(mo, T::div(F(1), c.inertia[gi]));
+    dom[1] = dom[2] = F(0);
+  }
+}
+
+// final state update for one sphere (reflect.py:254-297)
+template <typename F>
+__device__ __forceinline__ void reflect_update(const Ctx<F>& c, int b, size_t gi, const F* dv_in,
+                                               const F* dom_in, F alpha_clump) {
+  using T = RT<F>;
+  const int D = c.dim;
+  const bool fixed = c.fixed[gi] != 0;
+  const F dt_rem = T::mul(T::sub(F(1), alpha_clump), c.dt[b]);
+  F dv[3], dom[3];
+  for (int d = 0; d < 3; ++d) {
+    dv[d] = fixed ? F(0) : dv_in[d];
+    dom[d] = fixed ? F(0) : dom_in[d];
+  }
+  for (int d = 0; d < D; ++d) c.vel[gi * D + d] = T::add(c.vel[gi * D + d], dv[d]);
+  V3<F> dth;
+  if (D == 3) {
+    for (int a = 0; a < 3; ++a) c.ang_vel[gi * 3 + a] = T::add(c.ang_vel[gi * 3 + a], dom[a]);
+    dth = {T::mul(dom[0], dt_rem), T::mul(dom[1], dt_rem), T::mul(dom[2], dt_rem)};
+  } else {
+    c.ang_vel[gi] = T::add(c.ang_vel[gi], dom[0]);
+    dth = {F(0), F(0), T::mul(dom[0], dt_rem)};
+  }
+  const Q4<F> q = xqunit(xqmul(xsmall(dth), load_q(c, gi)));  // LEFT multiply (reflect.py:293)
+  store_q_and_cache(c, gi, q);
+  for (int d = 0; d < D; ++d)
+    c.pos_c[gi * D + d] = T::add(c.pos_c[gi * D + d], T::mul(dv[d], dt_rem));
+}
+
+template <typename F>
+__global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  ReflectLocal<F> L;
+  F Rm[9];
+  reflect_local(c, b, gi, L, Rm);
+  F active[3] = {0, 0, 0}, ws[3] = {0, 0, 0}, cnt[3] = {0, 0, 0};
+  F amin = F(1);
+  const F dt = c.dt[b];
+  for (int d = 0; d < c.dim; ++d) {
+    // own clump: max_lo == over_lo, so "deepest" reduces to over > 0
+    const F wsd = T::sub(L.over_lo[d] > F(0) ? F(1) : F(0), L.over_hi[d] > F(0) ? F(1) : F(0));
+    ws[d] = wsd;
+    active[d] = T::abs(wsd);
+    cnt[d] = active[d];
+    const F delta = T::fmax(L.over_lo[d], L.over_hi[d]);
+    const F al = toc_alpha(L.vcs[d], L.accc[d], delta, wsd, dt);
+    if (active[d] > F(0)) amin = T::fmin(amin, al);
+  }
+  F dv[3] = {0, 0, 0}, dom[3] = {0, 0, 0};
+  reflect_impulse(c, b, gi, L, Rm, active, ws, cnt, amin, dv, dom);
+  reflect_update(c, b, gi, dv, dom, amin);
+}
+
+// general clumps: 4 phases through scratch (segf, 8 F per sphere + seg2, 8 F per sphere)
+template <typename F>
+__global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {  // over_lo / over_hi
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  ReflectLocal<F> L;
+  F Rm[9];
+  reflect_local(c, b, gi, L, Rm);
+  F* o = c.segf + gi * 8;
+  for (int d = 0; d < 3; ++d) {
+    o[d] = d < c.dim ? L.over_lo[d] : F(0);
+    o[3 + d] = d < c.dim ? L.over_hi[d] : F(0);
+  }
+}
+template <typename F>
+__global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F* seg2) {
+  // clump maxima -> wall_sign / active / alpha_min_dim per sphere
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n, gi = off + i;
+  int s, e;
+  clump_range(c, csr, b, gi, s, e);
+  F mlo[3] = {0, 0, 0}, mhi[3] = {0, 0, 0};
+  for (int k = s; k < e; ++k) {
+    const F* o = c.segf + (off + csr.members[off + k]) * 8;
+    for (int d = 0; d < 3; ++d) {
+      mlo[d] = k == s ? o[d] : T::fmax(mlo[d], o[d]);
+      mhi[d] = k == s ? o[3 + d] : T::fmax(mhi[d], o[3 + d]);
+    }
+  }
+  ReflectLocal<F> L;
+  F Rm[9];
+  reflect_local(c, b, gi, L, Rm);
+  const F dt = c.dt[b];
+  F amin = F(1);
+  F* o2 = seg2 + gi * 8;
+  for (int d = 0; d < 3; ++d) {
+    F wsd = F(0);
+    if (d < c.dim) {
+      const bool dlo = L.over_lo[d] > F(0) && L.over_lo[d] == mlo[d];
+      const bool dhi = L.over_hi[d] > F(0) && L.over_hi[d] == mhi[d];
+      wsd = T::sub(dlo ? F(1) : F(0), dhi ? F(1) : F(0));
+      const F delta = T::fmax(mlo[d], mhi[d]);
+      const F al = toc_alpha(L.vcs[d], L.accc[d], delta, wsd, dt);
+      if (T::abs(wsd) > F(0)) amin = T::fmin(amin, al);
+    }
+    o2[d] = wsd;
+  }
+  o2[3] = amin;
+}
+template <typename F>
+__global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, const F* seg2) {
+  // clump alpha / active counts -> per-sphere impulse contributions (into segf)
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n, gi = off + i;
+  int s, e;
+  clump_range(c, csr, b, gi, s, e);
+  F alpha = F(0), cnt[3] = {0, 0, 0};
+  for (int k = s; k < e; ++k) {
+    const F* o = seg2 + (off + csr.members[off + k]) * 8;
+    alpha = k == s ? o[3] : T::fmin(alpha, o[3]);
+    for (int d = 0; d < 3; ++d) cnt[d] = T::add(cnt[d], T::abs(o[d]));
+  }
+  ReflectLocal<F> L;
+  F Rm[9];
+  reflect_local(c, b, gi, L, Rm);
+  const F* mine = seg2 + gi * 8;
+  F ws[3] = {mine[0], mine[1], mine[2]};
+  F active[3] = {T::abs(ws[0]), T::abs(ws[1]), T::abs(ws[2])};
+  F dv[3] = {0, 0, 0}, dom[3] = {0, 0, 0};
+  reflect_impulse(c, b, gi, L, Rm, active, ws, cnt, alpha, dv, dom);
+  F* o = c.segf + gi * 8;
+  for (int d = 0; d < 3; ++d) {
+    o[d] = dv[d];
+    o[3 + d] = dom[d];
+  }
+  o[6] = alpha;
+}
+template <typename F>
+__global__ void __launch_bounds__(128) k_reflect_p4(Ctx<F> c, ClumpCsr<F> csr) {
+  using T = RT<F>;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n, gi = off + i;
+  int s, e;
+  clump_range(c, csr, b, gi, s, e);
+  F dv[3] = {0, 0, 0}, dom[3] = {0, 0, 0};
+  for (int k = s; k < e; ++k) {
+    const F* o = c.segf + (off + csr.members[off + k]) * 8;
+    for (int d = 0; d < 3; ++d) {
+      dv[d] = T::add(dv[d], o[d]);
+      dom[d] = T::add(dom[d], o[3 + d]);
+    }
+  }
+  reflect_update(c, b, gi, dv, dom, c.segf[gi * 8 + 6]);
+}
+
+template <typename F>
+int domain_apply(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0) return 0;
+  if (c.domain == JDB200_DOMAIN_FREE) {
+    const int nb = cdiv(c.n, 256);
+    JDB_LAUNCH(k_free_partial<F>, dim3(nb, c.batch), 256, s, c, c.segf);
+    JDB_LAUNCH(k_free_final<F>, dim3(c.batch), 256, s, c, c.segf, nb);
+  } else if (c.domain == JDB200_DOMAIN_REFLECT) {
+    const dim3 gp(cdiv(c.n, 128), c.batch);
+    if (!c.clumps) {
+      JDB_LAUNCH(k_reflect_spheres<F>, gp, 128, s, c);
+    } else {
+      ClumpCsr<F> csr;
+      int rc = build_clump_csr<F>(s, c, &csr);
+      if (rc) return rc;
+      JDB_LAUNCH(k_reflect_p1<F>, gp, 128, s, c);
+      JDB_LAUNCH(k_reflect_p2<F>, gp, 128, s, c, csr, c.segf2);
+      JDB_LAUNCH(k_reflect_p3<F>, gp, 128, s, c, csr, c.segf2);
+      JDB_LAUNCH(k_reflect_p4<F>, gp, 128, s, c, csr);
+    }
+  }
+  return 0;
+}
+
+template <typename F>
+int refresh_inv_box(cudaStream_t s, Ctx<F>& c) {
+  JDB_LAUNCH(k_inv_box<F>, dim3(cdiv((long long)c.batch * c.dim, 128)), 128, s, c);
+  return 0;
+}
+
+template <typename F>
+int linear_before(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0 || c.lin != JDB200_LIN_VERLET) return 0;  // DirectEuler.step_before_force is a no-op
+  JDB_LAUNCH((k_linear<F, true, true>), dim3(cdiv(c.n * c.dim, 256), c.batch), 256, s, c);
+  return 0;
+}
+template <typename F>
+int linear_after(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0 || c.lin == JDB200_LIN_NONE) return 0;
+  const dim3 g(cdiv(c.n * c.dim, 256), c.batch);
+  if (c.lin == JDB200_LIN_VERLET) JDB_LAUNCH((k_linear<F, true, false>), g, 256, s, c);
+  else JDB_LAUNCH((k_linear<F, false, true>), g, 256, s, c);
+  return 0;
+}
+template <typename F>
+int rotation_before(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0 || c.rot != JDB200_ROT_VERLETSPIRAL) return 0;  // Spiral has no before-force part
+  JDB_LAUNCH((k_rotation<F, 0>), dim3(cdiv(c.n, 256), c.batch), 256, s, c);
+  return 0;
+}
+template <typename F>
+int rotation_after(cudaStream_t s, Ctx<F>& c) {
+  if (c.n == 0 || c.rot == JDB200_ROT_NONE) return 0;
+  const dim3 g(cdiv(c.n, 256), c.batch);
+  if (c.rot == JDB200_ROT_VERLETSPIRAL) JDB_LAUNCH((k_rotation<F, 1>), g, 256, s, c);
+  else JDB_LAUNCH((k_rotation<F, 2>), g, 256, s, c);
+  return 0;
+}
+
+#define JDB_INST(F)                                                   \
+  template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
+  template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
+  template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \
+  template int linear_before<F>(cudaStream_t, Ctx<F>&);               \
+  template int linear_after<F>(cudaStream_t, Ctx<F>&);                \
+  template int rotation_before<F>(cudaStream_t, Ctx<F>&);             \
+  template int rotation_after<F>(cudaStream_t, Ctx<F>&);
+JDB_INST(float)
+JDB_INST(double)
+
+}  // namespace jdb

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the jaxdem_b200 plugin classes)
+against the CPU oracle on the same seeded inputs.  Integer / index results must be
+BIT-EXACT; floating point within rel 1e-5 (f32) / 1e-12 (f64) of the field scale."""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import colliders as ocol, domains as odom, force_manager as ofm, integrators as oint
+from helpers import assert_close, build_gpu, build_oracle, compare_states, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+DT = [np.float32, np.float64]
+
+
+def _partition_oracle(ost, osy):
+    pos = ost.pos
+    perm, sh, nh, ovf, _ = ocol.get_spatial_partition(pos, osy, osy.collider.cell_size,
+                                                      osy.collider.neighbor_mask, ost.idtype)
+    if osy.domain.periodic:
+        nh = ocol.dedup_stencil_hashes(nh)
+    return perm, sh, nh, ovf
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("domain", ["periodic", "free", "reflect"])
+@pytest.mark.parametrize("grid_mode", ["auto", "sorted"])
+def test_partition_bit_exact(dtype, dim, domain, grid_mode):
+    n = 3000
+    # spread 1.3: a third of the particles lie outside the box (un-wrapped periodic
+    # coordinates / out-of-grid cells for bounded domains)
+    inp = make_inputs(n, dim, seed=11, dtype=dtype, poly=1.6, spread=1.3)
+    inp["pos"] -= 0.15 * inp["box"]
+    ost, osy = build_oracle(inp, dtype=dtype, domain=domain)
+    gst, gsy = build_gpu(inp, dtype=dtype, domain=domain, grid_mode=grid_mode)
+    perm, sh, nh, ovf = _partition_oracle(ost, osy)
+    gperm, gsh, gnh, dense = gsy.collider.partition(gst, gsy)
+    assert np.array_equal(gsh.cpu().numpy(), sh)
+    assert np.array_equal(gperm.cpu().numpy(), perm)
+    assert np.array_equal(gnh.cpu().numpy(), nh)
+    if grid_mode == "sorted":
+        assert not bool(dense)
+    elif domain == "periodic":
+        assert bool(dense)  # periodic hashes always fit the dense table here
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_partition_dense_equals_sorted_and_tiny_grids(dtype):
+    # box of 2 cells per axis: stencil rows collide after the wrap (de-dup path)
+    for dim, n in ((2, 200), (3, 400)):
+        inp = make_inputs(n, dim, seed=5, dtype=dtype, box=2.3)
+        ost, osy = build_oracle(inp, dtype=dtype)
+        perm, sh, nh, _ = _partition_oracle(ost, osy)
+        assert (nh == -1).any()
+        for mode in ("auto", "sorted"):
+            gst, gsy = build_gpu(inp, dtype=dtype, grid_mode=mode)
+            gperm, gsh, gnh, dense = gsy.collider.partition(gst, gsy)
+            assert np.array_equal(gperm.cpu().numpy(), perm) and np.array_equal(gsh.cpu().numpy(), sh)
+            assert np.array_equal(gnh.cpu().numpy(), nh)
+        ocol.celllist_compute_force(ost, osy)
+        gsy.collider.compute_force(gst, gsy)
+        assert_close(gst.force, ost.force, dtype, "force")
+
+
+def test_dense_falls_back_when_cell_is_overfull():
+    # 500 particles in ONE cell (> JDB200_DENSE_MAX_OCC): auto must take the sorted path
+    rng = np.random.default_rng(0)
+    inp = make_inputs(500, 3, seed=1, dtype=np.float64, box=20.0)
+    inp["pos"] = (10.0 + rng.uniform(0, 0.4, (500, 3)))
+    ost, osy = build_oracle(inp, dtype=np.float64)
+    gst, gsy = build_gpu(inp, dtype=np.float64)
+    perm, sh, nh, _ = _partition_oracle(ost, osy)
+    gperm, gsh, gnh, dense = gsy.collider.partition(gst, gsy)
+    assert not bool(dense)
+    assert np.array_equal(gperm.cpu().numpy(), perm) and np.array_equal(gsh.cpu().numpy(), sh)
+    ocol.celllist_compute_force(ost, osy)
+    gsy.collider.compute_force(gst, gsy)
+    assert_close(gst.force, ost.force, np.float64, "force")
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("law", ["spring", "hertz", "cundallstrack"])
+@pytest.mark.parametrize("domain", ["periodic", "free"])
+def test_compute_force_and_energy(dtype, dim, law, domain):
+    n = 2500
+    inp = make_inputs(n, dim, seed=3, dtype=dtype, poly=1.5, phi=0.6, clumps=True, bonds=True, nmat=3)
+    kw = dict(dtype=dtype, domain=domain, law=law, nmat=3)
+    ost, osy = build_oracle(inp, **kw)
+    gst, gsy = build_gpu(inp, **kw)
+    if domain == "free":
+        odom.free_apply(ost, osy)
+        osy.domain.inv_box_size = (1.0 / osy.domain.box_size).astype(dtype)
+        gsy.domain.apply(gst, gsy)
+        assert_close(gsy.domain.box_size, osy.domain.box_size, dtype, "box", factor=0)
+        assert_close(gsy.domain.anchor, osy.domain.anchor, dtype, "anchor", factor=0)
+    ocol.celllist_compute_force(ost, osy)
+    gsy.collider.compute_force(gst, gsy)
+    assert float(np.abs(ost.force).max()) > 0
+    assert_close(gst.force, ost.force, dtype, "force", factor=4)
+    assert_close(gst.torque, ost.torque, dtype, "torque", factor=4)
+    assert bool(gsy.collider.overflow) == bool(osy.collider.overflow)
+    e = ocol.celllist_compute_potential_energy(ost, osy)
+    _, _, ge = gsy.collider.compute_potential_energy(gst, gsy)
+    assert_close(ge, e, dtype, "energy", factor=8)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
+def test_naive_collider_matches_oracle_naive(dtype, law):
+    inp = make_inputs(300, 3, seed=9, dtype=dtype, phi=0.6, clumps=True, bonds=True, nmat=2)
+    kw = dict(dtype=dtype, law=law, nmat=2)
+    ost, osy = build_oracle(inp, collider="naive", **kw)
+    gst, gsy = build_gpu(inp, collider="naive", **kw)
+    ocol.naive_compute_force(ost, osy)
+    gsy.collider.compute_force(gst, gsy)
+    assert_close(gst.force, ost.force, dtype, "force", factor=4)
+    assert_close(gst.torque, ost.torque, dtype, "torque", factor=4)
+    _, _, ge = gsy.collider.compute_potential_energy(gst, gsy)
+    assert_close(ge, ocol.naive_compute_potential_energy(ost, osy), dtype, "energy", factor=8)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("domain", ["periodic", "reflect"])
+@pytest.mark.parametrize("K", [64, 6])
+def test_neighbor_list_bit_exact(dtype, dim, domain, K):
+    inp = make_inputs(1500, dim, seed=21, dtype=dtype, phi=0.55, clumps=True, bonds=True)
+    ost, osy = build_oracle(inp, dtype=dtype, domain=domain)
+    gst, gsy = build_gpu(inp, dtype=dtype, domain=domain)
+    cutoff = 1.35
+    nl, ovf = ocol.celllist_create_neighbor_list(ost, osy, cutoff, K)
+    _, _, gnl, govf = gsy.collider.create_neighbor_list(gst, gsy, cutoff, K)
+    assert bool(govf) == bool(ovf)
+    assert ovf == (K == 6)
+    assert np.array_equal(gnl.cpu().numpy(), nl)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+def test_integrator_hooks(dtype, dim):
+    inp = make_inputs(2000, dim, seed=2, dtype=dtype, clumps=True, fixed_frac=0.2)
+    rng = np.random.default_rng(4)
+    for lin, rot in (("verlet", "verletspiral"), ("euler", "spiral")):
+        ost, osy = build_oracle(inp, dtype=dtype, lin=lin, rot=rot, dt=5e-3)
+        gst, gsy = build_gpu(inp, dtype=dtype, lin=lin, rot=rot, dt=5e-3)
+        A = ost.torque.shape[1]
+        f = rng.normal(0, 5, ost.force.shape).astype(dtype)
+        t = rng.normal(0, 2, (ost.N, A)).astype(dtype)
+        ost.force, ost.torque = f.copy(), t.copy()
+        gst.force.copy_(torch.as_tensor(f))
+        gst.torque.copy_(torch.as_tensor(t))
+        for hook in (0, 1):
+            oint.LINEAR[lin][hook](ost, osy)
+            oint.ROTATION[rot][hook](ost, osy)
+            if hook == 0:
+                gsy.linear_integrator.step_before_force(gst, gsy)
+                gsy.rotation_integrator.step_before_force(gst, gsy)
+            else:
+                gsy.linear_integrator.step_after_force(gst, gsy)
+                gsy.rotation_integrator.step_after_force(gst, gsy)
+            compare_states(gst, ost, dtype, factor=0.1)  # unfused arithmetic: ~ulp agreement
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("clumps", [False, True])
+def test_force_manager_apply(dtype, dim, clumps):
+    inp = make_inputs(1800, dim, seed=8, dtype=dtype, clumps=clumps)
+    g = [0.0, -9.81] if dim == 2 else [0.0, 0.3, -9.81]
+    ost, osy = build_oracle(inp, dtype=dtype, gravity=g)
+    gst, gsy = build_gpu(inp, dtype=dtype, gravity=g)
+    rng = np.random.default_rng(1)
+    A = ost.torque.shape[1]
+    arrs = {k: rng.normal(0, 3, s).astype(dtype) for k, s in
+            (("force", ost.force.shape), ("torque", (ost.N, A)), ("ef", ost.force.shape),
+             ("efc", ost.force.shape), ("et", (ost.N, A)))}
+    ost.force, ost.torque = arrs["force"].copy(), arrs["torque"].copy()
+    osy.force_manager.external_force = arrs["ef"].copy()
+    osy.force_manager.external_force_com = arrs["efc"].copy()
+    osy.force_manager.external_torque = arrs["et"].copy()
+    gst.force.copy_(torch.as_tensor(arrs["force"]))
+    gst.torque.copy_(torch.as_tensor(arrs["torque"]))
+    gsy.force_manager.external_force.copy_(torch.as_tensor(arrs["ef"]))
+    gsy.force_manager.external_force_com.copy_(torch.as_tensor(arrs["efc"]))
+    gsy.force_manager.external_torque.copy_(torch.as_tensor(arrs["et"]))
+    ofm.apply(ost, osy)
+    gsy.force_manager.apply(gst, gsy)
+    assert_close(gst.force, ost.force, dtype, "force", factor=0.1)
+    assert_close(gst.torque, ost.torque, dtype, "torque", factor=0.1)
+    for k in ("external_force", "external_force_com", "external_torque"):
+        assert float(getattr(gsy.force_manager, k).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("clumps", [False, True])
+def test_reflect_apply(dtype, dim, clumps):
+    inp = make_inputs(1500, dim, seed=13, dtype=dtype, clumps=clumps, fixed_frac=0.1, spread=1.08)
+    inp["pos"] -= 0.04 * inp["box"]  # a layer of particles pokes through every wall
+    kw = dict(dtype=dtype, domain="reflect", restitution=0.8, dt=2e-3)
+    ost, osy = build_oracle(inp, **kw)
+    gst, gsy = build_gpu(inp, **kw)
+    rng = np.random.default_rng(6)
+    f = rng.normal(0, 20, ost.force.shape).astype(dtype)
+    t = rng.normal(0, 2, ost.torque.shape).astype(dtype)
+    ost.force, ost.torque = f.copy(), t.copy()
+    gst.force.copy_(torch.as_tensor(f))
+    gst.torque.copy_(torch.as_tensor(t))
+    v0 = ost.vel.copy()
+    odom.reflect_apply(ost, osy)
+    assert np.abs(ost.vel - v0).max() > 0.1  # impulses did fire
+    gsy.domain.apply(gst, gsy)
+    compare_states(gst, ost, dtype, factor=1.0, fields=("pos_c", "vel", "ang_vel"))
+
+
+CONFIGS = [
+    # (dim, domain, law, lin, rot, clumps)
+    (3, "periodic", "spring", "verlet", "", False),            # BASELINE config 2 (scaled down)
+    (3, "periodic", "cundallstrack", "verlet", "verletspiral", False),  # config 3
+    (3, "periodic", "cundallstrack", "verlet", "verletspiral", True),   # config 5
+    (3, "reflect", "spring", "verlet", "verletspiral", False),  # config 1 (README), cell list
+    (2, "periodic", "spring", "verlet", "verletspiral", False),  # config 4 geometry
+    (2, "free", "hertz", "euler", "spiral", True),
+    (3, "free", "spring", "euler", "spiral", False),
+]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "-".join(map(str, c)))
+def test_full_step_matches_oracle(dtype, cfg):
+    dim, domain, law, lin, rot, clumps = cfg
+    inp = make_inputs(1200, dim, seed=17, dtype=dtype, phi=0.55, clumps=clumps, fixed_frac=0.05, poly=1.3)
+    g = None if domain == "periodic" else ([0.0, -1.0] if dim == 2 else [0.0, 0.0, -1.0])
+    kw = dict(dtype=dtype, domain=domain, law=law, lin=lin, rot=rot, dt=1e-3, gravity=g)
+    ost, osy = build_oracle(inp, **kw)
+    gst, gsy = build_gpu(inp, **kw)
+    import jaxdem_b200 as jd
+    hst, hsy = build_gpu(inp, **kw)  # hook-by-hook twin of the fused driver
+    for step in range(3):
+        oracle.step(ost, osy, 1)
+        jd.System.step(gst, gsy, n=1)
+        jd.System.step(hst, hsy, n=1, fused=False)
+        compare_states(gst, ost, dtype, factor=4.0 * (step + 1))
+        for f in ("pos_c", "vel", "force", "torque", "ang_vel", "_pos_p_rot"):  # same kernels, same order
+            assert torch.equal(getattr(gst, f), getattr(hst, f)), f
+    assert float(gsy.step_count) == 3
+
+
+def test_readme_config_naive_reflect():
+    # BASELINE config 1: 10x10x10 grid, spacing 0.5, r 0.1, reflect box 20, naive collider,
+    # defaults of System.create (dt 0.005, verlet + verletspiral, spring, young_eff 1e4)
+    import jaxdem_b200 as jd
+    ost = oracle.grid_state((10, 10, 10), 0.5, 0.1, seed=0, dtype=np.float32)
+    osy = oracle.create_system(ost, domain_type="reflect", domain_kw=dict(box_size=[20.0] * 3))
+    gst = jd.State.create(ost.pos_c, vel=ost.vel, rad=ost.rad, mass=ost.mass, dtype=torch.float32)
+    gsy = jd.System.create(gst.shape, domain_type="reflect", domain_kw=dict(box_size=[20.0] * 3))
+    oracle.step(ost, osy, 20)
+    jd.System.step(gst, gsy, n=20)
+    compare_states(gst, ost, np.float32, factor=40.0)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_batched_systems_match_unbatched(dtype):
+    import jaxdem_b200 as jd
+    F = torch.float32 if dtype == np.float32 else torch.float64
+    singles, batched = [], []
+    B = 5
+    for b in range(B):
+        inp = make_inputs(400, 2, seed=100 + b, dtype=dtype, phi=0.5 + 0.05 * b)
+        st, sy = build_gpu(inp, dtype=dtype, law="hertz")
+        singles.append((st, sy, inp))
+    st_b = jd.State.stack([s[0].clone() for s in singles])
+    sy_b = jd.System.create(st_b.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=singles[0][0]),
+                            domain_type="periodic", domain_kw=dict(box_size=np.stack([s[2]["box"] for s in singles])),
+                            force_model_type="hertz",
+                            mat_table=jd.MaterialTable.from_materials(
+                                [jd.Material.create("elasticfrict", young=1.0e3, poisson=0.3, density=1.0,
+                                                    mu=0.5, e=0.8, mu_r=0.05)]), dtype=F)
+    jd.System.step(st_b, sy_b, n=4)
+    for b, (st, sy, _) in enumerate(singles):
+        jd.System.step(st, sy, n=4)
+        for f in ("pos_c", "vel", "force", "ang_vel"):
+            assert torch.equal(getattr(st_b, f)[b], getattr(st, f)), (b, f)
+
+
+def test_pins_through_the_gpu_path():
+    # reference tests/test_clump_pair_friction.py:167-186 and tests/test_excluded_pairs.py:11-61
+    import jaxdem_b200 as jd
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elastic", young=1.0, poisson=0.3, density=1.0)])
+    st = jd.State.create([[9.8, 5.0], [0.2, 5.4]], rad=[0.5, 0.5], clump_id=[0, 1], dtype=torch.float64)
+    for col in ("naive", "CellList"):
+        sy = jd.System.create(st.shape, collider_type=col, collider_kw=dict(state=st) if col == "CellList" else {},
+                              domain_type="periodic", domain_kw=dict(box_size=[10.0, 10.0]), mat_table=mt,
+                              dtype=torch.float64)
+        sy.collider.compute_force(st, sy)
+        np.testing.assert_allclose(st.force[0].cpu().numpy(), [-0.3071067811865475] * 2, rtol=1e-12)
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elastic", young=1000.0, poisson=0.3, density=1.0)],
+                                         matcher=jd.MaterialMatchmaker.create("linear"))
+    st = jd.State.create([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]], rad=[1.1] * 3, bond_id=[[1], [0, 2], [1]],
+                         dtype=torch.float64)
+    for col in ("naive", "CellList"):
+        sy = jd.System.create(st.shape, dt=1e-3, collider_type=col,
+                              collider_kw=dict(state=st) if col == "CellList" else {}, mat_table=mt,
+                              dtype=torch.float64)
+        sy.collider.compute_force(st, sy)
+        f = st.force.cpu().numpy()
+        assert np.allclose(f[1], 0.0, atol=1e-5) and abs(f[0, 0]) > 0.1 and np.allclose(f[0], -f[2], atol=1e-5)
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 2 at full size (1M spheres): size-independent properties."""
+    import jaxdem_b200 as jd
+    n_side = 102
+    N = n_side**3
+    r, phi = 0.5, 0.5
+    L = (N * 4 / 3 * np.pi * r**3 / phi) ** (1 / 3)
+    st = jd.utils.grid_state(n_per_axis=(n_side,) * 3, spacing=L / n_side, radius=r, jitter=0.05, seed=1,
+                             dtype=torch.float32)
+    sy = jd.System.create(st.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=st),
+                          rotation_integrator_type="", domain_type="periodic", domain_kw=dict(box_size=[L] * 3),
+                          dtype=torch.float32)
+    perm, sh, _, dense = sy.collider.partition(st, sy)
+    assert bool(dense)
+    assert bool((sh[1:] >= sh[:-1]).all())  # sortedness
+    assert torch.equal(torch.sort(perm).values, torch.arange(N, device=perm.device, dtype=perm.dtype))
+    same = sh[1:] == sh[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())  # stable: ties in index order
+    # dense and sorted strategies give the same permutation
+    sy2 = jd.System.create(st.shape, dt=1e-3, collider_type="CellList",
+                           collider_kw=dict(state=st, grid_mode="sorted"), rotation_integrator_type="",
+                           domain_type="periodic", domain_kw=dict(box_size=[L] * 3), dtype=torch.float32)
+    perm2, sh2, _, dense2 = sy2.collider.partition(st, sy2)
+    assert not bool(dense2) and torch.equal(perm, perm2) and torch.equal(sh, sh2)
+    sy.collider.compute_force(st, sy)
+    f = st.force.double()
+    assert float(f.abs().max()) > 0
+    assert float(f.sum(0).abs().max()) < 1e-3 * float(f.abs().sum(0).max())  # Newton's third law
+    f1 = st.force.clone()
+    sy.collider.compute_force(st, sy)
+    assert torch.equal(f1, st.force)  # deterministic: bitwise repeatable
+    p0 = (st.vel.double() * st.mass.double()[:, None]).sum(0)
+    jd.System.step(st, sy, n=5)
+    p1 = (st.vel.double() * st.mass.double()[:, None]).sum(0)
+    assert float((p1 - p0).abs().max()) < 1e-2  # momentum conserved

@@ -1,0 +1,114 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the host
+mirror of the plugin API behaves like the reference's, and the product path refuses to
+run without CUDA.  No compute calls (there is no GPU here)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import jaxdem_b200 as jd
+from jaxdem_b200 import _call, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "jaxdem_b200.h")).read()
+    declared = set(re.findall(r"JDB200_API\s+[\w\s]+?\b(jdb200_\w+)\s*\(", header))
+    assert declared and declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.jdb200_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header():
+    header = open(os.path.join(ROOT, "include", "jaxdem_b200.h")).read()
+    body = re.search(r"typedef struct jdb200_params \{(.*?)\} jdb200_params;", header, re.S).group(1)
+    names = re.findall(r"int(?:32|64)_t\s+(\w+);", body)
+    assert names == [f[0] for f in _lib.Params._fields_]
+    for struct, tag in ((_lib.StateView, "jdb200_state"), (_lib.SystemView, "jdb200_system")):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (tag, tag), header, re.S).group(1)
+        names = re.findall(r"void\*\s+(\w+);", body)
+        assert names == [f[0] for f in struct._fields_], tag
+
+
+def test_workspace_bytes_and_argument_errors():
+    lib = _lib.lib()
+    st = jd.utils.grid_state(n_per_axis=(6, 6, 6), spacing=1.0, radius=0.5, device="cpu")
+    sy = jd.System.create(st.shape, collider_type="CellList", collider_kw=dict(state=st), domain_type="periodic",
+                          domain_kw=dict(box_size=[6.0] * 3), device="cpu")
+    p = _call.params_for(st, sy)
+    small = lib.jdb200_workspace_bytes(ctypes.byref(p))
+    assert small > 0
+    p.n = 1 << 20
+    p.max_cells = 4 << 20
+    big = lib.jdb200_workspace_bytes(ctypes.byref(p))
+    assert 64e6 < big < 1e9
+    p.dim = 4
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
+    sv, yv = _lib.StateView(), _lib.SystemView()
+    assert lib.jdb200_celllist_compute_force(None, ctypes.byref(p), ctypes.byref(sv), ctypes.byref(yv), None, 0) == -1
+    p.dim = 3
+    assert lib.jdb200_celllist_compute_force(None, ctypes.byref(p), ctypes.byref(sv), ctypes.byref(yv), None, 0) == -2
+    buf = ctypes.create_string_buffer(16)
+    assert lib.jdb200_celllist_compute_force(None, ctypes.byref(p), ctypes.byref(sv), ctypes.byref(yv), buf, 16) == -3
+
+
+def test_no_cpu_fallback():
+    st = jd.utils.grid_state(n_per_axis=(4, 4), spacing=1.0, radius=0.5, device="cpu")
+    sy = jd.System.create(st.shape, collider_type="CellList", collider_kw=dict(state=st), device="cpu")
+    for fn in (lambda: jd.System.step(st, sy, n=1), lambda: sy.collider.compute_force(st, sy),
+               lambda: sy.force_manager.apply(st, sy), lambda: sy.linear_integrator.step_before_force(st, sy)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn()
+
+
+def test_registry_keys_and_normalisation():
+    # reference tests/test_public_api.py:24-35
+    assert type(jd.Collider.create("cell_list", state=jd.State.create(np.zeros((3, 2)), device="cpu"))).__name__ == "DynamicCellList"
+    assert jd.Collider.create("Cell-List", state=jd.State.create(np.zeros((3, 2)), device="cpu")).type_name == "celllist"
+    assert jd.LinearIntegrator.create("Verlet").type_name == "verlet"
+    assert jd.RotationIntegrator.create("verlet_spiral").type_name == "verletspiral"
+    assert jd.Domain.create("Periodic", dim=2).periodic and not jd.Domain.create("reflect", dim=2).periodic
+    assert jd.ForceModel.create("cundall strack").type_name == "cundallstrack"
+    with pytest.raises(KeyError):
+        jd.Collider.create("nope")
+    with pytest.warns(UserWarning):
+        jd.LinearIntegrator.create("verlet", bogus=1)
+    with pytest.raises(ValueError):
+        jd.Domain.create("periodic", dim=3, box_size=[1.0, 1.0])
+    # separate registries per root
+    assert "verlet" in jd.LinearIntegrator._registry and "verlet" not in jd.RotationIntegrator._registry
+
+
+def test_state_create_defaults():
+    # reference State.create defaults (state.py:647-867)
+    st = jd.State.create(np.zeros((5, 3)), rad=[1, 2, 1, 1, 1], clump_id=[7, 7, 3, 9, 9],
+                         bond_id=[[1], [], [4], [], []], device="cpu")
+    assert st.clump_id.tolist() == [1, 1, 0, 2, 2] and st.has_clumps
+    assert st.bond_id.tolist() == [[1], [0], [4], [-1], [2]]
+    assert st.q.w.shape == (5, 1) and st.q.xyz.shape == (5, 3) and st.ang_vel.shape == (5, 3)
+    np.testing.assert_allclose(st.inertia[1].numpy(), 0.4 * 1.0 * 4.0)
+    assert st.dtype == torch.float32 and st.clump_id.dtype == torch.int32 and st.fixed.dtype == torch.bool
+    st2 = jd.State.create(np.zeros((4, 2)), dtype=torch.float64, device="cpu")
+    assert st2.ang_vel.shape == (4, 1) and st2.clump_id.dtype == torch.int64 and not st2.has_clumps
+    st2.q = jd.Quaternion(torch.full((4, 1), np.cos(0.3)), torch.tensor([[0, 0, np.sin(0.3)]] * 4))
+    assert st2._pos_p_rot.shape == (4, 2)  # cache refreshed on assignment (state.py:264-273)
+
+
+def test_celllist_create_matches_oracle_create():
+    import oracle
+    from oracle import colliders as ocol
+    rng = np.random.default_rng(0)
+    for poly, box in ((1.0, None), (3.0, None), (1.2, [2.5, 2.5, 2.5])):
+        rad = rng.uniform(0.5 / poly, 0.5, 50)
+        ost = oracle.create_state(rng.uniform(0, 5, (50, 3)), rad=rad, dtype=np.float32)
+        oc = ocol.celllist_create(ost, box_size=box)
+        gc = jd.Collider.create("CellList", state=jd.State.create(ost.pos_c, rad=rad, device="cpu"), box_size=box)
+        assert np.array_equal(gc.neighbor_mask.numpy(), oc.neighbor_mask)
+        assert float(gc.cell_size) == float(oc.cell_size)
