@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the DEM step hot path (BASELINE.json: particle-steps/s at 1M 3D spheres).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): N = 2**20 monodisperse spheres
+(r = 0.5) in a periodic cube at packing fraction 0.5, jittered simple-cubic packing,
+spring contacts (young_eff 1e4), velocity Verlet, cell-list collider, float32/int32.
+A "step" is one System.step (one _step_once, jaxdem/system.py:60-82) over all particles.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally
+``roofline`` (dominant kernel), ``step_roofline`` (whole step, 168 algorithmic bytes per
+particle-step), ``cpu_baseline`` and ``kernels`` (per-kernel device time of one step).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PARTICLES = 1 << 20
+B_ALG_STEP = 168.0  # algorithmic bytes per particle-step, config 2
+# algorithmic bytes per particle of each kernel family
+B_ALG_KERNEL = {
+    "k_pair_force": 28.0,   # R pos 12 + rad 4, W force 12
+}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def make_workload(n=N_PARTICLES, seed=1, phi=0.5, dtype=np.float32, packing="grid"):
+    """jittered simple-cubic ("grid") or uniform random ("random") packing."""
+    rng = np.random.default_rng(seed)
+    r = 0.5
+    L = (n * (4.0 / 3.0) * np.pi * r**3 / phi) ** (1.0 / 3.0)
+    if packing == "grid":
+        g = int(np.ceil(n ** (1.0 / 3.0)))
+        sites = rng.permutation(g**3)[:n]
+        sites.sort()
+        ijk = np.stack(np.unravel_index(sites, (g, g, g)), axis=1).astype(np.float64)
+        pos = (ijk + 0.5) * (L / g) + rng.uniform(-0.1, 0.1, (n, 3)) * r
+        order = rng.permutation(n)  # particle index carries no spatial order
+        pos = pos[order]
+    else:
+        pos = rng.uniform(0, L, (n, 3))
+    vel = rng.uniform(-1, 1, (n, 3))
+    return dict(pos=pos.astype(dtype), vel=vel.astype(dtype), rad=np.full(n, r, dtype),
+                mass=np.ones(n, dtype), box=np.full(3, L, dtype))
+
+
+# ---------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except (OSError, ValueError):
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# CPU restatement of the reference path (oracle/c, OpenMP)
+# ---------------------------------------------------------------------------
+def cpu_steps_per_s(wl, steps, warmup=1, threads=None):
+    """Time `steps` System.step's of the SAME workload on the host cores with the C/OpenMP
+    restatement of the reference algorithm (oracle/c): stable sort of (hash, iota), 27
+    binary searches per particle, run walk, spring law, velocity Verlet."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import build_oracle
+    from oracle import c_oracle
+    if threads:
+        c_oracle.set_num_threads(threads)
+    dtype = wl["pos"].dtype.type
+    # default material of System.create: elastic(young 1e4, poisson 0.3) harmonic -> young_eff 1e4
+    import oracle
+    st = oracle.create_state(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=dtype)
+    sy = oracle.create_system(st, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                              collider_type="celllist", domain_type="periodic",
+                              domain_kw=dict(box_size=wl["box"]), force_model_type="spring")
+    cs = c_oracle.CStep(st, sy)
+    cs.step(warmup)
+    t0 = time.perf_counter()
+    cs.step(steps)
+    dt = time.perf_counter() - t0
+    return st.N * steps / dt, dt, c_oracle.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(packing=args.packing)
+    n = wl["pos"].shape[0]
+    # bounded sample: each "step" of this arm is one full 1M-particle step on the host cores
+    steps = max(1, min(args.steps, 20))
+    rate, secs, cores = cpu_steps_per_s(wl, steps, warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec at 1M 3D spheres", "value": rate,
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full steps of the 1M-sphere workload, C/OpenMP restatement of the "
+                                   "reference cell-list path (JAX is not installed in this image: the reference "
+                                   "itself cannot run)"},
+        "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": f"C2: {n} monodisperse 3D spheres r=0.5, periodic cube phi=0.5, {args.packing} packing, "
+                        "cell-list collider (27-cell stencil), spring contact young_eff=1e4, velocity Verlet, dt=1e-3",
+            "n_particles": n, "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": "1 system per GPU (replicas)" if args.gpus > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    import jaxdem_b200 as jd
+    from jaxdem_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: jaxdem_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = make_workload(seed=1 + rank, packing=args.packing)
+    n = wl["pos"].shape[0]
+    st = jd.State.create(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=torch.float32, device=dev)
+    sy = jd.System.create(st.shape, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                          collider_type="CellList", collider_kw=dict(state=st), domain_type="periodic",
+                          domain_kw=dict(box_size=wl["box"]), force_model_type="spring",
+                          dtype=torch.float32, device=dev)
+    lib = _lib.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = jd.System.compile_step(st, sy, n=1) if args.graph else (lambda: jd.System.step(st, sy, n=1))
+    jd.System.step(st, sy, n=1)  # first force evaluation (loop-carried state.force)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed: K steps, each bracketed by events, L2 flushed in between ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = lib.jdb200_launch_count()
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    barrier()
+    launches = lib.jdb200_launch_count() - l0
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    if args.graph:  # graph replays do not pass through the counter: one capture's worth per replay
+        launches = args.steps * step_launches(jd, st, sy, lib)
+    # steady state without the flush (what a real rollout sees): K steps in ONE call
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    jd.System.step(st, sy, n=args.steps)
+    b.record()
+    torch.cuda.synchronize()
+    ms_warm = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, every step ----
+    fields = ("pos_c", "vel", "force")
+    host_in = {k: getattr(st, k).detach().cpu().pin_memory() for k in fields}
+    host_out = {k: torch.empty_like(v).pin_memory() for k, v in host_in.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        for k in fields:
+            getattr(st, k).copy_(host_in[k], non_blocking=True)
+        jd.System.step(st, sy, n=1)
+        for k in fields:
+            host_out[k].copy_(getattr(st, k), non_blocking=True)
+        torch.cuda.synchronize()
+        for k in fields:  # next step's input is this step's output (a rollout driven from the host)
+            host_in[k], host_out[k] = host_out[k], host_in[k]
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+
+    # ---- per-kernel device time of the step (diagnostic events; separate pass) ----
+    _lib.kernel_timing(True)
+    prof_steps = 5
+    for _ in range(prof_steps):
+        flush.fill_(1)
+        jd.System.step(st, sy, n=1)
+    torch.cuda.synchronize()
+    kt = _lib.kernel_timing_collect()
+    _lib.kernel_timing(False)
+    kernels = {k: {"us_per_launch": 1e3 * v[0] / v[1], "launches_per_step": v[1] / prof_steps,
+                   "us_per_step": 1e3 * v[0] / prof_steps} for k, v in kt.items()}
+    tot = sum(v["us_per_step"] for v in kernels.values())
+    for v in kernels.values():
+        v["share"] = v["us_per_step"] / tot if tot else 0.0
+    peak, peak_src = measured_peak()
+    dom = max(kernels, key=lambda k: kernels[k]["us_per_step"]) if kernels else None
+    roof = None
+    if dom is not None:
+        bpp = B_ALG_KERNEL.get(dom)
+        dur_s = kernels[dom]["us_per_launch"] * 1e-6
+        ach = (bpp * n / dur_s / 1e9) if bpp else None
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": None,
+                "algorithmic_bytes_per_launch": (bpp * n) if bpp else None,
+                "us_per_launch": kernels[dom]["us_per_launch"], "peak_source": peak_src}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(dom)
+            except (OSError, ValueError):
+                pass
+    step_gbs = B_ALG_STEP * n * args.steps / (ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": "particle-steps/sec at 1M 3D spheres", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, n), launch="cuda-graph replay" if args.graph else "stream launches"),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": h2d, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak, "algorithmic_bytes_per_particle_step": B_ALG_STEP,
+                              "peak_source": peak_src},
+            "l2_warm": {"value": n * args.steps / (ms_warm * 1e-3), "unit": "particle-steps/s",
+                        "ms_per_step": ms_warm / args.steps,
+                        "note": "same K steps back to back in one jdb200_system_step call, no L2 flush"},
+            "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu:
+            cpu_steps = args.cpu_steps
+            rate, secs, cores = cpu_steps_per_s(wl, cpu_steps)
+            line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cpu_steps} full steps of the same 1M-sphere workload "
+                                              f"({secs:.1f} s), C/OpenMP restatement (oracle/c)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def step_launches(jd, st, sy, lib):
+    """Kernels one step launches (counted on a throw-away stream-launched step)."""
+    import torch
+    c0 = lib.jdb200_launch_count()
+    jd.System.step(st, sy, n=1)
+    torch.cuda.synchronize()
+    return lib.jdb200_launch_count() - c0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--packing", default="grid", choices=["grid", "random"])
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (System.compile_step)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -216,6 +216,15 @@ JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jd
  * bench.py's `gpu_launches`; relaxed atomic, not part of the data path). */
 JDB200_API int64_t jdb200_launch_count(void);
 
+/* Diagnostic per-kernel device timing for bench.py's roofline (no reference equivalent;
+ * the reference's benchmarks/run_benchmarks.py:27-51 times whole hooks with timeit).
+ * While enabled, every kernel launch is bracketed by CUDA events on its stream (this
+ * mode is NOT graph-capture safe and is off by default).  jdb200_timing_collect waits
+ * for the recorded events, sums device milliseconds and launch counts per kernel name
+ * (names: max_entries x 64 chars), clears the records and returns the number of names. */
+JDB200_API int jdb200_timing_enable(int on);
+JDB200_API int jdb200_timing_collect(int max_entries, char* names, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

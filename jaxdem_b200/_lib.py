@@ -71,6 +71,8 @@ SYMBOLS = {
     "jdb200_rotation_step_after_force": (C.c_int, [_V, _PP, _PS, _PY]),
     "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
+    "jdb200_timing_enable": (C.c_int, [C.c_int]),
+    "jdb200_timing_collect": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -96,3 +98,18 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed: {ERRORS.get(rc, rc)}")
+
+
+def kernel_timing(enable: bool) -> None:
+    """Diagnostic: bracket every kernel launch with CUDA events (bench.py roofline)."""
+    lib().jdb200_timing_enable(1 if enable else 0)
+
+
+def kernel_timing_collect(max_entries: int = 64) -> dict:
+    """-> {kernel name: (total device ms, launches)} since the last collect."""
+    names = C.create_string_buffer(64 * max_entries)
+    ms = (C.c_double * max_entries)()
+    cnt = (C.c_int64 * max_entries)()
+    n = lib().jdb200_timing_collect(max_entries, names, ms, cnt)
+    raw = names.raw
+    return {raw[i * 64:(i + 1) * 64].split(b"\0", 1)[0].decode(): (ms[i], int(cnt[i])) for i in range(n)}

@@ -1,11 +1,39 @@
 // jaxdem_b200 — extern "C" entry points (include/jaxdem_b200.h) and the fused
 // n-step driver replacing _step_once / System.step (jaxdem/system.py:60-98,701-748).
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "ctx.cuh"
 #include "launch.cuh"
 
 namespace jdb {
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_timing{0};
+
+// ---- diagnostic per-kernel timing (bench.py roofline; never on in production) ----
+struct TimingRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_timing_mu;
+static std::vector<TimingRec> g_timing_recs;
+
+void timing_begin(const char* name, cudaStream_t s) {
+  TimingRec r{name, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, s);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing_recs.push_back(r);
+}
+void timing_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  cudaEventRecord(g_timing_recs.back().e1, s);
+}
 
 template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*);
 template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, bool);
@@ -130,6 +158,41 @@ extern "C" {
 JDB200_API int jdb200_abi_version(void) { return JDB200_ABI_VERSION; }
 
 JDB200_API int64_t jdb200_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+JDB200_API int jdb200_timing_enable(int on) {
+  g_timing.store(on ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
+
+JDB200_API int jdb200_timing_collect(int max_entries, char* names, double* total_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  std::map<std::string, std::pair<double, int64_t>> acc;
+  std::vector<std::string> order;
+  for (auto& r : g_timing_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess) cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    std::string nm(r.name);
+    size_t a = nm.find_first_not_of("( ");
+    size_t b = nm.find_first_of("<) ", a);
+    nm = nm.substr(a, b == std::string::npos ? b : b - a);
+    if (!acc.count(nm)) order.push_back(nm);
+    acc[nm].first += ms;
+    acc[nm].second += 1;
+  }
+  g_timing_recs.clear();
+  int n = 0;
+  for (auto& nm : order) {
+    if (n >= max_entries) break;
+    std::strncpy(names + (size_t)n * 64, nm.c_str(), 63);
+    names[(size_t)n * 64 + 63] = 0;
+    total_ms[n] = acc[nm].first;
+    launches[n] = acc[nm].second;
+    ++n;
+  }
+  return n;
+}
 
 JDB200_API size_t jdb200_workspace_bytes(const jdb200_params* p) {
   if (check_params(p)) return 0;

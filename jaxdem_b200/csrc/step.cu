@@ -548,15 +548,14 @@ struct ReflectLocal {
   F denom[3], vcs[3], accc[3];
 };
 
-template <typename F>
+template <typename F, int D>
 __device__ __forceinline__ void reflect_local(const Ctx<F>& c, int b, size_t gi, ReflectLocal<F>& L,
                                               F* Rm /*3x3 rows = n_prime*/) {
   // per-sphere quantities that do not depend on clump reductions (reflect.py:165-226)
   using T = RT<F>;
-  const int D = c.dim;
   const F rad = c.rad[gi];
   F ppl[3] = {0, 0, 0}, pp[3] = {0, 0, 0};
-  for (int d = 0; d < D; ++d) {
+  _Pragma("unroll") for (int d = 0; d < D; ++d) {
     ppl[d] = c.pos_p_rot[gi * D + d];
     pp[d] = c.pos_p[gi * D + d];
     const F pos = T::add(c.pos_c[gi * D + d], ppl[d]);
@@ -632,18 +631,17 @@ __device__ __forceinline__ void reflect_local(const Ctx<F>& c, int b, size_t gi,
 
 // Impulse of one sphere given clump-level maxima / alpha / active counts; returns the
 // per-sphere contributions j*inv_mass (dv) and d_omega_lab (reflect.py:239-276).
-template <typename F>
+template <typename F, int D>
 __device__ __forceinline__ void reflect_impulse(const Ctx<F>& c, int b, size_t gi,
                                                 const ReflectLocal<F>& L, const F* Rm,
                                                 const F* active, const F* wall_sign,
                                                 const F* count_active, F alpha_clump, F* dv, F* dom) {
   using T = RT<F>;
-  const int D = c.dim;
   const F dt = c.dt[b], e = c.restitution[b];
   const F inv_mass = T::div(F(1), c.mass[gi]);
   const F dt_factor = T::mul(T::sub(alpha_clump, F(1)), dt);
   F jm[3] = {0, 0, 0};
-  for (int d = 0; d < D; ++d) {
+  _Pragma("unroll") for (int d = 0; d < D; ++d) {
     const F vc = T::add(L.vcs[d], T::mul(dt_factor, L.accc[d]));
     F j = T::div(T::mul(-T::add(F(1), e), vc), L.denom[d]);
     const F closing = T::mul(vc, wall_sign[d]) < F(0) ? F(1) : F(0);
@@ -676,11 +674,10 @@ __device__ __forceinline__ void reflect_impulse(const Ctx<F>& c, int b, size_t g
 }
 
 // final state update for one sphere (reflect.py:254-297)
-template <typename F>
+template <typename F, int D>
 __device__ __forceinline__ void reflect_update(const Ctx<F>& c, int b, size_t gi, const F* dv_in,
                                                const F* dom_in, F alpha_clump) {
   using T = RT<F>;
-  const int D = c.dim;
   const bool fixed = c.fixed[gi] != 0;
   const F dt_rem = T::mul(T::sub(F(1), alpha_clump), c.dt[b]);
   F dv[3], dom[3];
@@ -688,7 +685,7 @@ __device__ __forceinline__ void reflect_update(const Ctx<F>& c, int b, size_t gi
     dv[d] = fixed ? F(0) : dv_in[d];
     dom[d] = fixed ? F(0) : dom_in[d];
   }
-  for (int d = 0; d < D; ++d) c.vel[gi * D + d] = T::add(c.vel[gi * D + d], dv[d]);
+  _Pragma("unroll") for (int d = 0; d < D; ++d) c.vel[gi * D + d] = T::add(c.vel[gi * D + d], dv[d]);
   V3<F> dth;
   if (D == 3) {
     for (int a = 0; a < 3; ++a) c.ang_vel[gi * 3 + a] = T::add(c.ang_vel[gi * 3 + a], dom[a]);
@@ -699,11 +696,11 @@ __device__ __forceinline__ void reflect_update(const Ctx<F>& c, int b, size_t gi
   }
   const Q4<F> q = xqunit(xqmul(xsmall(dth), load_q(c, gi)));  // LEFT multiply (reflect.py:293)
   store_q_and_cache(c, gi, q);
-  for (int d = 0; d < D; ++d)
+  _Pragma("unroll") for (int d = 0; d < D; ++d)
     c.pos_c[gi * D + d] = T::add(c.pos_c[gi * D + d], T::mul(dv[d], dt_rem));
 }
 
-template <typename F>
+template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
   using T = RT<F>;
   const int b = blockIdx.y;
@@ -712,11 +709,11 @@ __global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
   const size_t gi = (size_t)b * c.n + i;
   ReflectLocal<F> L;
   F Rm[9];
-  reflect_local(c, b, gi, L, Rm);
+  reflect_local<F, D>(c, b, gi, L, Rm);
   F active[3] = {0, 0, 0}, ws[3] = {0, 0, 0}, cnt[3] = {0, 0, 0};
   F amin = F(1);
   const F dt = c.dt[b];
-  for (int d = 0; d < c.dim; ++d) {
+  _Pragma("unroll") for (int d = 0; d < D; ++d) {
     // own clump: max_lo == over_lo, so "deepest" reduces to over > 0
     const F wsd = T::sub(L.over_lo[d] > F(0) ? F(1) : F(0), L.over_hi[d] > F(0) ? F(1) : F(0));
     ws[d] = wsd;
@@ -727,12 +724,12 @@ __global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
     if (active[d] > F(0)) amin = T::fmin(amin, al);
   }
   F dv[3] = {0, 0, 0}, dom[3] = {0, 0, 0};
-  reflect_impulse(c, b, gi, L, Rm, active, ws, cnt, amin, dv, dom);
-  reflect_update(c, b, gi, dv, dom, amin);
+  reflect_impulse<F, D>(c, b, gi, L, Rm, active, ws, cnt, amin, dv, dom);
+  reflect_update<F, D>(c, b, gi, dv, dom, amin);
 }
 
 // general clumps: 4 phases through scratch (segf, 8 F per sphere + seg2, 8 F per sphere)
-template <typename F>
+template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {  // over_lo / over_hi
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -740,14 +737,14 @@ __global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {  // over_lo / ov
   const size_t gi = (size_t)b * c.n + i;
   ReflectLocal<F> L;
   F Rm[9];
-  reflect_local(c, b, gi, L, Rm);
+  reflect_local<F, D>(c, b, gi, L, Rm);
   F* o = c.segf + gi * 8;
   for (int d = 0; d < 3; ++d) {
-    o[d] = d < c.dim ? L.over_lo[d] : F(0);
-    o[3 + d] = d < c.dim ? L.over_hi[d] : F(0);
+    o[d] = d < D ? L.over_lo[d] : F(0);
+    o[3 + d] = d < D ? L.over_hi[d] : F(0);
   }
 }
-template <typename F>
+template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F* seg2) {
   // clump maxima -> wall_sign / active / alpha_min_dim per sphere
   using T = RT<F>;
@@ -767,13 +764,13 @@ __global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F
   }
   ReflectLocal<F> L;
   F Rm[9];
-  reflect_local(c, b, gi, L, Rm);
+  reflect_local<F, D>(c, b, gi, L, Rm);
   const F dt = c.dt[b];
   F amin = F(1);
   F* o2 = seg2 + gi * 8;
   for (int d = 0; d < 3; ++d) {
     F wsd = F(0);
-    if (d < c.dim) {
+    if (d < D) {
       const bool dlo = L.over_lo[d] > F(0) && L.over_lo[d] == mlo[d];
       const bool dhi = L.over_hi[d] > F(0) && L.over_hi[d] == mhi[d];
       wsd = T::sub(dlo ? F(1) : F(0), dhi ? F(1) : F(0));
@@ -785,7 +782,7 @@ __global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F
   }
   o2[3] = amin;
 }
-template <typename F>
+template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, const F* seg2) {
   // clump alpha / active counts -> per-sphere impulse contributions (into segf)
   using T = RT<F>;
@@ -803,12 +800,12 @@ __global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, c
   }
   ReflectLocal<F> L;
   F Rm[9];
-  reflect_local(c, b, gi, L, Rm);
+  reflect_local<F, D>(c, b, gi, L, Rm);
   const F* mine = seg2 + gi * 8;
   F ws[3] = {mine[0], mine[1], mine[2]};
   F active[3] = {T::abs(ws[0]), T::abs(ws[1]), T::abs(ws[2])};
   F dv[3] = {0, 0, 0}, dom[3] = {0, 0, 0};
-  reflect_impulse(c, b, gi, L, Rm, active, ws, cnt, alpha, dv, dom);
+  reflect_impulse<F, D>(c, b, gi, L, Rm, active, ws, cnt, alpha, dv, dom);
   F* o = c.segf + gi * 8;
   for (int d = 0; d < 3; ++d) {
     o[d] = dv[d];
@@ -816,7 +813,7 @@ __global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, c
   }
   o[6] = alpha;
 }
-template <typename F>
+template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p4(Ctx<F> c, ClumpCsr<F> csr) {
   using T = RT<F>;
   const int b = blockIdx.y;
@@ -833,7 +830,24 @@ __global__ void __launch_bounds__(128) k_reflect_p4(Ctx<F> c, ClumpCsr<F> csr) {
       dom[d] = T::add(dom[d], o[3 + d]);
     }
   }
-  reflect_update(c, b, gi, dv, dom, c.segf[gi * 8 + 6]);
+  reflect_update<F, D>(c, b, gi, dv, dom, c.segf[gi * 8 + 6]);
+}
+
+template <typename F, int D>
+int reflect_apply(cudaStream_t s, Ctx<F>& c) {
+  const dim3 gp(cdiv(c.n, 128), c.batch);
+  if (!c.clumps) {
+    JDB_LAUNCH((k_reflect_spheres<F, D>), gp, 128, s, c);
+  } else {
+    ClumpCsr<F> csr;
+    int rc = build_clump_csr<F>(s, c, &csr);
+    if (rc) return rc;
+    JDB_LAUNCH((k_reflect_p1<F, D>), gp, 128, s, c);
+    JDB_LAUNCH((k_reflect_p2<F, D>), gp, 128, s, c, csr, c.segf2);
+    JDB_LAUNCH((k_reflect_p3<F, D>), gp, 128, s, c, csr, c.segf2);
+    JDB_LAUNCH((k_reflect_p4<F, D>), gp, 128, s, c, csr);
+  }
+  return 0;
 }
 
 template <typename F>
@@ -844,18 +858,7 @@ int domain_apply(cudaStream_t s, Ctx<F>& c) {
     JDB_LAUNCH(k_free_partial<F>, dim3(nb, c.batch), 256, s, c, c.segf);
     JDB_LAUNCH(k_free_final<F>, dim3(c.batch), 256, s, c, c.segf, nb);
   } else if (c.domain == JDB200_DOMAIN_REFLECT) {
-    const dim3 gp(cdiv(c.n, 128), c.batch);
-    if (!c.clumps) {
-      JDB_LAUNCH(k_reflect_spheres<F>, gp, 128, s, c);
-    } else {
-      ClumpCsr<F> csr;
-      int rc = build_clump_csr<F>(s, c, &csr);
-      if (rc) return rc;
-      JDB_LAUNCH(k_reflect_p1<F>, gp, 128, s, c);
-      JDB_LAUNCH(k_reflect_p2<F>, gp, 128, s, c, csr, c.segf2);
-      JDB_LAUNCH(k_reflect_p3<F>, gp, 128, s, c, csr, c.segf2);
-      JDB_LAUNCH(k_reflect_p4<F>, gp, 128, s, c, csr);
-    }
+    return c.dim == 3 ? reflect_apply<F, 3>(s, c) : reflect_apply<F, 2>(s, c);
   }
   return 0;
 }

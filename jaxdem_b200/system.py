@@ -122,6 +122,13 @@ class System:
         return state, system
 
     @staticmethod
+    def compile_step(state: State, system: "System", *, n: int = 1) -> "CompiledStep":
+        """The counterpart of ``jax.jit(System.step)``: capture ``n`` steps into a CUDA graph
+        (every C-ABI entry point is stream-ordered and capture-legal, include/jaxdem_b200.h)
+        and return a callable that replays it on the current stream."""
+        return CompiledStep(state, system, int(n))
+
+    @staticmethod
     def trajectory_rollout(state: State, system: "System", *, n: int, stride: int = 1, strides=None,
                            save_fn: Callable | None = None):
         """System.trajectory_rollout (system.py:606-699): n frames, each saved AFTER
@@ -141,3 +148,24 @@ class System:
         else:
             traj = frames
         return state, system, traj
+
+
+class CompiledStep:
+    """``n`` fused steps captured once in a CUDA graph; ``__call__`` replays them in place on
+    the same State / System buffers (pointers are baked into the graph)."""
+
+    def __init__(self, state: State, system: System, n: int):
+        if not system._is_native():
+            raise RuntimeError("compile_step needs native components and identity user hooks")
+        self.state, self.system, self.n = state, system, n
+        _call.require_cuda(state)
+        _call.workspace(_call.params_for(state, system), state.device)  # allocate before capture
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=state.device)
+        side.wait_stream(torch.cuda.current_stream(state.device))
+        with torch.cuda.graph(self.graph, stream=side):
+            System.step(state, system, n=n, fused=True)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.state, self.system
