@@ -89,7 +89,7 @@ class MaterialTable:
         raise AttributeError(item)
 
     def __len__(self) -> int:
-        return int(next(iter(self.props.values())).shape[0])
+        return int(next(iter(self.props.values())).shape[-1])  # (M,) or batched (B, M)
 
     def to(self, device=None, dtype=None) -> "MaterialTable":
         f = lambda t: t.to(device=device, dtype=dtype).contiguous()

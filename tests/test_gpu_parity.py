@@ -343,6 +343,41 @@ def test_full_size_properties_1m():
     sy.collider.compute_force(st, sy)
     assert torch.equal(f1, st.force)  # deterministic: bitwise repeatable
     p0 = (st.vel.double() * st.mass.double()[:, None]).sum(0)
+    pabs = float((st.vel.double().abs() * st.mass.double()[:, None]).sum())
     jd.System.step(st, sy, n=5)
     p1 = (st.vel.double() * st.mass.double()[:, None]).sum(0)
-    assert float((p1 - p0).abs().max()) < 1e-2  # momentum conserved
+    # momentum conserved up to float32 rounding of 1M velocity updates (the float64 CPU
+    # oracle conserves it to 1e-11; the float32 oracle drifts by the same 0.58 as the kernels)
+    assert float((p1 - p0).abs().max()) < 1e-5 * pabs
+
+
+def test_full_size_parity_vs_c_oracle_1m():
+    """BASELINE config 2 at FULL size (2**20 spheres, bench.py's workload): the CUDA path
+    against the C/OpenMP restatement of the reference — cell permutation and sorted hashes
+    bit for bit, forces / velocities / positions to rel 1e-5 per step (float32)."""
+    import jaxdem_b200 as jd
+    import bench
+    from oracle import c_oracle
+    wl = bench.make_workload()
+    ost = oracle.create_state(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=np.float32)
+    osy = oracle.create_system(ost, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                               collider_type="celllist", domain_type="periodic",
+                               domain_kw=dict(box_size=wl["box"]), force_model_type="spring")
+    gst = jd.State.create(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=torch.float32)
+    gsy = jd.System.create(gst.shape, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                           collider_type="CellList", collider_kw=dict(state=gst), domain_type="periodic",
+                           domain_kw=dict(box_size=wl["box"]), force_model_type="spring", dtype=torch.float32)
+    cs = c_oracle.CStep(ost, osy)
+    cperm, csh, _ = cs.partition()
+    perm, sh, _, _ = gsy.collider.partition(gst, gsy)
+    assert np.array_equal(perm.cpu().numpy(), cperm) and np.array_equal(sh.cpu().numpy(), csh)
+    cs.compute_force()
+    gsy.collider.compute_force(gst, gsy)
+    assert float(gst.force.abs().max()) > 100.0
+    assert_close(gst.force, ost.force, np.float32, "force")
+    n_steps = 3
+    cs.step(n_steps)
+    jd.System.step(gst, gsy, n=n_steps)
+    for f in ("pos_c", "vel", "force"):
+        assert_close(getattr(gst, f), getattr(ost, f), np.float32, f, factor=float(n_steps))
+    assert not bool(gsy.collider.overflow)
