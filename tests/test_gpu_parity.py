@@ -375,9 +375,15 @@ def test_full_size_parity_vs_c_oracle_1m():
     gsy.collider.compute_force(gst, gsy)
     assert float(gst.force.abs().max()) > 100.0
     assert_close(gst.force, ost.force, np.float32, "force")
-    n_steps = 3
-    cs.step(n_steps)
-    jd.System.step(gst, gsy, n=n_steps)
-    for f in ("pos_c", "vel", "force"):
-        assert_close(getattr(gst, f), getattr(ost, f), np.float32, f, factor=float(n_steps))
+    # per-step parity on the SAME inputs (north_star): after every step the CUDA state is
+    # re-synchronised to the oracle's, because at 1M stiff contacts in float32 a 1-ulp
+    # difference in one position (7.6e-6 at x ~ 100) changes that particle's contact forces
+    # by k * ulp ~ 0.08 and the two trajectories then separate chaotically
+    for _ in range(3):
+        for f in ("pos_c", "vel", "force"):
+            getattr(gst, f).copy_(torch.as_tensor(getattr(ost, f)))
+        cs.step(1)
+        jd.System.step(gst, gsy, n=1)
+        for f in ("pos_c", "vel", "force"):
+            assert_close(getattr(gst, f), getattr(ost, f), np.float32, f)
     assert not bool(gsy.collider.overflow)
