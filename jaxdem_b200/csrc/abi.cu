@@ -35,13 +35,14 @@ void timing_end(cudaStream_t s) {
   cudaEventRecord(g_timing_recs.back().e1, s);
 }
 
-template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*);
-template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, bool);
+template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*, int, bool);
+template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, int, bool, bool);
 template <typename F> int celllist_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int celllist_neighbor_list(cudaStream_t, Ctx<F>&, const F*, typename RT<F>::I*, uint8_t*);
 template <typename F> int naive_force(cudaStream_t, Ctx<F>&);
 template <typename F> int naive_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int force_manager_apply(cudaStream_t, Ctx<F>&);
+template <typename F> int fm_after_fused(cudaStream_t, Ctx<F>&, bool);
 template <typename F> int domain_apply(cudaStream_t, Ctx<F>&);
 template <typename F> int refresh_inv_box(cudaStream_t, Ctx<F>&);
 template <typename F> int linear_before(cudaStream_t, Ctx<F>&);
@@ -90,7 +91,8 @@ template <typename F>
 int partition_entry(cudaStream_t s, Ctx<F>& c, void* perm, void* sorted_hash, void* nbr_hash,
                     void* used_dense) {
   using I = typename RT<F>::I;
-  int rc = build_partition<F>(s, c, nullptr);
+  c.want_skey = 1;
+  int rc = build_partition<F>(s, c, nullptr, 0, false);
   if (rc || c.n == 0) return rc;
   JDB_LAUNCH(k_export_partition<F>, dim3(cdiv(c.n, 256), c.batch), 256, s, c, (I*)perm, (I*)sorted_hash,
              (I*)nbr_hash, (uint8_t*)used_dense);
@@ -99,7 +101,7 @@ int partition_entry(cudaStream_t s, Ctx<F>& c, void* perm, void* sorted_hash, vo
 
 template <typename F>
 int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
-  if (collider == JDB200_COLLIDER_CELLLIST) return celllist_force<F>(s, c, true);
+  if (collider == JDB200_COLLIDER_CELLLIST) return celllist_force<F>(s, c, 0, false, true);
   if (collider == JDB200_COLLIDER_NAIVE) return naive_force<F>(s, c);
   // "" no-op collider zeroes force and torque (colliders/__init__.py:56-88)
   if (c.n == 0) return 0;
@@ -114,6 +116,20 @@ template <typename F>
 int system_step(cudaStream_t s, Ctx<F>& c, int collider, long long n_steps) {
   int rc = 0;
   if (c.domain != JDB200_DOMAIN_FREE && n_steps > 0) rc = refresh_inv_box<F>(s, c);  // box is constant
+  // Fused flow for sphere systems (clump_id == arange), periodic box (domain.apply is a
+  // no-op), linear velocity Verlet, no rotation integrator: per step ONE partition build whose
+  // hash kernel also applies force manager + after-kick of the previous step and the
+  // before-kick + drift of this one, and ONE pair kernel.  Same arithmetic, same order per
+  // particle as the hook-by-hook sequence; the torque store is skipped on steps whose
+  // torque nothing can observe.
+  const bool fused = collider == JDB200_COLLIDER_CELLLIST && !c.clumps && c.lin == JDB200_LIN_VERLET &&
+                     c.rot == JDB200_ROT_NONE && c.domain == JDB200_DOMAIN_PERIODIC && c.n > 0;
+  if (fused && n_steps > 0 && !rc) {
+    for (long long it = 0; it < n_steps && !rc; ++it)
+      rc = celllist_force<F>(s, c, it == 0 ? 1 : 2, it == 1, it == n_steps - 1);
+    if (!rc) rc = fm_after_fused<F>(s, c, n_steps == 1);
+    return rc;
+  }
   for (long long it = 0; it < n_steps && !rc; ++it) {
     if ((rc = domain_apply<F>(s, c))) break;  // free: also refreshes inv_box_size
     if ((rc = linear_before<F>(s, c))) break;
@@ -216,7 +232,7 @@ JDB200_API int jdb200_celllist_partition(void* stream, const jdb200_params* p, c
 JDB200_API int jdb200_celllist_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
                                   const jdb200_system* sys, void* ws, size_t ws_bytes) {
   JDB_ENTER(true)
-  JDB_DISPATCH(celllist_force<F>(s, c, true))
+  JDB_DISPATCH(celllist_force<F>(s, c, 0, false, true))
 }
 
 JDB200_API int jdb200_celllist_compute_potential_energy(void* stream, const jdb200_params* p,

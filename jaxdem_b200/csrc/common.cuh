@@ -113,7 +113,11 @@ struct GridInfo {
   int dense;         // 1: dense cell table valid for this call, 0: sorted/binary search
   int dense_fail;    // set by kernels when the dense strategy cannot represent the data
   int nl_overflow;   // neighbour-list overflow accumulator
-  int pad;
+  int canonical;     // neighbor_mask == meshgrid(-R..R)^D ("ij", last axis fastest): x-run walk is legal
+  int range;         // R of the canonical stencil
+  int any_bond;      // some particle has a bond_id >= 0 (set by the hash kernel)
+  int any_ppr;       // some particle has a non-zero _pos_p_rot (set by the hash kernel)
+  int pad[3];
 };
 
 template <typename F, typename I>

@@ -10,6 +10,7 @@ struct Ctx {
   // static
   long long n;
   long long max_cells;
+  long long cell_stride;  // ints per system in the dense cell tables (max_cells + 1 rounded up to 64)
   int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
   // state (in place)
   F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;
@@ -27,7 +28,12 @@ struct Ctx {
   I* skey;                     // [B*N] sorted hashes
   int *perm, *perm_b, *perm_c; // [B*N] final perm + scratch
   int* rank;                   // [B*N] arrival rank inside the cell (dense)
-  int* cell_start;             // [B*(max_cells+1)] counts -> exclusive starts (dense)
+  int* cell_count;             // [B*(max_cells+1)] per-cell counts (dense; zeroed by every build)
+  int* cell_start;             // [B*(max_cells+1)] exclusive starts (dense)
+  int* tmp_key;                // [B*N] dense key of the particle in arrival slot k
+  Vec4<F>* upos;               // [B*N] (x, y, z, rad) in ORIGINAL order (pos = pos_c + pos_p_rot)
+  unsigned* coop_bar;          // [4] software state of the cooperative sort fallback
+  int want_skey;               // host flag: dense builds also fill skey (partition export)
   unsigned long long* tile_state;  // [B*scan_tiles] decoupled look-back descriptors
   int* tile_counter;           // [B]
   int* radix_counts;           // [B*256*radix_blocks]
@@ -55,6 +61,7 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   using I = typename RT<F>::I;
   Bump b(ws);
   const size_t B = (size_t)c.batch, N = (size_t)c.n, BN = B * N;
+  c.cell_stride = (c.max_cells + 1 + 63) / 64 * 64;
   c.scan_tiles = cdiv(c.max_cells + 1, kScanTile);
   c.radix_blocks = cdiv(c.n, kRadixTile);
   c.reduce_blocks = cdiv(c.n, kReduceBlock);
@@ -67,7 +74,11 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.perm_b = b.take<int>(BN);
   c.perm_c = b.take<int>(BN);
   c.rank = b.take<int>(BN);
-  c.cell_start = b.take<int>(B * (size_t)(c.max_cells + 1));
+  c.cell_count = b.take<int>(B * (size_t)c.cell_stride);
+  c.cell_start = b.take<int>(B * (size_t)c.cell_stride);
+  c.tmp_key = b.take<int>(BN);
+  c.upos = b.take<Vec4<F>>(BN);
+  c.coop_bar = b.take<unsigned>(4);
   c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);
   c.tile_counter = b.take<int>(B);
   c.radix_counts = b.take<int>(B * 256 * (size_t)c.radix_blocks);
@@ -137,7 +148,7 @@ inline int check_params(const jdb200_params* p) {
   if (p->dtype != JDB200_F32 && p->dtype != JDB200_F64) return JDB200_EINVAL;
   if (p->batch < 1 || p->n < 0 || p->n > 0x7fffffffLL) return JDB200_EINVAL;
   if (p->domain < 0 || p->domain > 2 || p->law < 0 || p->law > 2) return JDB200_EINVAL;
-  if (p->grid_mode < 0 || p->grid_mode > 2 || p->max_cells < 0) return JDB200_EINVAL;
+  if (p->grid_mode < 0 || p->grid_mode > 2 || p->max_cells < 0 || p->max_cells > 0x7ffffff0LL) return JDB200_EINVAL;
   if (p->bond_width < 0 || p->n_materials < 0 || p->stencil_m < 0 || p->max_neighbors < 0)
     return JDB200_EINVAL;
   return 0;

@@ -101,11 +101,9 @@ __device__ __forceinline__ F pow25(F x) { return x * x * RT<F>::sqrt(x); }  // x
 
 // ---- force on a due to b --------------------------------------------------------
 template <typename F, int LAW>
-__device__ __forceinline__ void pair_force(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b,
-                                           F* f, F* t) {
+__device__ __forceinline__ void pair_force_rij(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b,
+                                               const F* rij, F* f, F* t) {
   using T = RT<F>;
-  F rij[3];
-  displacement_mul(lc, a, b, rij);
   if (LAW == JDB200_LAW_SPRING) {
     // jaxdem/forces/spring.py:97-108
     const F R = a.r + b.r;
@@ -184,12 +182,19 @@ __device__ __forceinline__ void pair_force(const LawCtx<F>& lc, const Body<F>& a
   }
 }
 
-// ---- pair energy E_ab (the 0.5 is applied by the caller, _partition.py:39-51) ----
 template <typename F, int LAW>
-__device__ __forceinline__ F pair_energy(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b) {
-  using T = RT<F>;
+__device__ __forceinline__ void pair_force(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b,
+                                           F* f, F* t) {
   F rij[3];
   displacement_mul(lc, a, b, rij);
+  pair_force_rij<F, LAW>(lc, a, b, rij, f, t);
+}
+
+// ---- pair energy E_ab (the 0.5 is applied by the caller, _partition.py:39-51) ----
+template <typename F, int LAW>
+__device__ __forceinline__ F pair_energy_rij(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b,
+                                             const F* rij) {
+  using T = RT<F>;
   if (LAW == JDB200_LAW_SPRING) {
     // spring.py:136-147
     const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
@@ -215,6 +220,13 @@ __device__ __forceinline__ F pair_energy(const LawCtx<F>& lc, const Body<F>& a, 
     delta = delta > F(0) ? delta : F(0);
     return F(0.5) * kn * delta * delta;
   }
+}
+
+template <typename F, int LAW>
+__device__ __forceinline__ F pair_energy(const LawCtx<F>& lc, const Body<F>& a, const Body<F>& b) {
+  F rij[3];
+  displacement_mul(lc, a, b, rij);
+  return pair_energy_rij<F, LAW>(lc, a, b, rij);
 }
 
 }  // namespace jdb

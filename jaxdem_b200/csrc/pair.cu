@@ -87,7 +87,7 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
                              c.periodic);
   const I* mask = c.mask + (size_t)b * c.M * c.dim;
   const I* skey = c.skey + off;
-  const int* cstart = c.cell_start + (size_t)b * (c.max_cells + 1);
+  const int* cstart = c.cell_start + (size_t)b * c.cell_stride;
   const int n = (int)c.n;
   for (int m = 0; m < c.M; ++m) {
     const I h = neighbor_hash<F, I>(cc, mask + m * c.dim, g.gd, g.stride, c.dim, c.periodic);
@@ -121,64 +121,192 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
 }
 
 // ---------------------------------------------------------------------------
-// K4  pair force
+// Fast stencil walk (dense table, canonical cubic stencil, no periodic de-dup needed):
+// the x-fastest linear hash makes the cells (cx-R .. cx+R, ny, nz) ONE contiguous run of
+// the sorted arrays, so a (2R+1)^D stencil costs (2R+1)^(D-1) range look-ups.  The set of
+// cells visited is exactly the reference's stencil (same wrapped / out-of-grid rules,
+// cell_list.py:66-80); only the ORDER differs from neighbor_mask order (x innermost), which
+// changes floating-point summation order but nothing else.  Row-exact consumers (the
+// neighbour list) keep walk_stencil.
 // ---------------------------------------------------------------------------
-template <typename F, int LAW>
+template <typename I>
+__device__ __forceinline__ bool fast_walk_ok(const GridInfo<I>& g) {
+  return g.dense && !g.dense_fail && g.canonical && !g.need_dedup;
+}
+
+template <typename F, int D, typename Vis>
+__device__ __forceinline__ void walk_runs(const Ctx<F>& c, int b, const GridInfo<typename RT<F>::I>& g,
+                                          const F* pp, Vis& vis) {
+  using T = RT<F>;
+  using I = typename RT<F>::I;
+  const F cs = c.cell_size[b];
+  int cc[3] = {0, 0, 0}, gd[3] = {1, 1, 1};
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    cc[d] = (int)cell_coord<F, I>(pp[d], c.anchor[b * D + d], c.box[b * D + d], cs, g.gd[d], c.periodic);
+    gd[d] = (int)g.gd[d];
+  }
+  const int R = g.range;
+  const int sy = (int)g.stride[1], sz = D == 3 ? (int)g.stride[2] : 0;
+  const int* __restrict__ cstart = c.cell_start + (size_t)b * c.cell_stride;
+  const int bound = (int)g.bound;
+  const int zlo = D == 3 ? -R : 0, zhi = D == 3 ? R : 0;
+  for (int dz = zlo; dz <= zhi; ++dz) {
+    int nz = cc[2] + dz;
+    if (D == 3) {
+      if (c.periodic) nz -= gd[2] * (int)floorf((float)nz / (float)gd[2]);
+      else if (nz < 0 || nz >= gd[2]) continue;
+    }
+    for (int dy = -R; dy <= R; ++dy) {
+      int ny = cc[1] + dy;
+      if (c.periodic) ny -= gd[1] * (int)floorf((float)ny / (float)gd[1]);
+      else if (ny < 0 || ny >= gd[1]) continue;
+      const int hb = ny * sy + nz * sz;
+      int lo = cc[0] - R, hi = cc[0] + R;
+      if (c.periodic) {
+        if (lo < 0 || hi >= gd[0]) {  // the x-run wraps: visit the cells one by one
+          for (int dx = -R; dx <= R; ++dx) {
+            int nx = cc[0] + dx;
+            nx -= gd[0] * (int)floorf((float)nx / (float)gd[0]);
+            const int h = hb + nx;
+            if (h < 0 || h >= bound) continue;
+            const int s = cstart[h], e = cstart[h + 1];
+            if (e > s) vis.cell(0, s, e);
+          }
+          continue;
+        }
+      } else {
+        lo = lo < 0 ? 0 : lo;
+        hi = hi >= gd[0] ? gd[0] - 1 : hi;
+        if (lo > hi) continue;
+      }
+      const int h0 = hb + lo, h1 = hb + hi + 1;
+      if (h0 < 0 || h1 > bound) {  // defensive: never read outside the table
+        for (int h = h0 < 0 ? 0 : h0; h < h1 && h < bound; ++h) {
+          const int s = cstart[h], e = cstart[h + 1];
+          if (e > s) vis.cell(0, s, e);
+        }
+        continue;
+      }
+      const int s = cstart[h0], e = cstart[h1];
+      if (e > s) vis.cell(0, s, e);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4  pair force.  One thread owns one particle (sorted slot k) and accumulates its
+// contacts in a fixed order: deterministic, no atomics.
+// ---------------------------------------------------------------------------
+template <typename F, int LAW, int D>
 struct ForceVis {
+  using T = RT<F>;
   const Ctx<F>& c;
   const LawCtx<F>& lc;
   size_t off;
   Body<F> a;
-  int idx, clump;
-  bool interact;
+  int k, idx, clump;
+  bool interact, simple;
+  F hb[3];  // |rij| below this => the minimum-image term is exactly zero
   F f[3], t[3];
   __device__ __forceinline__ void cell(int, int s, int e) {
+    constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
     for (int kj = s; kj < e; ++kj) {
-      const int sc = c.sclump[off + kj];
-      if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
-      const Body<F> bj = load_sorted(c, off, kj, LAW == JDB200_LAW_CUNDALLSTRACK);
+      if (simple) {
+        if (kj == k) continue;  // clump_id == arange(N): only self is excluded
+      } else {
+        const int sc = c.sclump[off + kj];
+        if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
+      }
+      const Vec4<F> q = c.spos[off + kj];
+      F rij[3] = {T::sub(a.x, q.x), T::sub(a.y, q.y), D == 3 ? T::sub(a.z, q.z) : F(0)};
+      if (lc.periodic) {
+        // Domain._displacement (periodic.py:75-79); rint(rij * inv_box) is exactly 0 below hb
+        bool far = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) far |= !(T::abs(rij[d]) < hb[d]);
+        if (far) {
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
+        }
+      }
+      const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+      const F rs = a.r + q.w;
+      // no overlap => every law returns exactly zero force and torque (the margin keeps
+      // pairs within rounding of touching on the full path)
+      if (!(d2 < rs * rs * F(1.00001))) continue;
+      Body<F> bj;
+      bj.x = q.x; bj.y = q.y; bj.z = q.z; bj.r = q.w;
+      bj.mat = (c.nmat > 1) ? c.smat[off + kj] : 0;
+      if (CS) {
+        const Vec4<F> v = c.svel[off + kj];
+        const Vec4<F> w = c.sang[off + kj];
+        bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
+        bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
+      }
       F ff[3], tt[3];
-      pair_force<F, LAW>(lc, a, bj, ff, tt);
+      pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
       f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
-      t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2];
+      if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
     }
   }
 };
 
-template <typename F>
-__device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx, const F* f, const F* t) {
-  // collider epilogue (cell_list.py:461-462): torque = sum T + cross(_pos_p_rot, sum F)
-  F* fo = c.force + gidx * c.dim;
-  F* to = c.torque + gidx * c.A;
-  const F* pr = c.pos_p_rot + gidx * c.dim;
-  if (c.dim == 3) {
-    fo[0] = f[0]; fo[1] = f[1]; fo[2] = f[2];
+// epilogue of DynamicCellList.compute_force (cell_list.py:461-462):
+// torque = sum T + cross(_pos_p_rot, sum F).  with_torque = false skips the torque store
+// (fused driver, steps whose torque nobody can observe).
+template <typename F, int D>
+__device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx, const F* f, const F* t,
+                                                   bool any_ppr, bool with_torque) {
+  F* fo = c.force + gidx * D;
+#pragma unroll
+  for (int d = 0; d < D; ++d) fo[d] = f[d];
+  if (!with_torque) return;
+  constexpr int A = D == 3 ? 3 : 1;
+  F* to = c.torque + gidx * A;
+  F pr[3] = {0, 0, 0};
+  if (any_ppr) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) pr[d] = c.pos_p_rot[gidx * D + d];
+  }
+  if (D == 3) {
     to[0] = t[0] + (pr[1] * f[2] - pr[2] * f[1]);
     to[1] = t[1] + (pr[2] * f[0] - pr[0] * f[2]);
     to[2] = t[2] + (pr[0] * f[1] - pr[1] * f[0]);
   } else {
-    fo[0] = f[0]; fo[1] = f[1];
     to[0] = t[2] + (pr[0] * f[1] - pr[1] * f[0]);
   }
 }
 
-template <typename F, int LAW>
-__global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c) {
+template <typename F, int LAW, int D>
+__global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
+  using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= c.n) return;
   const size_t off = (size_t)b * c.n;
+  const GridInfo<I> g = c.gi[b];
   const LawCtx<F> lc = make_law_ctx(c, b);
-  ForceVis<F, LAW> vis{c, lc, off};
+  ForceVis<F, LAW, D> vis{c, lc, off};
   vis.a = load_sorted(c, off, k, LAW == JDB200_LAW_CUNDALLSTRACK);
+  vis.k = k;
   vis.idx = c.perm[off + k];
-  vis.clump = c.sclump[off + k] & 0x7fffffff;
+  vis.simple = !c.clumps && !g.any_bond;
+  vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
   vis.interact = c.interact && c.interact[b];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) vis.hb[d] = lc.box[d] * F(0.499999);
   vis.f[0] = vis.f[1] = vis.f[2] = F(0);
   vis.t[0] = vis.t[1] = vis.t[2] = F(0);
-  walk_stencil<F>(c, b, k, nullptr, vis);
-  store_force_torque(c, off + vis.idx, vis.f, vis.t);
-  if (k == 0 && c.overflow) c.overflow[b] = (uint8_t)c.gi[b].hash_overflow;  // cell_list.py:463
+  if (fast_walk_ok(g)) {
+    const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
+    walk_runs<F, D>(c, b, g, pp, vis);
+  } else {
+    walk_stencil<F>(c, b, k, nullptr, vis);
+  }
+  store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
+  if (k == 0 && c.overflow) c.overflow[b] = (uint8_t)g.hash_overflow;  // cell_list.py:463
 }
 
 // ---------------------------------------------------------------------------
@@ -190,13 +318,17 @@ struct EnergyVis {
   const LawCtx<F>& lc;
   size_t off;
   Body<F> a;
-  int idx, clump;
-  bool interact;
+  int k, idx, clump;
+  bool interact, simple;
   F e;
   __device__ __forceinline__ void cell(int, int s, int en) {
     for (int kj = s; kj < en; ++kj) {
-      const int sc = c.sclump[off + kj];
-      if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
+      if (simple) {
+        if (kj == k) continue;
+      } else {
+        const int sc = c.sclump[off + kj];
+        if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
+      }
       const Body<F> bj = load_sorted(c, off, kj, false);
       e += F(0.5) * pair_energy<F, LAW>(lc, a, bj);
     }
@@ -217,19 +349,29 @@ __device__ __forceinline__ F block_sum_256(F v) {  // fixed tree order => determ
 
 template <typename F, int LAW>
 __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
+  using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t off = (size_t)b * c.n;
   F e = F(0);
   if (k < c.n) {
+    const GridInfo<I> g = c.gi[b];
     const LawCtx<F> lc = make_law_ctx(c, b);
     EnergyVis<F, LAW> vis{c, lc, off};
     vis.a = load_sorted(c, off, k, false);
+    vis.k = k;
     vis.idx = c.perm[off + k];
-    vis.clump = c.sclump[off + k] & 0x7fffffff;
+    vis.simple = !c.clumps && !g.any_bond;
+    vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
     vis.interact = c.interact && c.interact[b];
     vis.e = F(0);
-    walk_stencil<F>(c, b, k, nullptr, vis);
+    if (fast_walk_ok(g)) {
+      const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
+      if (c.dim == 3) walk_runs<F, 3>(c, b, g, pp, vis);
+      else walk_runs<F, 2>(c, b, g, pp, vis);
+    } else {
+      walk_stencil<F>(c, b, k, nullptr, vis);
+    }
     e = vis.e;
   }
   const F tot = block_sum_256(e);
@@ -260,8 +402,8 @@ struct NlVis {
   const LawCtx<F>& lc;
   size_t off;
   Body<F> a;
-  int idx, clump;
-  bool interact;
+  int k, idx, clump;
+  bool interact, simple;
   F cutoff_sq;
   I* row;
   long long row_off;  // running sum of raw per-cell counts
@@ -273,8 +415,12 @@ struct NlVis {
       for (int u = 0; u < 4; ++u) {
         const int kj = k0 + u;
         if (kj >= e) break;
-        const int sc = c.sclump[off + kj];
-        if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
+        if (simple) {
+          if (kj == k) continue;
+        } else {
+          const int sc = c.sclump[off + kj];
+          if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
+        }
         const Body<F> bj = load_sorted(c, off, kj, false);
         F r[3];
         displacement_div(lc, a, bj, r);
@@ -302,8 +448,10 @@ __global__ void __launch_bounds__(128) k_neighbor_list(Ctx<F> c, const F* __rest
   const LawCtx<F> lc = make_law_ctx(c, b);
   NlVis<F> vis{c, lc, off};
   vis.a = load_sorted(c, off, k, false);
+  vis.k = k;
   vis.idx = c.perm[off + k];
-  vis.clump = c.sclump[off + k] & 0x7fffffff;
+  vis.simple = !c.clumps && !c.gi[b].any_bond;
+  vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
   vis.interact = c.interact && c.interact[b];
   vis.cutoff_sq = cutoff[b] * cutoff[b];
   vis.row = nl + (off + vis.idx) * c.K;
@@ -368,7 +516,8 @@ __global__ void __launch_bounds__(128) k_naive_force(Ctx<F> c) {
     f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
     t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2];
   }
-  store_force_torque(c, off + i, f, t);
+  if (c.dim == 3) store_force_torque<F, 3>(c, off + i, f, t, true, true);
+  else store_force_torque<F, 2>(c, off + i, f, t, true, true);
 }
 
 template <typename F, int LAW>
@@ -394,7 +543,7 @@ __global__ void __launch_bounds__(kReduceBlock) k_naive_energy(Ctx<F> c) {
 // host side
 // ---------------------------------------------------------------------------
 template <typename F>
-int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override);
+int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override, int hash_mode, bool ext);
 
 #define JDB_LAW_SWITCH(law, CALL)                                     \
   switch (law) {                                                      \
@@ -403,22 +552,27 @@ int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override);
     default: { constexpr int L = JDB200_LAW_CUNDALLSTRACK; CALL; } break;                   \
   }
 
+// hash_mode / ext: fusion of the linear integrator into the hash kernel (celllist.cu k_hash);
+// with_torque = false skips the torque store (fused driver only).
 template <typename F>
-int celllist_force(cudaStream_t s, Ctx<F>& c, bool rebuild) {
+int celllist_force(cudaStream_t s, Ctx<F>& c, int hash_mode, bool ext, bool with_torque) {
   if (c.n == 0) return 0;
-  if (rebuild) {
-    int rc = build_partition<F>(s, c, nullptr);
-    if (rc) return rc;
-  }
+  int rc = build_partition<F>(s, c, nullptr, hash_mode, ext);
+  if (rc) return rc;
   const dim3 grid(cdiv(c.n, 128), c.batch);
-  JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L>), grid, 128, s, c));
+  const int wt = with_torque ? 1 : 0;
+  if (c.dim == 3) {
+    JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, 3>), grid, 128, s, c, wt));
+  } else {
+    JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, 2>), grid, 128, s, c, wt));
+  }
   return 0;
 }
 
 template <typename F>
 int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
   if (c.n == 0) return cudaMemsetAsync(energy, 0, sizeof(F) * c.batch, s) == cudaSuccess ? 0 : JDB200_ECUDA;
-  int rc = build_partition<F>(s, c, nullptr);
+  int rc = build_partition<F>(s, c, nullptr, 0, false);
   if (rc) return rc;
   const dim3 grid(c.reduce_blocks, c.batch);
   JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
@@ -433,7 +587,7 @@ int celllist_neighbor_list(cudaStream_t s, Ctx<F>& c, const F* cutoff, typename 
     return cudaMemsetAsync(overflow, 0, c.batch, s) == cudaSuccess ? 0 : JDB200_ECUDA;
   F* cs_nl = c.partial;  // [B] scratch for the inflated cell size
   JDB_LAUNCH(k_nl_cell_size<F>, dim3(cdiv(c.batch, 64)), 64, s, c, cutoff, cs_nl);
-  int rc = build_partition<F>(s, c, cs_nl);
+  int rc = build_partition<F>(s, c, cs_nl, 0, false);
   if (rc) return rc;
   JDB_LAUNCH(k_neighbor_list<F>, dim3(cdiv(c.n, 128), c.batch), 128, s, c, cs_nl, cutoff, nl);
   JDB_LAUNCH(k_nl_flag<F>, dim3(cdiv(c.batch, 64)), 64, s, c, overflow);
@@ -458,7 +612,7 @@ int naive_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
 }
 
 #define JDB_INST(F)                                                                     \
-  template int celllist_force<F>(cudaStream_t, Ctx<F>&, bool);                          \
+  template int celllist_force<F>(cudaStream_t, Ctx<F>&, int, bool, bool);                          \
   template int celllist_energy<F>(cudaStream_t, Ctx<F>&, F*);                           \
   template int celllist_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, RT<F>::I*, uint8_t*); \
   template int naive_force<F>(cudaStream_t, Ctx<F>&);                                   \

@@ -270,7 +270,7 @@ template <typename F>
 __global__ void __launch_bounds__(512) k_clump_scan(Ctx<F> c, int* cl_start, unsigned long long* ts,
                                                      int* tc, int tiles) {
   const int b = blockIdx.y;
-  scan_tile(cl_start + (size_t)b * (c.n + 1), c.n + 1, ts + (size_t)b * tiles, &tc[b], 0x7fffffff);
+  scan_tile(cl_start + (size_t)b * (c.n + 1), cl_start + (size_t)b * (c.n + 1), c.n + 1, ts + (size_t)b * tiles, &tc[b], 0x7fffffff);
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_clump_scatter(Ctx<F> c, const int* cl_start, const int* cl_rank,
@@ -417,6 +417,70 @@ __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
     c.torque[gi * c.A + a] = acc[3 + a];
     c.ext_torque[gi * c.A + a] = F(0);
   }
+}
+
+// Fused-driver epilogue for sphere systems: ForceManager.apply (force_manager.py:359-423 with
+// clump_id == arange(N)) + VelocityVerlet.step_after_force (velocity_verlet.py:92-95) in one
+// pass.  EXT = false: the external buffers are known to be zero (cleared earlier in the call).
+template <typename F, int D, bool EXT>
+__global__ void __launch_bounds__(256) k_fm_after(Ctx<F> c) {
+  using T = RT<F>;
+  constexpr int A = D == 3 ? 3 : 1;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t gi = (size_t)b * c.n + i;
+  const F mass = c.mass[gi];
+  const F sc = T::div(T::mul(c.dt[b], F(0.5)), mass);
+  const F free = c.fixed[gi] ? F(0) : F(1);
+  F fp[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    F fc = F(0);
+    if (EXT) {
+      fp[d] = c.ext_force[gi * D + d];
+      fc = c.ext_force_com[gi * D + d];
+      r[d] = c.pos_p_rot[gi * D + d];
+      c.ext_force[gi * D + d] = F(0);
+      c.ext_force_com[gi * D + d] = F(0);
+    }
+    const F fcom = T::add(fc, T::mul(c.gravity[b * D + d], T::div(mass, F(1))));
+    const F ft = T::add(T::add(c.force[gi * D + d], fp[d]), fcom);
+    c.force[gi * D + d] = ft;
+    c.vel[gi * D + d] = T::add(c.vel[gi * D + d], T::mul(T::mul(ft, sc), free));
+  }
+  F cr[3] = {0, 0, 0};
+  if (EXT) {
+    if (D == 3) {
+      const V3<F> x = xcross(V3<F>{r[0], r[1], r[2]}, V3<F>{fp[0], fp[1], fp[2]});
+      cr[0] = x.x; cr[1] = x.y; cr[2] = x.z;
+    } else {
+      cr[0] = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    F et = F(0);
+    if (EXT) {
+      et = c.ext_torque[gi * A + a];
+      c.ext_torque[gi * A + a] = F(0);
+    }
+    c.torque[gi * A + a] = T::add(c.torque[gi * A + a], T::add(et, cr[a]));
+  }
+}
+
+template <typename F>
+int fm_after_fused(cudaStream_t s, Ctx<F>& c, bool ext) {
+  if (c.n == 0) return 0;
+  const dim3 gp(cdiv(c.n, 256), c.batch);
+  if (c.dim == 3) {
+    if (ext) JDB_LAUNCH((k_fm_after<F, 3, true>), gp, 256, s, c);
+    else JDB_LAUNCH((k_fm_after<F, 3, false>), gp, 256, s, c);
+  } else {
+    if (ext) JDB_LAUNCH((k_fm_after<F, 2, true>), gp, 256, s, c);
+    else JDB_LAUNCH((k_fm_after<F, 2, false>), gp, 256, s, c);
+  }
+  return 0;
 }
 
 template <typename F>
@@ -900,6 +964,7 @@ int rotation_after(cudaStream_t s, Ctx<F>& c) {
 
 #define JDB_INST(F)                                                   \
   template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
+  template int fm_after_fused<F>(cudaStream_t, Ctx<F>&, bool);        \
   template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
   template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \
   template int linear_before<F>(cudaStream_t, Ctx<F>&);               \
