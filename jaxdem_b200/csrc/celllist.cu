@@ -143,73 +143,94 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   using T = RT<F>;
   using I = typename RT<F>::I;
   using U = typename RT<F>::U;
+  constexpr int A = D == 3 ? 3 : 1;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < c.n;
   const size_t gidx = (size_t)b * c.n + (live ? i : 0);
   bool bond = false, ppr_nz = false;
   if (live) {
+    // ---- all loads first (stores below may alias as far as the compiler knows) ----
     const GridInfo<I> g = c.gi[b];
-    F pc[3] = {0, 0, 0}, pr[3] = {0, 0, 0};
+    F pc[3] = {0, 0, 0}, pr[3] = {0, 0, 0}, f[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+    F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       pc[d] = c.pos_c[gidx * D + d];
       pr[d] = c.pos_p_rot[gidx * D + d];
-      ppr_nz |= pr[d] != F(0);
-    }
-    if (MODE != 0) {
-      const F dt = c.dt[b];
-      const F mass = c.mass[gidx];
-      const F sc = T::div(T::mul(dt, F(0.5)), mass);  // dt * 0.5 / mass
-      const F free = c.fixed[gidx] ? F(0) : F(1);
-      F f[3] = {0, 0, 0}, v[3] = {0, 0, 0};
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
+      if (MODE != 0) {
         f[d] = c.force[gidx * D + d];
         v[d] = c.vel[gidx * D + d];
       }
       if (MODE == 2) {
-        // ForceManager.apply, clump_id == arange(N): count == 1, segment ops are identities
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          F fp = F(0), fc = F(0);
-          if (EXT) {
-            fp = c.ext_force[gidx * D + d];
-            fc = c.ext_force_com[gidx * D + d];
-            c.ext_force[gidx * D + d] = F(0);
-            c.ext_force_com[gidx * D + d] = F(0);
-          }
-          const F fcom = T::add(fc, T::mul(c.gravity[b * D + d], T::div(mass, F(1))));
-          f[d] = T::add(T::add(f[d], fp), fcom);
-          v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_after_force of the previous step
-        }
+        grav[d] = c.gravity[b * D + d];
         if (EXT) {
-          constexpr int A = D == 3 ? 3 : 1;
-#pragma unroll
-          for (int a = 0; a < A; ++a) c.ext_torque[gidx * A + a] = F(0);
+          fp[d] = c.ext_force[gidx * D + d];
+          fc[d] = c.ext_force_com[gidx * D + d];
         }
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_before_force: kick ...
-        pc[d] = T::add(pc[d], T::mul(dt, v[d]));              // ... and drift
-        c.vel[gidx * D + d] = v[d];
-        c.pos_c[gidx * D + d] = pc[d];
       }
     }
+    const F rad = c.rad[gidx];
+    F dt = F(0), mass = F(1);
+    bool fixed = false;
+    if (MODE != 0) {
+      dt = c.dt[b];
+      mass = c.mass[gidx];
+      fixed = c.fixed[gidx] != 0;
+    }
+    for (int w = 0; w < c.W; ++w) bond |= c.bond_id[gidx * c.W + w] >= 0;
     const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
+    F anchor[3] = {0, 0, 0}, box[3] = {1, 1, 1};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      anchor[d] = c.anchor[b * D + d];
+      box[d] = c.box[b * D + d];
+    }
+    // ---- arithmetic ----
+    if (MODE != 0) {
+      const F sc = T::div(T::mul(dt, F(0.5)), mass);  // dt * 0.5 / mass
+      const F free = fixed ? F(0) : F(1);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (MODE == 2) {
+          // ForceManager.apply, clump_id == arange(N): count == 1, segment ops are identities
+          const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
+          f[d] = T::add(T::add(f[d], fp[d]), fcom);
+          v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_after_force of the previous step
+        }
+        v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_before_force: kick ...
+        pc[d] = T::add(pc[d], T::mul(dt, v[d]));              // ... and drift
+      }
+    }
     F p[3] = {0, 0, 0};
     U h = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
+      ppr_nz |= pr[d] != F(0);
       p[d] = T::add(pc[d], pr[d]);  // State.pos = pos_c + _pos_p_rot
-      const I cd = cell_coord<F, I>(p[d], c.anchor[b * D + d], c.box[b * D + d], cs, g.gd[d], c.periodic);
+      const I cd = cell_coord<F, I>(p[d], anchor[d], box[d], cs, g.gd[d], c.periodic);
       h += (U)cd * (U)g.stride[d];
     }
     const I key = (I)h;
+    // ---- stores ----
+    if (MODE != 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        c.vel[gidx * D + d] = v[d];
+        c.pos_c[gidx * D + d] = pc[d];
+      }
+    }
+    if (MODE == 2 && EXT) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        c.ext_force[gidx * D + d] = F(0);
+        c.ext_force_com[gidx * D + d] = F(0);
+      }
+#pragma unroll
+      for (int a = 0; a < A; ++a) c.ext_torque[gidx * A + a] = F(0);
+    }
     c.key[gidx] = key;
-    c.upos[gidx] = Vec4<F>{p[0], p[1], p[2], c.rad[gidx]};
-    for (int w = 0; w < c.W; ++w) bond |= c.bond_id[gidx * c.W + w] >= 0;
+    c.upos[gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
       if (key >= 0 && (long long)key < g.bound) {
         c.rank[gidx] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + key, 1);

@@ -123,73 +123,69 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
 // ---------------------------------------------------------------------------
 // Fast stencil walk (dense table, canonical cubic stencil, no periodic de-dup needed):
 // the x-fastest linear hash makes the cells (cx-R .. cx+R, ny, nz) ONE contiguous run of
-// the sorted arrays, so a (2R+1)^D stencil costs (2R+1)^(D-1) range look-ups.  The set of
-// cells visited is exactly the reference's stencil (same wrapped / out-of-grid rules,
-// cell_list.py:66-80); only the ORDER differs from neighbor_mask order (x innermost), which
-// changes floating-point summation order but nothing else.  Row-exact consumers (the
-// neighbour list) keep walk_stencil.
+// the sorted arrays (two where the run wraps around the periodic box), so a (2R+1)^D
+// stencil costs (2R+1)^(D-1) range look-ups.  The set of cells visited is exactly the
+// reference's stencil (same wrapped / out-of-grid rules, cell_list.py:66-80); only the
+// ORDER differs from neighbor_mask order (x innermost), which changes floating-point
+// summation order but nothing else.  Row-exact consumers (the neighbour list) keep
+// walk_stencil.
 // ---------------------------------------------------------------------------
 template <typename I>
 __device__ __forceinline__ bool fast_walk_ok(const GridInfo<I>& g) {
   return g.dense && !g.dense_fail && g.canonical && !g.need_dedup;
 }
 
-template <typename F, int D, typename Vis>
+// wrap n into [0, g) for |n| < 2g: identical to n - g*floor(n/g) (cell_list.py:70-72)
+__device__ __forceinline__ int wrap1(int n, int g) { return n < 0 ? n + g : (n >= g ? n - g : n); }
+
+// Calls vis.run(s1, e1, s2, e2) once per stencil row: candidates are the sorted slots
+// [s1, e1) followed by [s2, e2) (the second segment is empty unless the x-run wraps).
+template <typename F, int D, bool PERIODIC, typename Vis>
 __device__ __forceinline__ void walk_runs(const Ctx<F>& c, int b, const GridInfo<typename RT<F>::I>& g,
                                           const F* pp, Vis& vis) {
-  using T = RT<F>;
   using I = typename RT<F>::I;
   const F cs = c.cell_size[b];
   int cc[3] = {0, 0, 0}, gd[3] = {1, 1, 1};
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    cc[d] = (int)cell_coord<F, I>(pp[d], c.anchor[b * D + d], c.box[b * D + d], cs, g.gd[d], c.periodic);
+    cc[d] = (int)cell_coord<F, I>(pp[d], c.anchor[b * D + d], c.box[b * D + d], cs, g.gd[d], PERIODIC);
     gd[d] = (int)g.gd[d];
   }
-  const int R = g.range;
+  const int R = g.range, len = 2 * R + 1;
   const int sy = (int)g.stride[1], sz = D == 3 ? (int)g.stride[2] : 0;
   const int* __restrict__ cstart = c.cell_start + (size_t)b * c.cell_stride;
-  const int bound = (int)g.bound;
+  // x segment(s): [x1, x1 + n1) and, when it wraps, [0, n2)
+  int x1, n1, n2 = 0;
+  if (PERIODIC) {
+    x1 = wrap1(cc[0] - R, gd[0]);
+    n1 = min(len, gd[0] - x1);
+    n2 = len - n1;
+  } else {
+    x1 = max(cc[0] - R, 0);
+    n1 = min(cc[0] + R, gd[0] - 1) - x1 + 1;  // <= 0: the whole x-range is out of the grid
+  }
   const int zlo = D == 3 ? -R : 0, zhi = D == 3 ? R : 0;
   for (int dz = zlo; dz <= zhi; ++dz) {
     int nz = cc[2] + dz;
     if (D == 3) {
-      if (c.periodic) nz -= gd[2] * (int)floorf((float)nz / (float)gd[2]);
+      if (PERIODIC) nz = wrap1(nz, gd[2]);
       else if (nz < 0 || nz >= gd[2]) continue;
     }
     for (int dy = -R; dy <= R; ++dy) {
       int ny = cc[1] + dy;
-      if (c.periodic) ny -= gd[1] * (int)floorf((float)ny / (float)gd[1]);
+      if (PERIODIC) ny = wrap1(ny, gd[1]);
       else if (ny < 0 || ny >= gd[1]) continue;
       const int hb = ny * sy + nz * sz;
-      int lo = cc[0] - R, hi = cc[0] + R;
-      if (c.periodic) {
-        if (lo < 0 || hi >= gd[0]) {  // the x-run wraps: visit the cells one by one
-          for (int dx = -R; dx <= R; ++dx) {
-            int nx = cc[0] + dx;
-            nx -= gd[0] * (int)floorf((float)nx / (float)gd[0]);
-            const int h = hb + nx;
-            if (h < 0 || h >= bound) continue;
-            const int s = cstart[h], e = cstart[h + 1];
-            if (e > s) vis.cell(0, s, e);
-          }
-          continue;
-        }
-      } else {
-        lo = lo < 0 ? 0 : lo;
-        hi = hi >= gd[0] ? gd[0] - 1 : hi;
-        if (lo > hi) continue;
+      int s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+      if (n1 > 0) {
+        s1 = cstart[hb + x1];
+        e1 = cstart[hb + x1 + n1];
       }
-      const int h0 = hb + lo, h1 = hb + hi + 1;
-      if (h0 < 0 || h1 > bound) {  // defensive: never read outside the table
-        for (int h = h0 < 0 ? 0 : h0; h < h1 && h < bound; ++h) {
-          const int s = cstart[h], e = cstart[h + 1];
-          if (e > s) vis.cell(0, s, e);
-        }
-        continue;
+      if (PERIODIC && n2 > 0) {
+        s2 = cstart[hb];
+        e2 = cstart[hb + n2];
       }
-      const int s = cstart[h0], e = cstart[h1];
-      if (e > s) vis.cell(0, s, e);
+      vis.run(s1, e1, s2, e2);
     }
   }
 }
@@ -198,7 +194,7 @@ __device__ __forceinline__ void walk_runs(const Ctx<F>& c, int b, const GridInfo
 // K4  pair force.  One thread owns one particle (sorted slot k) and accumulates its
 // contacts in a fixed order: deterministic, no atomics.
 // ---------------------------------------------------------------------------
-template <typename F, int LAW, int D>
+template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
 struct ForceVis {
   using T = RT<F>;
   const Ctx<F>& c;
@@ -206,50 +202,64 @@ struct ForceVis {
   size_t off;
   Body<F> a;
   int k, idx, clump;
-  bool interact, simple;
+  bool interact;
   F hb[3];  // |rij| below this => the minimum-image term is exactly zero
   F f[3], t[3];
-  __device__ __forceinline__ void cell(int, int s, int e) {
+
+  __device__ __forceinline__ void one(int kj) {
     constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
-    for (int kj = s; kj < e; ++kj) {
-      if (simple) {
-        if (kj == k) continue;  // clump_id == arange(N): only self is excluded
-      } else {
-        const int sc = c.sclump[off + kj];
-        if (!pair_valid(c, off, idx, clump, sc, kj, interact)) continue;
-      }
-      const Vec4<F> q = c.spos[off + kj];
-      F rij[3] = {T::sub(a.x, q.x), T::sub(a.y, q.y), D == 3 ? T::sub(a.z, q.z) : F(0)};
-      if (lc.periodic) {
-        // Domain._displacement (periodic.py:75-79); rint(rij * inv_box) is exactly 0 below hb
-        bool far = false;
-#pragma unroll
-        for (int d = 0; d < D; ++d) far |= !(T::abs(rij[d]) < hb[d]);
-        if (far) {
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
-        }
-      }
-      const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-      const F rs = a.r + q.w;
-      // no overlap => every law returns exactly zero force and torque (the margin keeps
-      // pairs within rounding of touching on the full path)
-      if (!(d2 < rs * rs * F(1.00001))) continue;
-      Body<F> bj;
-      bj.x = q.x; bj.y = q.y; bj.z = q.z; bj.r = q.w;
-      bj.mat = (c.nmat > 1) ? c.smat[off + kj] : 0;
-      if (CS) {
-        const Vec4<F> v = c.svel[off + kj];
-        const Vec4<F> w = c.sang[off + kj];
-        bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
-        bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
-      }
-      F ff[3], tt[3];
-      pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
-      f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
-      if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+    if (!SIMPLE) {
+      const int sc = c.sclump[off + kj];
+      if (!pair_valid(c, off, idx, clump, sc, kj, interact)) return;
     }
+    const Vec4<F> q = c.spos[off + kj];
+    F rij[3] = {T::sub(a.x, q.x), T::sub(a.y, q.y), D == 3 ? T::sub(a.z, q.z) : F(0)};
+    if (PERIODIC) {
+      // Domain._displacement (periodic.py:75-79); rint(rij * inv_box) is exactly 0 below hb
+      bool far = false;
+#pragma unroll
+      for (int d = 0; d < D; ++d) far |= !(T::abs(rij[d]) < hb[d]);
+      if (far) {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
+      }
+    }
+    const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+    const F rs = a.r + q.w;
+    // no overlap => every law returns exactly zero force and torque (the margin keeps
+    // pairs within rounding of touching on the full path); SIMPLE: clump_id == arange(N),
+    // only the particle itself is excluded
+    if (!(d2 < rs * rs * F(1.00001)) || (SIMPLE && kj == k)) return;
+    Body<F> bj;
+    bj.x = q.x; bj.y = q.y; bj.z = q.z; bj.r = q.w;
+    bj.mat = (c.nmat > 1) ? c.smat[off + kj] : 0;
+    if (CS) {
+      const Vec4<F> v = c.svel[off + kj];
+      const Vec4<F> w = c.sang[off + kj];
+      bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
+      bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
+    }
+    F ff[3], tt[3];
+    pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
+    f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
+    if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+  }
+  // two-segment iterator: [s1, e1) then [s2, e2)
+  __device__ __forceinline__ void run(int s1, int e1, int s2, int e2) {
+    int kj = s1, e = e1;
+    while (true) {
+      if (kj == e) {
+        if (s2 == e2) break;
+        kj = s2; e = e2; s2 = e2;
+        continue;
+      }
+      one(kj);
+      ++kj;
+    }
+  }
+  __device__ __forceinline__ void cell(int, int s, int e) {  // general walk
+    for (int kj = s; kj < e; ++kj) one(kj);
   }
 };
 
@@ -279,34 +289,48 @@ __device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx,
   }
 }
 
-template <typename F, int LAW, int D>
-__global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
-  using I = typename RT<F>::I;
-  const int b = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= c.n) return;
+template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
+__device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
+                                                const GridInfo<typename RT<F>::I>& g, bool fast,
+                                                int with_torque) {
   const size_t off = (size_t)b * c.n;
-  const GridInfo<I> g = c.gi[b];
   const LawCtx<F> lc = make_law_ctx(c, b);
-  ForceVis<F, LAW, D> vis{c, lc, off};
+  ForceVis<F, LAW, D, PERIODIC, SIMPLE> vis{c, lc, off};
   vis.a = load_sorted(c, off, k, LAW == JDB200_LAW_CUNDALLSTRACK);
   vis.k = k;
   vis.idx = c.perm[off + k];
-  vis.simple = !c.clumps && !g.any_bond;
-  vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
+  vis.clump = SIMPLE ? 0 : (c.sclump[off + k] & 0x7fffffff);
   vis.interact = c.interact && c.interact[b];
 #pragma unroll
   for (int d = 0; d < 3; ++d) vis.hb[d] = lc.box[d] * F(0.499999);
   vis.f[0] = vis.f[1] = vis.f[2] = F(0);
   vis.t[0] = vis.t[1] = vis.t[2] = F(0);
-  if (fast_walk_ok(g)) {
+  if (fast) {
     const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
-    walk_runs<F, D>(c, b, g, pp, vis);
+    walk_runs<F, D, PERIODIC>(c, b, g, pp, vis);
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
   store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
-  if (k == 0 && c.overflow) c.overflow[b] = (uint8_t)g.hash_overflow;  // cell_list.py:463
+}
+
+// FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
+// (sorted fallback, custom stencils, periodic de-dup).  Both kernels are launched; each
+// exits at once for the systems the other one owns.
+template <typename F, int LAW, int D, bool PERIODIC, bool FAST>
+__global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
+  using I = typename RT<F>::I;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const GridInfo<I> g = c.gi[b];
+  const bool mine = fast_walk_ok(g) == FAST;
+  // Collider.overflow (cell_list.py:463).  JDB200_GRID_DENSE launches only the FAST kernel: a
+  // system it cannot serve (table too small, custom stencil, periodic de-dup) raises the flag.
+  if (k == 0 && c.overflow && (mine || (FAST && c.grid_mode == JDB200_GRID_DENSE)))
+    c.overflow[b] = (uint8_t)(g.hash_overflow || !mine);
+  if (!mine || k >= c.n) return;
+  if (!c.clumps && !g.any_bond) pair_force_body<F, LAW, D, PERIODIC, true>(c, b, k, g, FAST, with_torque);
+  else pair_force_body<F, LAW, D, PERIODIC, false>(c, b, k, g, FAST, with_torque);
 }
 
 // ---------------------------------------------------------------------------
@@ -332,6 +356,10 @@ struct EnergyVis {
       const Body<F> bj = load_sorted(c, off, kj, false);
       e += F(0.5) * pair_energy<F, LAW>(lc, a, bj);
     }
+  }
+  __device__ __forceinline__ void run(int s1, int e1, int s2, int e2) {
+    cell(0, s1, e1);
+    cell(0, s2, e2);
   }
 };
 
@@ -367,8 +395,13 @@ __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
     vis.e = F(0);
     if (fast_walk_ok(g)) {
       const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
-      if (c.dim == 3) walk_runs<F, 3>(c, b, g, pp, vis);
-      else walk_runs<F, 2>(c, b, g, pp, vis);
+      if (c.dim == 3) {
+        if (c.periodic) walk_runs<F, 3, true>(c, b, g, pp, vis);
+        else walk_runs<F, 3, false>(c, b, g, pp, vis);
+      } else {
+        if (c.periodic) walk_runs<F, 2, true>(c, b, g, pp, vis);
+        else walk_runs<F, 2, false>(c, b, g, pp, vis);
+      }
     } else {
       walk_stencil<F>(c, b, k, nullptr, vis);
     }
@@ -552,6 +585,27 @@ int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override, int 
     default: { constexpr int L = JDB200_LAW_CUNDALLSTRACK; CALL; } break;                   \
   }
 
+template <typename F, int D>
+int launch_pair_force(cudaStream_t s, Ctx<F>& c, bool with_torque) {
+  const dim3 grid(cdiv(c.n, 128), c.batch);
+  const int wt = with_torque ? 1 : 0;
+  if (c.max_cells > 0) {  // a dense table exists: the x-run kernel owns the systems it can serve
+    if (c.periodic) {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true>), grid, 128, s, c, wt));
+    } else {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, true>), grid, 128, s, c, wt));
+    }
+  }
+  if (c.grid_mode != JDB200_GRID_DENSE || c.max_cells == 0) {  // everything else
+    if (c.periodic) {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false>), grid, 128, s, c, wt));
+    } else {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false>), grid, 128, s, c, wt));
+    }
+  }
+  return 0;
+}
+
 // hash_mode / ext: fusion of the linear integrator into the hash kernel (celllist.cu k_hash);
 // with_torque = false skips the torque store (fused driver only).
 template <typename F>
@@ -559,14 +613,7 @@ int celllist_force(cudaStream_t s, Ctx<F>& c, int hash_mode, bool ext, bool with
   if (c.n == 0) return 0;
   int rc = build_partition<F>(s, c, nullptr, hash_mode, ext);
   if (rc) return rc;
-  const dim3 grid(cdiv(c.n, 128), c.batch);
-  const int wt = with_torque ? 1 : 0;
-  if (c.dim == 3) {
-    JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, 3>), grid, 128, s, c, wt));
-  } else {
-    JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, 2>), grid, 128, s, c, wt));
-  }
-  return 0;
+  return c.dim == 3 ? launch_pair_force<F, 3>(s, c, with_torque) : launch_pair_force<F, 2>(s, c, with_torque);
 }
 
 template <typename F>

@@ -430,24 +430,40 @@ __global__ void __launch_bounds__(256) k_fm_after(Ctx<F> c) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
   const size_t gi = (size_t)b * c.n + i;
-  const F mass = c.mass[gi];
-  const F sc = T::div(T::mul(c.dt[b], F(0.5)), mass);
-  const F free = c.fixed[gi] ? F(0) : F(1);
-  F fp[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+  // ---- all loads first (the stores below may alias as far as the compiler knows) ----
+  const F mass = c.mass[gi], dt = c.dt[b];
+  const bool fixed = c.fixed[gi] != 0;
+  F fo[3] = {0, 0, 0}, v[3] = {0, 0, 0}, fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+  F grav[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, et[3] = {0, 0, 0};
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    F fc = F(0);
+    fo[d] = c.force[gi * D + d];
+    v[d] = c.vel[gi * D + d];
+    grav[d] = c.gravity[b * D + d];
     if (EXT) {
       fp[d] = c.ext_force[gi * D + d];
-      fc = c.ext_force_com[gi * D + d];
+      fc[d] = c.ext_force_com[gi * D + d];
       r[d] = c.pos_p_rot[gi * D + d];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    tq[a] = c.torque[gi * A + a];
+    if (EXT) et[a] = c.ext_torque[gi * A + a];
+  }
+  // ---- arithmetic + stores ----
+  const F sc = T::div(T::mul(dt, F(0.5)), mass);
+  const F free = fixed ? F(0) : F(1);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
+    const F ft = T::add(T::add(fo[d], fp[d]), fcom);
+    c.force[gi * D + d] = ft;
+    c.vel[gi * D + d] = T::add(v[d], T::mul(T::mul(ft, sc), free));
+    if (EXT) {
       c.ext_force[gi * D + d] = F(0);
       c.ext_force_com[gi * D + d] = F(0);
     }
-    const F fcom = T::add(fc, T::mul(c.gravity[b * D + d], T::div(mass, F(1))));
-    const F ft = T::add(T::add(c.force[gi * D + d], fp[d]), fcom);
-    c.force[gi * D + d] = ft;
-    c.vel[gi * D + d] = T::add(c.vel[gi * D + d], T::mul(T::mul(ft, sc), free));
   }
   F cr[3] = {0, 0, 0};
   if (EXT) {
@@ -460,12 +476,8 @@ __global__ void __launch_bounds__(256) k_fm_after(Ctx<F> c) {
   }
 #pragma unroll
   for (int a = 0; a < A; ++a) {
-    F et = F(0);
-    if (EXT) {
-      et = c.ext_torque[gi * A + a];
-      c.ext_torque[gi * A + a] = F(0);
-    }
-    c.torque[gi * A + a] = T::add(c.torque[gi * A + a], T::add(et, cr[a]));
+    c.torque[gi * A + a] = T::add(tq[a], T::add(et[a], cr[a]));
+    if (EXT) c.ext_torque[gi * A + a] = F(0);
   }
 }
 
