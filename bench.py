@@ -141,12 +141,52 @@ def cpu_steps_per_s(wl, steps, warmup=1, threads=None):
     return st.N * steps / dt, dt, c_oracle.num_threads()
 
 
+def try_jax_reference(wl, steps):
+    """BASELINE.md §3 plan 1: the UNMODIFIED reference (baseline/_ref) on JAX CPU, if JAX is
+    importable (it is not in this image; then None is returned and the C port is timed)."""
+    try:
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import jax  # noqa: F401
+        import jax.numpy as jnp
+        import jaxdem as jdem
+    except Exception:
+        return None
+    state = jdem.State.create(pos=jnp.asarray(wl["pos"]), vel=jnp.asarray(wl["vel"]),
+                              rad=jnp.asarray(wl["rad"]), mass=jnp.asarray(wl["mass"]))
+    system = jdem.System.create(state.shape, dt=1e-3, linear_integrator_type="verlet",
+                                rotation_integrator_type="", collider_type="CellList",
+                                collider_kw=dict(state=state), domain_type="periodic",
+                                domain_kw=dict(box_size=jnp.asarray(wl["box"])), force_model_type="spring")
+    state, system = jdem.System.step(state, system, n=1)
+    jax.block_until_ready(state.pos_c)
+    t0 = time.perf_counter()
+    state, system = jdem.System.step(state, system, n=steps)
+    jax.block_until_ready(state.pos_c)
+    dt = time.perf_counter() - t0
+    return wl["pos"].shape[0] * steps / dt, dt, os.cpu_count()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = make_workload(packing=args.packing)
     n = wl["pos"].shape[0]
+    jr = try_jax_reference(wl, max(1, min(args.steps, 20)))
+    if jr is not None:
+        rate, secs, cores = jr
+        steps = max(1, min(args.steps, 20))
+        print(json.dumps({
+            "impl": "reference", "metric": "particle-steps/sec at 1M 3D spheres", "value": rate,
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+            "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
+            "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "reference",
+                             "sample": f"{steps} steps, jaxdem System.step on JAX CPU"},
+            "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     # bounded sample: each "step" of this arm is one full 1M-particle step on the host cores
     steps = max(1, min(args.steps, 20))
     rate, secs, cores = cpu_steps_per_s(wl, steps, warmup=max(1, min(args.warmup, 2)))

@@ -200,19 +200,19 @@ struct ForceVis {
   const Ctx<F>& c;
   const LawCtx<F>& lc;
   size_t off;
+  const Vec4<F>* __restrict__ sp;  // c.spos + off
   Body<F> a;
   int k, idx, clump;
   bool interact;
   F hb[3];  // |rij| below this => the minimum-image term is exactly zero
   F f[3], t[3];
 
-  __device__ __forceinline__ void one(int kj) {
+  __device__ __forceinline__ void one(int kj, const Vec4<F>& q) {
     constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
     if (!SIMPLE) {
       const int sc = c.sclump[off + kj];
       if (!pair_valid(c, off, idx, clump, sc, kj, interact)) return;
     }
-    const Vec4<F> q = c.spos[off + kj];
     F rij[3] = {T::sub(a.x, q.x), T::sub(a.y, q.y), D == 3 ? T::sub(a.z, q.z) : F(0)};
     if (PERIODIC) {
       // Domain._displacement (periodic.py:75-79); rint(rij * inv_box) is exactly 0 below hb
@@ -254,12 +254,12 @@ struct ForceVis {
         kj = s2; e = e2; s2 = e2;
         continue;
       }
-      one(kj);
+      one(kj, sp[kj]);
       ++kj;
     }
   }
   __device__ __forceinline__ void cell(int, int s, int e) {  // general walk
-    for (int kj = s; kj < e; ++kj) one(kj);
+    for (int kj = s; kj < e; ++kj) one(kj, sp[kj]);
   }
 };
 
@@ -295,7 +295,7 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
                                                 int with_torque) {
   const size_t off = (size_t)b * c.n;
   const LawCtx<F> lc = make_law_ctx(c, b);
-  ForceVis<F, LAW, D, PERIODIC, SIMPLE> vis{c, lc, off};
+  ForceVis<F, LAW, D, PERIODIC, SIMPLE> vis{c, lc, off, c.spos + off};
   vis.a = load_sorted(c, off, k, LAW == JDB200_LAW_CUNDALLSTRACK);
   vis.k = k;
   vis.idx = c.perm[off + k];
@@ -321,16 +321,22 @@ template <typename F, int LAW, int D, bool PERIODIC, bool FAST>
 __global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const GridInfo<I> g = c.gi[b];
   const bool mine = fast_walk_ok(g) == FAST;
   // Collider.overflow (cell_list.py:463).  JDB200_GRID_DENSE launches only the FAST kernel: a
   // system it cannot serve (table too small, custom stencil, periodic de-dup) raises the flag.
-  if (k == 0 && c.overflow && (mine || (FAST && c.grid_mode == JDB200_GRID_DENSE)))
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow &&
+      (mine || (FAST && c.grid_mode == JDB200_GRID_DENSE)))
     c.overflow[b] = (uint8_t)(g.hash_overflow || !mine);
-  if (!mine || k >= c.n) return;
-  if (!c.clumps && !g.any_bond) pair_force_body<F, LAW, D, PERIODIC, true>(c, b, k, g, FAST, with_torque);
-  else pair_force_body<F, LAW, D, PERIODIC, false>(c, b, k, g, FAST, with_torque);
+  if (!mine) return;
+  const bool simple = !c.clumps && !g.any_bond;
+  // the FAST kernel has one thread per particle; the fallback kernel is launched with a
+  // small grid (an idle launch must cost nothing) and strides over the particles
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < c.n;
+       k += (long long)gridDim.x * blockDim.x) {
+    if (simple) pair_force_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, FAST, with_torque);
+    else pair_force_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, FAST, with_torque);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -597,10 +603,11 @@ int launch_pair_force(cudaStream_t s, Ctx<F>& c, bool with_torque) {
     }
   }
   if (c.grid_mode != JDB200_GRID_DENSE || c.max_cells == 0) {  // everything else
+    const dim3 gs(std::min(cdiv(c.n, 128), std::max(1, 4736 / c.batch)), c.batch);  // <= 32 CTAs per SM
     if (c.periodic) {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false>), grid, 128, s, c, wt));
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false>), gs, 128, s, c, wt));
     } else {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false>), grid, 128, s, c, wt));
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false>), gs, 128, s, c, wt));
     }
   }
   return 0;
