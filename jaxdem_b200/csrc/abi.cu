@@ -55,6 +55,7 @@ template <typename F>
 __global__ void __launch_bounds__(256) k_export_partition(Ctx<F> c, typename RT<F>::I* perm,
                                                            typename RT<F>::I* sorted_hash,
                                                            typename RT<F>::I* nbr_hash, uint8_t* used_dense) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,21 +116,22 @@ int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
 template <typename F>
 int system_step(cudaStream_t s, Ctx<F>& c, int collider, long long n_steps) {
   int rc = 0;
-  if (c.domain != JDB200_DOMAIN_FREE && n_steps > 0) rc = refresh_inv_box<F>(s, c);  // box is constant
   // Fused flow for sphere systems (clump_id == arange), periodic box (domain.apply is a
-  // no-op), linear velocity Verlet, no rotation integrator: per step ONE partition build whose
-  // hash kernel also applies force manager + after-kick of the previous step and the
-  // before-kick + drift of this one, and ONE pair kernel.  Same arithmetic, same order per
-  // particle as the hook-by-hook sequence; the torque store is skipped on steps whose
-  // torque nothing can observe.
+  // no-op), linear velocity Verlet, no rotation integrator.  Per step: ONE partition build
+  // whose setup kernel refreshes inv_box_size and whose hash kernel applies
+  // step_before_force (kick + drift), and ONE pair kernel whose epilogue applies the collider
+  // epilogue, ForceManager.apply and step_after_force to the particle it owns.  Same
+  // arithmetic, same order per particle as the hook-by-hook sequence; the torque store is
+  // skipped on steps whose torque nothing can observe.
   const bool fused = collider == JDB200_COLLIDER_CELLLIST && !c.clumps && c.lin == JDB200_LIN_VERLET &&
                      c.rot == JDB200_ROT_NONE && c.domain == JDB200_DOMAIN_PERIODIC && c.n > 0;
-  if (fused && n_steps > 0 && !rc) {
+  if (fused) {
+    c.fused = 1;
     for (long long it = 0; it < n_steps && !rc; ++it)
-      rc = celllist_force<F>(s, c, it == 0 ? 1 : 2, it == 1, it == n_steps - 1);
-    if (!rc) rc = fm_after_fused<F>(s, c, n_steps == 1);
+      rc = celllist_force<F>(s, c, 3, false, it == n_steps - 1);
     return rc;
   }
+  if (c.domain != JDB200_DOMAIN_FREE && n_steps > 0) rc = refresh_inv_box<F>(s, c);  // box is constant
   for (long long it = 0; it < n_steps && !rc; ++it) {
     if ((rc = domain_apply<F>(s, c))) break;  // free: also refreshes inv_box_size
     if ((rc = linear_before<F>(s, c))) break;

@@ -22,6 +22,7 @@ namespace jdb {
 // ---------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ cell_size_override) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   __shared__ I s_gd[3], s_stride[3];
@@ -55,6 +56,9 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
       ts[i] = 0ull;
   }
   if (blockIdx.x != 0) return;
+  // fused driver: the _step_once refresh of inv_box_size (system.py:69-74) rides along
+  if (c.fused && (int)threadIdx.x < c.dim)
+    c.inv_box[b * c.dim + threadIdx.x] = RT<F>::div(F(1), c.box[b * c.dim + threadIdx.x]);
   // ---- stencil classification (block 0 of each system) ----
   const I* mask = c.mask + (size_t)b * c.M * c.dim;
   // canonical cube: M == (2R+1)^D and row m == digits of m in base (2R+1), last axis fastest
@@ -116,6 +120,9 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
     g.range = R;
     g.any_bond = 0;
     g.any_ppr = 0;
+    g.any_ext = 0;
+    g.any_fixed = 0;
+    g.edge = 0;
     c.tile_counter[b] = 0;
     c.radix_skip[b] = 0;
   }
@@ -133,6 +140,10 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 //   MODE 1  VelocityVerlet.step_before_force, then hash (first step of the driver)
 //   MODE 2  ForceManager.apply (spheres) + VelocityVerlet.step_after_force of the previous
 //           step, then step_before_force of this one, then hash
+//   MODE 3  fused driver: step_before_force, then hash; the kicked velocity goes to the
+//           (vx, vy, vz, mass) shadow record instead of State.vel (the pair kernel's epilogue
+//           writes the final velocity), and the external buffers / fixed flags are scanned
+//           so that epilogue knows whether it has to gather them at all
 // EXT: the force manager reads and clears the external buffers (first application
 // after the call was entered); otherwise they are known to be zero.
 // References: velocity_verlet.py:57-61,92-95; force_manager.py:359-423;
@@ -140,6 +151,7 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 // ---------------------------------------------------------------------------
 template <typename F, int D, int MODE, bool EXT>
 __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ cell_size_override) {
+  pdl_prologue();
   using T = RT<F>;
   using I = typename RT<F>::I;
   using U = typename RT<F>::U;
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < c.n;
   const size_t gidx = (size_t)b * c.n + (live ? i : 0);
-  bool bond = false, ppr_nz = false;
+  bool bond = false, ppr_nz = false, ext_nz = false, fixed_any = false, edge = false;
   if (live) {
     // ---- all loads first (stores below may alias as far as the compiler knows) ----
     const GridInfo<I> g = c.gi[b];
@@ -179,6 +191,14 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       fixed = c.fixed[gidx] != 0;
     }
     for (int w = 0; w < c.W; ++w) bond |= c.bond_id[gidx * c.W + w] >= 0;
+    if (MODE == 3) {
+      fixed_any = fixed;
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        ext_nz |= (c.ext_force[gidx * D + d] != F(0)) | (c.ext_force_com[gidx * D + d] != F(0));
+#pragma unroll
+      for (int a = 0; a < A; ++a) ext_nz |= c.ext_torque[gidx * A + a] != F(0);
+    }
     const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
     F anchor[3] = {0, 0, 0}, box[3] = {1, 1, 1};
 #pragma unroll
@@ -209,6 +229,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       ppr_nz |= pr[d] != F(0);
       p[d] = T::add(pc[d], pr[d]);  // State.pos = pos_c + _pos_p_rot
       const I cd = cell_coord<F, I>(p[d], anchor[d], box[d], cs, g.gd[d], c.periodic);
+      edge |= cd < 0 || cd >= g.gd[d];  // hash aliases another cell (or leaves the table)
       h += (U)cd * (U)g.stride[d];
     }
     const I key = (I)h;
@@ -216,10 +237,11 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     if (MODE != 0) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        c.vel[gidx * D + d] = v[d];
+        if (MODE != 3) c.vel[gidx * D + d] = v[d];
         c.pos_c[gidx * D + d] = pc[d];
       }
     }
+    if (MODE == 3) c.uvel[gidx] = Vec4<F>{v[0], v[1], v[2], mass};
     if (MODE == 2 && EXT) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -242,6 +264,11 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   // flags consumed by the pair kernels (one store per warp at most)
   if (__any_sync(0xffffffffu, bond) && (threadIdx.x & 31) == 0) c.gi[b].any_bond = 1;
   if (__any_sync(0xffffffffu, ppr_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ppr = 1;
+  if (__any_sync(0xffffffffu, edge) && (threadIdx.x & 31) == 0) c.gi[b].edge = 1;
+  if (MODE == 3) {
+    if (__any_sync(0xffffffffu, ext_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ext = 1;
+    if (__any_sync(0xffffffffu, fixed_any) && (threadIdx.x & 31) == 0) c.gi[b].any_fixed = 1;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -250,6 +277,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
 // ---------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   GridInfo<I>& g = c.gi[b];
@@ -265,6 +293,7 @@ __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
 // cell is fixed up by k_finalize).
 template <typename F>
 __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,6 +443,7 @@ __device__ __forceinline__ void radix_scatter_tile(const Ctx<F>& c, int b, int t
 // see sorted_perm_buffer().
 template <typename F>
 __global__ void __launch_bounds__(256) k_radix_sort(Ctx<F> c) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   cg::grid_group grid = cg::this_grid();
   __shared__ int whist[8][256];
@@ -452,6 +482,7 @@ inline const int* sorted_perm_buffer(const Ctx<F>& c) {
 // ---------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restrict__ sorted_perm) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,9 +522,10 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
     c.sclump[gd] = (int)c.clump_id[gi] | (has_bond ? 0x80000000 : 0);
   }
   if (c.nmat > 1) c.smat[gd] = (int)c.mat_id[gi];
+  if (c.fused) c.svel[gd] = c.uvel[gi];
   if (c.law == JDB200_LAW_CUNDALLSTRACK) {
     const F* v = c.vel + gi * c.dim;
-    c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};
+    if (!c.fused) c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};
     const F* w = c.ang_vel + gi * c.A;
     c.sang[gd] = c.dim == 3 ? Vec4<F>{w[0], w[1], w[2], F(0)} : Vec4<F>{F(0), F(0), w[0], F(0)};
   }
@@ -517,6 +549,7 @@ static int launch_hash(cudaStream_t s, Ctx<F>& c, const F* cso, int mode, bool e
   const dim3 grid(cdiv(c.n, 256), c.batch);
   if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0, false>), grid, 256, s, c, cso);
   else if (mode == 1) JDB_LAUNCH((k_hash<F, D, 1, false>), grid, 256, s, c, cso);
+  else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3, false>), grid, 256, s, c, cso);
   else if (ext) JDB_LAUNCH((k_hash<F, D, 2, true>), grid, 256, s, c, cso);
   else JDB_LAUNCH((k_hash<F, D, 2, false>), grid, 256, s, c, cso);
   return 0;

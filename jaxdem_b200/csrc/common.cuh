@@ -27,6 +27,7 @@ struct RT<float> {
   static __device__ __forceinline__ float floor(float a) { return floorf(a); }
   static __device__ __forceinline__ float ceil(float a) { return ceilf(a); }
   static __device__ __forceinline__ float fmod(float a, float b) { return fmodf(a, b); }
+  static __device__ __forceinline__ float trunc(float a) { return truncf(a); }
   static __device__ __forceinline__ float rint(float a) { return rintf(a); }  // half-to-even
   static __device__ __forceinline__ float sqrt(float a) { return sqrtf(a); }
   static __device__ __forceinline__ float rsqrt(float a) { return rsqrtf(a); }
@@ -51,6 +52,7 @@ struct RT<double> {
   static __device__ __forceinline__ double floor(double a) { return ::floor(a); }
   static __device__ __forceinline__ double ceil(double a) { return ::ceil(a); }
   static __device__ __forceinline__ double fmod(double a, double b) { return ::fmod(a, b); }
+  static __device__ __forceinline__ double trunc(double a) { return ::trunc(a); }
   static __device__ __forceinline__ double rint(double a) { return ::rint(a); }
   static __device__ __forceinline__ double sqrt(double a) { return ::sqrt(a); }
   static __device__ __forceinline__ double rsqrt(double a) { return 1.0 / ::sqrt(a); }
@@ -117,7 +119,9 @@ struct GridInfo {
   int range;         // R of the canonical stencil
   int any_bond;      // some particle has a bond_id >= 0 (set by the hash kernel)
   int any_ppr;       // some particle has a non-zero _pos_p_rot (set by the hash kernel)
-  int pad[3];
+  int any_ext;       // some external force / torque buffer entry is non-zero (fused hash kernel)
+  int any_fixed;     // some particle is fixed (fused hash kernel)
+  int edge;          // some cell coordinate lies outside [0, g) (periodic: rounded up to g), so its hash aliases another cell: keys cannot be decoded
 };
 
 template <typename F, typename I>
@@ -150,7 +154,9 @@ __device__ __forceinline__ I cell_coord(F x, F anchor, F box, F cell_size, I g, 
   using T = RT<F>;
   if (periodic) {
     F u = T::div(T::sub(x, anchor), box);
-    F r = T::fmod(u, F(1));                  // jnp.remainder(u, 1): fmod + sign fix-up
+    // jnp.remainder(u, 1) = fmod(u, 1) + sign fix-up; fmod(u, 1) == u - trunc(u) EXACTLY for
+    // every finite u (trunc(u) is exact and the difference is representable), NaN for inf/NaN
+    F r = T::sub(u, T::trunc(u));
     if (r != F(0) && r < F(0)) r = T::add(r, F(1));
     return T::to_int(T::floor(T::mul(r, T::from_int(g))));
   }

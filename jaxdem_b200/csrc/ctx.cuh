@@ -12,6 +12,7 @@ struct Ctx {
   long long max_cells;
   long long cell_stride;  // ints per system in the dense cell tables (max_cells + 1 rounded up to 64)
   int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
+  int fused;  // fused sphere step driver (abi.cu system_step): hash kernel integrates, pair kernel finishes the step
   // state (in place)
   F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;
   I *clump_id, *mat_id, *bond_id;
@@ -32,6 +33,7 @@ struct Ctx {
   int* cell_start;             // [B*(max_cells+1)] exclusive starts (dense)
   int* tmp_key;                // [B*N] dense key of the particle in arrival slot k
   Vec4<F>* upos;               // [B*N] (x, y, z, rad) in ORIGINAL order (pos = pos_c + pos_p_rot)
+  Vec4<F>* uvel;               // [B*N] (vx, vy, vz, mass) in ORIGINAL order, after the before-force kick (fused driver)
   unsigned* coop_bar;          // [4] software state of the cooperative sort fallback
   int want_skey;               // host flag: dense builds also fill skey (partition export)
   unsigned long long* tile_state;  // [B*scan_tiles] decoupled look-back descriptors
@@ -78,6 +80,7 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start = b.take<int>(B * (size_t)c.cell_stride);
   c.tmp_key = b.take<int>(BN);
   c.upos = b.take<Vec4<F>>(BN);
+  c.uvel = b.take<Vec4<F>>(BN);
   c.coop_bar = b.take<unsigned>(4);
   c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);
   c.tile_counter = b.take<int>(B);

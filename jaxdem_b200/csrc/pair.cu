@@ -135,6 +135,12 @@ __device__ __forceinline__ bool fast_walk_ok(const GridInfo<I>& g) {
   return g.dense && !g.dense_fail && g.canonical && !g.need_dedup;
 }
 
+// the flat kernel (k_pair_flat) additionally wants the default stencil range R = 1
+template <typename I>
+__device__ __forceinline__ bool flat_walk_ok(const GridInfo<I>& g) {
+  return fast_walk_ok(g) && g.range == 1 && !g.edge;
+}
+
 // wrap n into [0, g) for |n| < 2g: identical to n - g*floor(n/g) (cell_list.py:70-72)
 __device__ __forceinline__ int wrap1(int n, int g) { return n < 0 ? n + g : (n >= g ? n - g : n); }
 
@@ -289,7 +295,77 @@ __device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx,
   }
 }
 
-template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
+// Fused sphere driver (abi.cu system_step): what follows the collider inside _step_once for a
+// sphere system (clump_id == arange(N)) with velocity Verlet and no rotation integrator, done
+// by the thread that owns the particle while the contact force is still in registers:
+//   DynamicCellList.compute_force epilogue  torque = sum T + cross(_pos_p_rot, sum F)   (cell_list.py:461-462)
+//   ForceManager.apply with count == 1      (force_manager.py:359-423)
+//   VelocityVerlet.step_after_force         (velocity_verlet.py:92-95)
+// Same expressions, same order per particle as k_fm_spheres + k_linear.  The kicked velocity
+// and the mass (vm) come from the sorted shadow record written by k_hash<MODE 3>; external
+// buffers and fixed flags are gathered only when that kernel saw a non-zero entry (they are
+// zero otherwise, and stay zero).
+template <typename F, int D>
+__device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
+                                                      const GridInfo<typename RT<F>::I>& g, const Vec4<F>& vm,
+                                                      int idx, const F* f, const F* t, bool with_torque) {
+  using T = RT<F>;
+  constexpr int A = D == 3 ? 3 : 1;
+  const size_t off = (size_t)b * c.n, gi = off + idx;
+  const F v[3] = {vm.x, vm.y, vm.z}, mass = vm.w;
+  const F dt = c.dt[b];
+  F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0}, et[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
+  F free = F(1);
+  if (g.any_fixed) free = c.fixed[gi] ? F(0) : F(1);
+#pragma unroll
+  for (int d = 0; d < D; ++d) grav[d] = c.gravity[b * D + d];
+  if (g.any_ppr) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = c.pos_p_rot[gi * D + d];
+  }
+  if (g.any_ext) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      fp[d] = c.ext_force[gi * D + d];
+      fc[d] = c.ext_force_com[gi * D + d];
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) et[a] = c.ext_torque[gi * A + a];
+  }
+  const F sc = T::div(T::mul(dt, F(0.5)), mass);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
+    const F ft = T::add(T::add(f[d], fp[d]), fcom);
+    c.force[gi * D + d] = ft;
+    c.vel[gi * D + d] = T::add(v[d], T::mul(T::mul(ft, sc), free));
+  }
+  if (g.any_ext) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      c.ext_force[gi * D + d] = F(0);
+      c.ext_force_com[gi * D + d] = F(0);
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) c.ext_torque[gi * A + a] = F(0);
+  }
+  if (!with_torque) return;
+  if (D == 3) {
+    // collider: t + cross(r, f) (contracted like store_force_torque); manager: unfused cross(r, fp)
+    const F tc[3] = {t[0] + (r[1] * f[2] - r[2] * f[1]), t[1] + (r[2] * f[0] - r[0] * f[2]),
+                     t[2] + (r[0] * f[1] - r[1] * f[0])};
+    const F cr[3] = {T::sub(T::mul(r[1], fp[2]), T::mul(r[2], fp[1])), T::sub(T::mul(r[2], fp[0]), T::mul(r[0], fp[2])),
+                     T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]))};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c.torque[gi * 3 + a] = T::add(tc[a], T::add(et[a], cr[a]));
+  } else {
+    const F tc = t[2] + (r[0] * f[1] - r[1] * f[0]);
+    const F cr = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
+    c.torque[gi] = T::add(tc, T::add(et[0], cr));
+  }
+}
+
+template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE, int EPI>
 __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
                                                 const GridInfo<typename RT<F>::I>& g, bool fast,
                                                 int with_torque) {
@@ -311,31 +387,349 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
-  store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.svel[off + k], vis.idx, vis.f, vis.t, with_torque != 0);
+  else store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
+}
+
+
+// ---------------------------------------------------------------------------
+// K4 main path: flat candidate walk.  Serves the systems whose partition is a dense table
+// with the default 3^D stencil (flat_walk_ok).  One thread owns one particle (sorted slot k):
+//   A  the 3^(D-1) stencil rows become slot ranges (x-runs of up to three cells; where the
+//      run wraps around the periodic box the wrapped cells are a range of their own), kept
+//      as (start, length) in a shared-memory column private to the thread; the first line
+//      of every range is prefetched into L1;
+//   B  ONE loop over the concatenated ranges (trip count = number of candidates, so lanes of a
+//      warp stay busy across row boundaries) does nothing but the overlap test
+//      |rij|^2 < (Ri + Rj)^2 and pushes the ordinal of every hit onto a per-thread contact
+//      list in shared memory.  Neighbouring lanes read neighbouring records of the sorted
+//      (x, y, z, rad) array, so the loads of a warp coalesce and hit L1;
+//   C  the contact list is evaluated with the force law: most lanes have work in every
+//      iteration, instead of ~1 lane in 8 when the law sits inside the candidate loop.
+// The kernel keeps registers (<= 64) and shared memory (14.25 KB per 128 threads) low on
+// purpose: it is bound by dependent-issue latency, and 32 resident warps per SM hide it.
+// Candidates are visited rows z-major, slots ascending, wrapped cells after the main run of
+// their row; contacts are summed in that order: deterministic, no atomics, no barriers.
+// EPI 0: DynamicCellList.compute_force epilogue (force / torque stores);
+// EPI 1: fused sphere driver epilogue (fused_sphere_epilogue).
+// ---------------------------------------------------------------------------
+template <int D>
+struct FlatCfg {
+  static constexpr int kThreads = 128;
+  static constexpr int kRows = D == 3 ? 9 : 3;
+  static constexpr int kRanges = 2 * kRows;  // main + wrapped range per row
+  static constexpr int kCap = 12;            // contact-list rows; a full list is evaluated and reused
+  static constexpr int kOffLen = kRanges * kThreads * 4;            // u8  [kRanges][kThreads]
+  static constexpr int kOffCl = kOffLen + kRanges * kThreads;       // u32 [kCap][kThreads]: sorted slots of the hits
+  static constexpr int kBytes = kOffCl + kCap * kThreads * 4;       // starts: u32 [kRanges][kThreads] at 0
+};
+
+// keeps the compiler from folding a base pointer back into per-access 64-bit index arithmetic
+template <typename P>
+__device__ __forceinline__ P* opaque_ptr(P* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ Vec4<float> ldg_vec4(const Vec4<float>* p) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  return Vec4<float>{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ Vec4<double> ldg_vec4(const Vec4<double>* p) {
+  const double2 u = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return Vec4<double>{u.x, u.y, v.x, v.y};
+}
+// explicit shared-memory accesses (32-bit shared addresses): the hot loop is a handful of
+// instructions per candidate and must not re-derive generic addresses
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// the overlap test of phase B
+template <typename F, int D, bool PERIODIC>
+__device__ __forceinline__ bool flat_overlap(const LawCtx<F>& lc, const Body<F>& a, const Vec4<F>& q, F hbmin2) {
+  using T = RT<F>;
+  F rx = T::sub(a.x, q.x), ry = T::sub(a.y, q.y), rz = D == 3 ? T::sub(a.z, q.z) : F(0);
+  F d2 = rx * rx + ry * ry + rz * rz;
+  if (PERIODIC && !(d2 < hbmin2)) {  // across the periodic boundary (rare): Domain._displacement
+    rx = T::sub(rx, T::mul(lc.box[0], T::rint(T::mul(rx, lc.inv_box[0]))));
+    ry = T::sub(ry, T::mul(lc.box[1], T::rint(T::mul(ry, lc.inv_box[1]))));
+    if (D == 3) rz = T::sub(rz, T::mul(lc.box[2], T::rint(T::mul(rz, lc.inv_box[2]))));
+    d2 = rx * rx + ry * ry + rz * rz;
+  }
+  const F rs = a.r + q.w;
+  // no overlap => every law returns exactly zero force and torque (the margin keeps pairs
+  // within rounding of touching on the list)
+  return d2 < rs * rs * F(1.00001);
+}
+
+// n / d for 0 <= n < 2^31, d >= 1, with rcp = 1.0f / d: float estimate + exact fix-up
+__device__ __forceinline__ int div_fix(int n, int d, float rcp, int& rem) {
+  int q = __float2int_rz(__int2float_rz(n) * rcp);
+  int r = n - q * d;
+  while (r < 0) { --q; r += d; }
+  while (r >= d) { ++q; r -= d; }
+  rem = r;
+  return q;
+}
+
+template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE, int EPI>
+__device__ __forceinline__ void pair_flat_body(const Ctx<F>& c, int b, int k,
+                                               const GridInfo<typename RT<F>::I>& g, int with_torque,
+                                               unsigned sbase) {
+  using T = RT<F>;
+  using Cfg = FlatCfg<D>;
+  constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
+  constexpr int NZ = D == 3 ? 3 : 1;
+  constexpr unsigned kT = Cfg::kThreads;
+  const unsigned tid = threadIdx.x;
+  const unsigned rg0 = sbase + tid * 4;                  // range starts, this thread's column
+  const unsigned ln0 = sbase + Cfg::kOffLen + tid;       // range lengths
+  const unsigned cl0 = sbase + Cfg::kOffCl + tid * 4;    // contact slots
+  const size_t off = (size_t)b * c.n;
+  const Vec4<F>* sp = opaque_ptr(c.spos + off);
+  const int* cst = opaque_ptr(c.cell_start + (size_t)b * c.cell_stride);
+  // loads whose latency the range set-up hides: own record, key, index, fused-epilogue record
+  const Body<F> a = load_sorted(c, off, k, CS);
+  const int key = c.tmp_key[off + k];  // hash of slot k (k_scatter; the in-cell fix-up keeps cells in place)
+  const int idx = c.perm[off + k];
+  Vec4<F> vm = Vec4<F>{0, 0, 0, 0};
+  if (EPI == 1) vm = c.svel[off + k];
+  const int clump = SIMPLE ? 0 : (c.sclump[off + k] & 0x7fffffff);
+  const bool interact = c.interact && c.interact[b];
+  const LawCtx<F> lc = make_law_ctx(c, b);
+
+  // ---- A: stencil rows -> slot ranges (wrapped / out-of-grid rules of cell_list.py:66-80).
+  // Cell coordinates are decoded from the hash: flat_walk_ok() guarantees that every
+  // coordinate of the system lies in [0, g), so hash <-> coordinates is one-to-one ----
+  unsigned rga = rg0, lna = ln0;
+  int total = 0;
+  {
+    const int gx = (int)g.gd[0], gy = (int)g.gd[1], gz = (int)g.gd[2];
+    const int sy = gx, sz = gx * gy;  // strides of the x-fastest hash (_partition.py:91-93)
+    int cx, cy, cz = 0;
+    const int tq = div_fix(key, gx, __frcp_rn(__int2float_rn(gx)), cx);
+    if (D == 3) cz = div_fix(tq, gy, __frcp_rn(__int2float_rn(gy)), cy);
+    else cy = tq;
+    // main x segment: the cells of [cx - 1, cx + 1] inside the grid; periodic: the cell
+    // outside wraps around to the second segment (the grid has >= 3 cells per axis here)
+    const int x1 = max(cx - 1, 0);
+    const int n1 = min(cx + 1, gx - 1) - x1 + 1;
+    int x2 = -1;
+    if (PERIODIC) x2 = cx == 0 ? gx - 1 : (cx == gx - 1 ? 0 : -1);
+    int yb[3], zb[3];  // ny * stride_y, nz * stride_z; -1: row outside a non-periodic grid
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int ny = cy + j - 1;
+      if (PERIODIC) yb[j] = wrap1(ny, gy) * sy;
+      else yb[j] = (ny >= 0 && ny < gy) ? ny * sy : -1;
+      const int nz = cz + j - 1;
+      if (D != 3) zb[j] = 0;
+      else if (PERIODIC) zb[j] = wrap1(nz, gz) * sz;
+      else zb[j] = (nz >= 0 && nz < gz) ? nz * sz : -1;
+    }
+    int s1[Cfg::kRows], e1[Cfg::kRows];
+#pragma unroll
+    for (int iz = 0; iz < NZ; ++iz) {
+#pragma unroll
+      for (int iy = 0; iy < 3; ++iy) {
+        const int r = iz * 3 + iy;
+        const int zrow = D == 3 ? zb[iz] : 0;
+        const bool ok = PERIODIC || (yb[iy] >= 0 && zrow >= 0);
+        const int h0 = yb[iy] + zrow + x1;
+        s1[r] = ok ? cst[h0] : 0;
+        e1[r] = ok ? cst[h0 + n1] : 0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < Cfg::kRows; ++r) {
+      if (e1[r] > s1[r]) {
+        sts_u32(rga, (unsigned)s1[r]);
+        sts_u8(lna, (unsigned)(e1[r] - s1[r]));
+        rga += kT * 4;
+        lna += kT;
+        total += e1[r] - s1[r];
+      }
+    }
+    if (PERIODIC && x2 >= 0) {  // boundary lanes: the wrapped cell of every row
+#pragma unroll
+      for (int iz = 0; iz < NZ; ++iz) {
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+          const int h2 = yb[iy] + (D == 3 ? zb[iz] : 0) + x2;
+          const int s2 = cst[h2], e2 = cst[h2 + 1];
+          if (e2 > s2) {
+            sts_u32(rga, (unsigned)s2);
+            sts_u8(lna, (unsigned)(e2 - s2));
+            rga += kT * 4;
+            lna += kT;
+            total += e2 - s2;
+          }
+        }
+      }
+    }
+  }
+  // |rij|^2 below this => every |rij_d| < box_d / 2 => the minimum-image term is exactly zero
+  F hbmin2 = F(0);
+  if (PERIODIC) {
+    F m = lc.box[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) m = T::fmin(m, lc.box[d]);
+    m *= F(0.499999);
+    hbmin2 = m * m;
+  }
+  F f[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+
+  rga = rg0;
+  lna = ln0;
+  int it = 0, kj = 0, ke = 0;
+  while (it < total) {
+    // ---- B: overlap tests, two candidates per trip (both loads in flight together) ----
+    unsigned cla = cl0;
+    const unsigned cle = cl0 + (Cfg::kCap - 1) * kT * 4;  // room for two pushes
+    do {
+      if (kj == ke) {
+        kj = (int)lds_u32(rga);
+        ke = kj + (int)lds_u8(lna);
+        rga += kT * 4;
+        lna += kT;
+      }
+      const int ka = kj++;
+      const bool two = it + 1 < total;
+      if (two && kj == ke) {
+        kj = (int)lds_u32(rga);
+        ke = kj + (int)lds_u8(lna);
+        rga += kT * 4;
+        lna += kT;
+      }
+      const int kb = two ? kj : ka;
+      kj += two ? 1 : 0;
+      const Vec4<F> qa = ldg_vec4(sp + ka);
+      const Vec4<F> qb = ldg_vec4(sp + kb);
+      if (flat_overlap<F, D, PERIODIC>(lc, a, qa, hbmin2)) {
+        sts_u32(cla, (unsigned)ka);
+        cla += kT * 4;
+      }
+      if (flat_overlap<F, D, PERIODIC>(lc, a, qb, hbmin2) && two) {
+        sts_u32(cla, (unsigned)kb);
+        cla += kT * 4;
+      }
+      it += 2;
+    } while (it < total && cla < cle);
+    // ---- C: force law on the contacts (the next contact's record is loaded ahead) ----
+    if (cla != cl0) {
+      int kc = (int)lds_u32(cl0);
+      Vec4<F> q = ldg_vec4(sp + kc);
+      for (unsigned ca = cl0; ca != cla; ca += kT * 4) {
+        const int kcur = kc;
+        const Vec4<F> qc = q;
+        if (ca + kT * 4 != cla) {
+          kc = (int)lds_u32(ca + kT * 4);
+          q = ldg_vec4(sp + kc);
+        }
+        if (SIMPLE) {
+          if (kcur == k) continue;  // clump_id == arange(N): only the particle itself is excluded
+        } else {
+          const int sc = c.sclump[off + kcur];
+          if (!pair_valid(c, off, idx, clump, sc, kcur, interact)) continue;
+        }
+        F rij[3] = {T::sub(a.x, qc.x), T::sub(a.y, qc.y), D == 3 ? T::sub(a.z, qc.z) : F(0)};
+        if (PERIODIC) {
+          const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+          if (!(d2 < hbmin2)) {
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+              rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
+          }
+        }
+        Body<F> bj;
+        bj.x = qc.x; bj.y = qc.y; bj.z = qc.z; bj.r = qc.w;
+        bj.mat = (c.nmat > 1) ? c.smat[off + kcur] : 0;
+        if (CS) {
+          const Vec4<F> v = c.svel[off + kcur];
+          const Vec4<F> w = c.sang[off + kcur];
+          bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
+          bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
+        }
+        F ff[3], tt[3];
+        pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
+        f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
+        if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+      }
+    }
+  }
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, vm, idx, f, t, with_torque != 0);
+  else store_force_torque<F, D>(c, off + idx, f, t, g.any_ppr != 0, with_torque != 0);
+}
+
+template <typename F, int LAW, int D, bool PERIODIC, int EPI>
+__global__ void __launch_bounds__(FlatCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_flat(Ctx<F> c, int with_torque) {
+  pdl_prologue();
+  using I = typename RT<F>::I;
+  __shared__ __align__(16) unsigned char smem[FlatCfg<D>::kBytes];
+  const int b = blockIdx.y;
+  const GridInfo<I> g = c.gi[b];
+  const bool mine = flat_walk_ok(g);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
+    if (mine) c.overflow[b] = (uint8_t)g.hash_overflow;
+    else if (c.grid_mode == JDB200_GRID_DENSE) c.overflow[b] = 1;  // nobody else serves this system
+  }
+  if (!mine) return;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n) return;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+  if (!c.clumps && !g.any_bond) pair_flat_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, with_torque, sbase);
+  else pair_flat_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, with_torque, sbase);
 }
 
 // FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
 // (sorted fallback, custom stencils, periodic de-dup).  Both kernels are launched; each
 // exits at once for the systems the other one owns.
-template <typename F, int LAW, int D, bool PERIODIC, bool FAST>
+template <typename F, int LAW, int D, bool PERIODIC, bool FAST, int EPI>
 __global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
-  const bool mine = fast_walk_ok(g) == FAST;
+  // FAST = false also serves the systems the flat kernel (below) cannot: stencil range > 1
+  // FAST: wider canonical stencils (range != 1; launched instead of the flat kernel when M != 3^D)
+  const bool mine = FAST ? (fast_walk_ok(g) && g.range != 1) : !(flat_walk_ok(g) || (fast_walk_ok(g) && g.range != 1));
   // Collider.overflow (cell_list.py:463).  JDB200_GRID_DENSE launches only the FAST kernel: a
   // system it cannot serve (table too small, custom stencil, periodic de-dup) raises the flag.
-  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow &&
-      (mine || (FAST && c.grid_mode == JDB200_GRID_DENSE)))
-    c.overflow[b] = (uint8_t)(g.hash_overflow || !mine);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
+    if (mine) c.overflow[b] = (uint8_t)g.hash_overflow;
+    else if (FAST && c.grid_mode == JDB200_GRID_DENSE && !fast_walk_ok(g)) c.overflow[b] = 1;
+  }
   if (!mine) return;
   const bool simple = !c.clumps && !g.any_bond;
   // the FAST kernel has one thread per particle; the fallback kernel is launched with a
   // small grid (an idle launch must cost nothing) and strides over the particles
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < c.n;
        k += (long long)gridDim.x * blockDim.x) {
-    if (simple) pair_force_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, FAST, with_torque);
-    else pair_force_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, FAST, with_torque);
+    if (simple) pair_force_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, FAST, with_torque);
+    else pair_force_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, FAST, with_torque);
   }
 }
 
@@ -383,6 +777,7 @@ __device__ __forceinline__ F block_sum_256(F v) {  // fixed tree order => determ
 
 template <typename F, int LAW>
 __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -421,6 +816,7 @@ __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
 template <typename F>
 __global__ void __launch_bounds__(kReduceBlock) k_final_sum(const F* __restrict__ partial, int nblocks,
                                                              F* __restrict__ out) {
+  pdl_prologue();
   const int b = blockIdx.x;
   F acc = F(0);
   for (int i = threadIdx.x; i < nblocks; i += kReduceBlock) acc += partial[(size_t)b * nblocks + i];
@@ -479,6 +875,7 @@ template <typename F>
 __global__ void __launch_bounds__(128) k_neighbor_list(Ctx<F> c, const F* __restrict__ cell_size_nl,
                                                         const F* __restrict__ cutoff,
                                                         typename RT<F>::I* __restrict__ nl) {
+  pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,6 +900,7 @@ __global__ void __launch_bounds__(128) k_neighbor_list(Ctx<F> c, const F* __rest
 
 template <typename F>
 __global__ void k_nl_cell_size(Ctx<F> c, const F* __restrict__ cutoff, F* __restrict__ out) {
+  pdl_prologue();
   // cell_list.py:537-538: cell_size = max(cell_size, cutoff / max(max(neighbor_mask), 1))
   using I = typename RT<F>::I;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,6 +913,7 @@ __global__ void k_nl_cell_size(Ctx<F> c, const F* __restrict__ cutoff, F* __rest
 
 template <typename F>
 __global__ void k_nl_flag(Ctx<F> c, uint8_t* __restrict__ overflow) {
+  pdl_prologue();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= c.batch) return;
   overflow[b] = (uint8_t)(c.gi[b].nl_overflow || c.gi[b].hash_overflow);
@@ -538,6 +937,7 @@ __device__ __forceinline__ bool naive_valid(const Ctx<F>& c, size_t off, int i, 
 
 template <typename F, int LAW>
 __global__ void __launch_bounds__(128) k_naive_force(Ctx<F> c) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -561,6 +961,7 @@ __global__ void __launch_bounds__(128) k_naive_force(Ctx<F> c) {
 
 template <typename F, int LAW>
 __global__ void __launch_bounds__(kReduceBlock) k_naive_energy(Ctx<F> c) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t off = (size_t)b * c.n;
@@ -591,26 +992,40 @@ int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override, int 
     default: { constexpr int L = JDB200_LAW_CUNDALLSTRACK; CALL; } break;                   \
   }
 
-template <typename F, int D>
-int launch_pair_force(cudaStream_t s, Ctx<F>& c, bool with_torque) {
+template <typename F, int D, int EPI>
+int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
   const dim3 grid(cdiv(c.n, 128), c.batch);
   const int wt = with_torque ? 1 : 0;
-  if (c.max_cells > 0) {  // a dense table exists: the x-run kernel owns the systems it can serve
-    if (c.periodic) {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true>), grid, 128, s, c, wt));
+  if (c.max_cells > 0) {  // a dense table exists
+    if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the flat kernel owns the systems it can serve
+      constexpr int kT = FlatCfg<D>::kThreads;
+      const dim3 gf(cdiv(c.n, kT), c.batch);
+      if (c.periodic) {
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, true, EPI>), gf, kT, s, c, wt));
+      } else {
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, false, EPI>), gf, kT, s, c, wt));
+      }
+    } else if (c.periodic) {         // wider canonical stencils: x-run kernel
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true, EPI>), grid, 128, s, c, wt));
     } else {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, true>), grid, 128, s, c, wt));
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, true, EPI>), grid, 128, s, c, wt));
     }
   }
   if (c.grid_mode != JDB200_GRID_DENSE || c.max_cells == 0) {  // everything else
     const dim3 gs(std::min(cdiv(c.n, 128), std::max(1, 4736 / c.batch)), c.batch);  // <= 32 CTAs per SM
     if (c.periodic) {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false>), gs, 128, s, c, wt));
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false, EPI>), gs, 128, s, c, wt));
     } else {
-      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false>), gs, 128, s, c, wt));
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false, EPI>), gs, 128, s, c, wt));
     }
   }
   return 0;
+}
+
+template <typename F, int D>
+int launch_pair_force(cudaStream_t s, Ctx<F>& c, bool with_torque) {
+  return c.fused ? launch_pair_force_epi<F, D, 1>(s, c, with_torque)
+                 : launch_pair_force_epi<F, D, 0>(s, c, with_torque);
 }
 
 // hash_mode / ext: fusion of the linear integrator into the hash kernel (celllist.cu k_hash);

@@ -22,6 +22,7 @@ using T_ = RT<F>;
 // (direct_euler.py:62-66) [full kick + drift].
 template <typename F, bool HALF, bool DRIFT>
 __global__ void __launch_bounds__(256) k_linear(Ctx<F> c) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // element of (N, D)
@@ -186,6 +187,7 @@ __device__ __forceinline__ void store_q_and_cache(const Ctx<F>& c, size_t gi, co
 // MODE 2: Spiral.step_after_force                (spiral.py:104-141)
 template <typename F, int MODE>
 __global__ void __launch_bounds__(256) k_rotation(Ctx<F> c) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(256) k_rotation(Ctx<F> c) {
 template <typename F>
 __global__ void __launch_bounds__(256) k_clump_zero(Ctx<F> c, int* cl_start, unsigned long long* ts,
                                                      int* tc, int tiles) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= c.n) cl_start[(size_t)b * (c.n + 1) + i] = 0;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(256) k_clump_zero(Ctx<F> c, int* cl_start, uns
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_clump_count(Ctx<F> c, int* cl_start, int* cl_rank) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -269,12 +273,14 @@ __global__ void __launch_bounds__(256) k_clump_count(Ctx<F> c, int* cl_start, in
 template <typename F>
 __global__ void __launch_bounds__(512) k_clump_scan(Ctx<F> c, int* cl_start, unsigned long long* ts,
                                                      int* tc, int tiles) {
+  pdl_prologue();
   const int b = blockIdx.y;
   scan_tile(cl_start + (size_t)b * (c.n + 1), cl_start + (size_t)b * (c.n + 1), c.n + 1, ts + (size_t)b * tiles, &tc[b], 0x7fffffff);
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_clump_scatter(Ctx<F> c, const int* cl_start, const int* cl_rank,
                                                         int* tmp) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(256) k_clump_scatter(Ctx<F> c, const int* cl_s
 template <typename F>
 __global__ void __launch_bounds__(256) k_clump_order(Ctx<F> c, const int* cl_start, const int* tmp,
                                                       int* members) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -363,6 +370,7 @@ __device__ __forceinline__ void fm_totals(const Ctx<F>& c, int b, size_t gi, F c
 
 template <typename F>
 __global__ void __launch_bounds__(256) k_fm_spheres(Ctx<F> c) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(256) k_fm_spheres(Ctx<F> c) {
 
 template <typename F>
 __global__ void __launch_bounds__(256) k_fm_totals(Ctx<F> c, ClumpCsr<F> csr) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(256) k_fm_totals(Ctx<F> c, ClumpCsr<F> csr) {
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,6 +434,7 @@ __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
 // pass.  EXT = false: the external buffers are known to be zero (cleared earlier in the call).
 template <typename F, int D, bool EXT>
 __global__ void __launch_bounds__(256) k_fm_after(Ctx<F> c) {
+  pdl_prologue();
   using T = RT<F>;
   constexpr int A = D == 3 ? 3 : 1;
   const int b = blockIdx.y;
@@ -516,6 +527,7 @@ int force_manager_apply(cudaStream_t s, Ctx<F>& c) {
 // ---------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(256) k_free_partial(Ctx<F> c, F* part) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -550,6 +562,7 @@ __global__ void __launch_bounds__(256) k_free_partial(Ctx<F> c, F* part) {
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_free_final(Ctx<F> c, const F* part, int nblocks) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.x;
   const F inf = F(1) / F(0);
@@ -584,6 +597,7 @@ __global__ void __launch_bounds__(256) k_free_final(Ctx<F> c, const F* part, int
 
 template <typename F>
 __global__ void k_inv_box(Ctx<F> c) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < c.batch * c.dim) c.inv_box[e] = RT<F>::div(F(1), c.box[e]);
 }
@@ -778,6 +792,7 @@ __device__ __forceinline__ void reflect_update(const Ctx<F>& c, int b, size_t gi
 
 template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -806,7 +821,8 @@ __global__ void __launch_bounds__(128) k_reflect_spheres(Ctx<F> c) {
 
 // general clumps: 4 phases through scratch (segf, 8 F per sphere + seg2, 8 F per sphere)
 template <typename F, int D>
-__global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {  // over_lo / over_hi
+__global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {
+  pdl_prologue();  // over_lo / over_hi
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
@@ -822,6 +838,7 @@ __global__ void __launch_bounds__(128) k_reflect_p1(Ctx<F> c) {  // over_lo / ov
 }
 template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F* seg2) {
+  pdl_prologue();
   // clump maxima -> wall_sign / active / alpha_min_dim per sphere
   using T = RT<F>;
   const int b = blockIdx.y;
@@ -860,6 +877,7 @@ __global__ void __launch_bounds__(128) k_reflect_p2(Ctx<F> c, ClumpCsr<F> csr, F
 }
 template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, const F* seg2) {
+  pdl_prologue();
   // clump alpha / active counts -> per-sphere impulse contributions (into segf)
   using T = RT<F>;
   const int b = blockIdx.y;
@@ -891,6 +909,7 @@ __global__ void __launch_bounds__(128) k_reflect_p3(Ctx<F> c, ClumpCsr<F> csr, c
 }
 template <typename F, int D>
 __global__ void __launch_bounds__(128) k_reflect_p4(Ctx<F> c, ClumpCsr<F> csr) {
+  pdl_prologue();
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
