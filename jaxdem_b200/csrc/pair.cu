@@ -1012,7 +1012,7 @@ int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
     }
   }
   if (c.grid_mode != JDB200_GRID_DENSE || c.max_cells == 0) {  // everything else
-    const dim3 gs(std::min(cdiv(c.n, 128), std::max(1, 4736 / c.batch)), c.batch);  // <= 32 CTAs per SM
+    const dim3 gs(std::min(cdiv(c.n, 128), std::max(1, 1184 / c.batch)), c.batch);  // <= 8 CTAs per SM: an idle launch is cheap
     if (c.periodic) {
       JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false, EPI>), gs, 128, s, c, wt));
     } else {
