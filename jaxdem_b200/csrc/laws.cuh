@@ -21,6 +21,7 @@ template <typename F>
 struct LawCtx {
   F box[3], inv_box[3];
   const F *young, *poisson, *e, *mu, *mu_r, *young_eff;
+  F k0;  // young_eff[0, 0], preloaded: the spring stiffness of single-material systems
   int nmat;
   bool periodic;
 };
@@ -40,6 +41,7 @@ __device__ __forceinline__ LawCtx<F> make_law_ctx(const Ctx<F>& c, int b) {
   lc.mu_r = c.mu_r ? c.mu_r + mo : nullptr;
   lc.young_eff = c.young_eff ? c.young_eff + mo * c.nmat : nullptr;
   lc.nmat = c.nmat;
+  lc.k0 = (c.law == JDB200_LAW_SPRING && c.nmat == 1 && c.young_eff) ? lc.young_eff[0] : F(0);
   lc.periodic = c.periodic;
   return lc;
 }
@@ -108,7 +110,7 @@ __device__ __forceinline__ void pair_force_rij(const LawCtx<F>& lc, const Body<F
     // jaxdem/forces/spring.py:97-108
     const F R = a.r + b.r;
     const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-    const F k = lc.young_eff[a.mat * lc.nmat + b.mat];
+    const F k = lc.nmat == 1 ? lc.k0 : lc.young_eff[a.mat * lc.nmat + b.mat];
     const F inv = d2 == F(0) ? F(0) : T::rsqrt(T::fmax(d2, F(1e-16)));
     const F r = d2 * inv;
     const F delta = T::fmax(F(0), R - r);

@@ -311,6 +311,31 @@ def test_pins_through_the_gpu_path():
         assert np.allclose(f[1], 0.0, atol=1e-5) and abs(f[0, 0]) > 0.1 and np.allclose(f[0], -f[2], atol=1e-5)
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim,n", [(3, 70000), (2, 20000)])
+@pytest.mark.parametrize("law", ["spring", "hertz", "cundallstrack"])
+@pytest.mark.parametrize("domain,plain", [("periodic", True), ("periodic", False), ("reflect", True), ("reflect", False)])
+def test_tile_kernel_midsize(dtype, dim, n, law, domain, plain):
+    """Systems large enough for interior tiles (the TMA-staged k_pair_tile path) next to
+    edge tiles (k_pair_flat work list): forces and torques against the C restatement,
+    bitwise repeatable.  plain = sphere system (clump_id == arange, no bonds, one material)."""
+    from oracle import c_oracle
+    inp = make_inputs(n, dim, seed=11, dtype=dtype, poly=1.0 if plain else 1.4, phi=0.55,
+                      clumps=not plain, bonds=not plain, nmat=1 if plain else 3)
+    kw = dict(dtype=dtype, domain=domain, law=law, nmat=1 if plain else 3)
+    ost, osy = build_oracle(inp, **kw)
+    gst, gsy = build_gpu(inp, **kw)
+    c_oracle.CStep(ost, osy).compute_force()
+    gsy.collider.compute_force(gst, gsy)
+    assert float(np.abs(ost.force).max()) > 0
+    assert_close(gst.force, ost.force, dtype, "force", factor=4)
+    assert_close(gst.torque, ost.torque, dtype, "torque", factor=4)
+    f1, t1 = gst.force.clone(), gst.torque.clone()
+    gsy.collider.compute_force(gst, gsy)
+    assert torch.equal(f1, gst.force) and torch.equal(t1, gst.torque)
+    assert not bool(gsy.collider.overflow)
+
+
 def test_full_size_properties_1m():
     """BASELINE config 2 at full size (1M spheres): size-independent properties."""
     import jaxdem_b200 as jd
