@@ -123,10 +123,8 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
     g.any_ext = 0;
     g.any_fixed = 0;
     g.edge = 0;
-    g.rmax_bits = 0ull;
     c.tile_counter[b] = 0;
     c.radix_skip[b] = 0;
-    c.wl_count[b] = 0;
   }
 }
 
@@ -163,7 +161,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   const bool live = i < c.n;
   const size_t gidx = (size_t)b * c.n + (live ? i : 0);
   bool bond = false, ppr_nz = false, ext_nz = false, fixed_any = false, edge = false;
-  F rmax = F(0);
   if (live) {
     // ---- all loads first (stores below may alias as far as the compiler knows) ----
     const GridInfo<I> g = c.gi[b];
@@ -186,7 +183,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       }
     }
     const F rad = c.rad[gidx];
-    rmax = RT<F>::fmax(rad, F(0));
     F dt = F(0), mass = F(1);
     bool fixed = false;
     if (MODE != 0) {
@@ -269,17 +265,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   if (__any_sync(0xffffffffu, bond) && (threadIdx.x & 31) == 0) c.gi[b].any_bond = 1;
   if (__any_sync(0xffffffffu, ppr_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ppr = 1;
   if (__any_sync(0xffffffffu, edge) && (threadIdx.x & 31) == 0) c.gi[b].edge = 1;
-  {  // largest radius of the system: the pair kernels' conservative touching distance
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rmax = RT<F>::fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    if ((threadIdx.x & 31) == 0) {
-      unsigned long long bits;
-      if (sizeof(F) == 4) bits = (unsigned long long)__float_as_uint((float)rmax);
-      else bits = (unsigned long long)__double_as_longlong((double)rmax);
-      unsigned long long* dst = &c.gi[b].rmax_bits;
-      if (bits > *((volatile unsigned long long*)dst)) atomicMax(dst, bits);
-    }
-  }
   if (MODE == 3) {
     if (__any_sync(0xffffffffu, ext_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ext = 1;
     if (__any_sync(0xffffffffu, fixed_any) && (threadIdx.x & 31) == 0) c.gi[b].any_fixed = 1;

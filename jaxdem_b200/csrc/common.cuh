@@ -121,7 +121,6 @@ struct GridInfo {
   int any_ppr;       // some particle has a non-zero _pos_p_rot (set by the hash kernel)
   int any_ext;       // some external force / torque buffer entry is non-zero (fused hash kernel)
   int any_fixed;     // some particle is fixed (fused hash kernel)
-  unsigned long long rmax_bits;  // bit pattern of the largest radius (non-negative reals order like unsigned integers; hash kernel)
   int edge;          // some cell coordinate lies outside [0, g) (periodic: rounded up to g), so its hash aliases another cell: keys cannot be decoded
 };
 

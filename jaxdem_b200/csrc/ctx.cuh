@@ -51,15 +51,12 @@ struct Ctx {
   int* cell_start_clump;       // [B*(N+1)] clump CSR starts
   unsigned long long* tile_state_clump;  // [B*tiles(N+1)]
   int* tile_counter_clump;     // [B]
-  int* wl;                     // [B*pair_blocks] pair-kernel CTAs handed from the tile kernel to the flat kernel
-  int* wl_count;               // [B]
-  int scan_tiles, radix_blocks, reduce_blocks, pair_blocks;
+  int scan_tiles, radix_blocks, reduce_blocks;
 };
 
 constexpr int kScanTile = 4096;    // cells per look-back tile (512 threads x 8)
 constexpr int kRadixTile = 2048;   // keys per radix block (256 threads x 8)
 constexpr int kReduceBlock = 256;
-constexpr int kPairBlock = 128;    // particles per CTA of the tile / flat pair kernels
 
 template <typename F>
 inline size_t carve(Ctx<F>& c, void* ws) {
@@ -70,7 +67,6 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.scan_tiles = cdiv(c.max_cells + 1, kScanTile);
   c.radix_blocks = cdiv(c.n, kRadixTile);
   c.reduce_blocks = cdiv(c.n, kReduceBlock);
-  c.pair_blocks = cdiv(c.n, kPairBlock);
   c.gi = b.take<GridInfo<I>>(B);
   c.key = b.take<I>(BN);
   c.key_b = b.take<I>(BN);
@@ -102,8 +98,6 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start_clump = b.take<int>(B * (N + 1));
   c.tile_state_clump = b.take<unsigned long long>(B * (size_t)cdiv(c.n + 1, kScanTile));
   c.tile_counter_clump = b.take<int>(B);
-  c.wl = b.take<int>(B * (size_t)c.pair_blocks);
-  c.wl_count = b.take<int>(B);
   return b.off + 256;
 }
 

@@ -30,12 +30,11 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
-                              Args&&... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -46,13 +45,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 }  // namespace jdb
 
-#define JDB_LAUNCH(kernel, grid, block, stream, ...) JDB_LAUNCH_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
-
-#define JDB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)            \
+#define JDB_LAUNCH(kernel, grid, block, stream, ...)                       \
   do {                                                                     \
     const bool jdb_t_ = jdb::g_timing.load(std::memory_order_relaxed) != 0; \
     if (jdb_t_) jdb::timing_begin(#kernel, (stream));                      \
-    jdb::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); \
+    jdb::launch_pdl(kernel, dim3(grid), dim3(block), (stream), __VA_ARGS__); \
     if (jdb_t_) jdb::timing_end((stream));                                 \
     jdb::g_launches.fetch_add(1, std::memory_order_relaxed);               \
     if (cudaPeekAtLastError() != cudaSuccess) return JDB200_ECUDA;         \

@@ -306,33 +306,19 @@ __device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx,
 // buffers and fixed flags are gathered only when that kernel saw a non-zero entry (they are
 // zero otherwise, and stay zero).
 template <typename F, int D>
-struct StepUniform {  // per-system values of the fused epilogue, loaded once per thread ahead of their use
-  F dt, grav[3];
-};
-template <typename F, int D>
-__device__ __forceinline__ StepUniform<F, D> load_step_uniform(const Ctx<F>& c, int b) {
-  StepUniform<F, D> u;
-  u.dt = c.dt[b];
-  u.grav[0] = u.grav[1] = u.grav[2] = F(0);
-#pragma unroll
-  for (int d = 0; d < D; ++d) u.grav[d] = c.gravity[b * D + d];
-  return u;
-}
-
-template <typename F, int D>
 __device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
                                                       const GridInfo<typename RT<F>::I>& g, const Vec4<F>& vm,
-                                                      int idx, const F* f, const F* t, bool with_torque,
-                                                      const StepUniform<F, D>& su) {
+                                                      int idx, const F* f, const F* t, bool with_torque) {
   using T = RT<F>;
   constexpr int A = D == 3 ? 3 : 1;
   const size_t off = (size_t)b * c.n, gi = off + idx;
   const F v[3] = {vm.x, vm.y, vm.z}, mass = vm.w;
-  const F dt = su.dt;
-  F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0}, et[3] = {0, 0, 0};
-  const F grav[3] = {su.grav[0], su.grav[1], su.grav[2]};
+  const F dt = c.dt[b];
+  F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0}, et[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
   F free = F(1);
   if (g.any_fixed) free = c.fixed[gi] ? F(0) : F(1);
+#pragma unroll
+  for (int d = 0; d < D; ++d) grav[d] = c.gravity[b * D + d];
   if (g.any_ppr) {
 #pragma unroll
     for (int d = 0; d < D; ++d) r[d] = c.pos_p_rot[gi * D + d];
@@ -401,7 +387,7 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.svel[off + k], vis.idx, vis.f, vis.t, with_torque != 0, load_step_uniform<F, D>(c, b));
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.svel[off + k], vis.idx, vis.f, vis.t, with_torque != 0);
   else store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
 }
 
@@ -694,45 +680,29 @@ __device__ __forceinline__ void pair_flat_body(const Ctx<F>& c, int b, int k,
       }
     }
   }
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, vm, idx, f, t, with_torque != 0, load_step_uniform<F, D>(c, b));
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, vm, idx, f, t, with_torque != 0);
   else store_force_torque<F, D>(c, off + idx, f, t, g.any_ppr != 0, with_torque != 0);
 }
 
 template <typename F, int LAW, int D, bool PERIODIC, int EPI>
-__global__ void __launch_bounds__(FlatCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_flat(Ctx<F> c, int with_torque,
-                                                                                            int use_wl) {
+__global__ void __launch_bounds__(FlatCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_flat(Ctx<F> c, int with_torque) {
   pdl_prologue();
   using I = typename RT<F>::I;
   __shared__ __align__(16) unsigned char smem[FlatCfg<D>::kBytes];
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
   const bool mine = flat_walk_ok(g);
-  if (!use_wl && blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
     if (mine) c.overflow[b] = (uint8_t)g.hash_overflow;
     else if (c.grid_mode == JDB200_GRID_DENSE) c.overflow[b] = 1;  // nobody else serves this system
   }
   if (!mine) return;
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-  const bool simple = !c.clumps && !g.any_bond;
-  if (use_wl) {  // the CTAs the tile kernel (k_pair_tile) handed over
-    const int cnt = c.wl_count[b];
-    const int* wl = c.wl + (size_t)b * c.pair_blocks;
-    constexpr int kSub = kPairBlock / FlatCfg<D>::kThreads;  // flat CTAs per tile
-    for (int w = blockIdx.x; w < cnt * kSub; w += gridDim.x) {
-      const long long k = (long long)wl[w / kSub] * kPairBlock + (w % kSub) * FlatCfg<D>::kThreads + threadIdx.x;
-      if (k >= c.n) continue;
-      if (simple) pair_flat_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, with_torque, sbase);
-      else pair_flat_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, with_torque, sbase);
-    }
-    return;
-  }
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= c.n) return;
-  if (simple) pair_flat_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, with_torque, sbase);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+  if (!c.clumps && !g.any_bond) pair_flat_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, with_torque, sbase);
   else pair_flat_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, with_torque, sbase);
 }
-
-#include "pair_tile.cuh"
 
 // FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
 // (sorted fallback, custom stencils, periodic de-dup).  Both kernels are launched; each
@@ -1027,18 +997,13 @@ int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
   const dim3 grid(cdiv(c.n, 128), c.batch);
   const int wt = with_torque ? 1 : 0;
   if (c.max_cells > 0) {  // a dense table exists
-    if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the tile kernel owns the systems it can serve
+    if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the flat kernel owns the systems it can serve
       constexpr int kT = FlatCfg<D>::kThreads;
-      constexpr int kTT = TileCfg<F, D>::kThreads;
-      const dim3 gt(c.pair_blocks, c.batch);
-      // CTAs the tile kernel declines (grid edges, sparse or overfull tiles) go through the flat kernel
-      const dim3 gf(std::min(c.pair_blocks * (kPairBlock / kT), std::max(1, 1184 / c.batch)), c.batch);
+      const dim3 gf(cdiv(c.n, kT), c.batch);
       if (c.periodic) {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH_TILE((k_pair_tile<F, L, D, true, EPI>), gt, kTT, (TileCfg<F, D>::kBytes), s, c, wt));
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, true, EPI>), gf, kT, s, c, wt, 1));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, true, EPI>), gf, kT, s, c, wt));
       } else {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH_TILE((k_pair_tile<F, L, D, false, EPI>), gt, kTT, (TileCfg<F, D>::kBytes), s, c, wt));
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, false, EPI>), gf, kT, s, c, wt, 1));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, false, EPI>), gf, kT, s, c, wt));
       }
     } else if (c.periodic) {         // wider canonical stencils: x-run kernel
       JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true, EPI>), grid, 128, s, c, wt));
