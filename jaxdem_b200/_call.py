@@ -51,10 +51,10 @@ def workspace(p: L.Params, device) -> torch.Tensor:
     nbytes = L.lib().jdb200_workspace_bytes(C.byref(p))
     if nbytes == 0:
         raise RuntimeError("jdb200_workspace_bytes rejected the parameters (JDB200_EINVAL)")
-    key = (str(device), nbytes)
+    key = str(device)
     ws = _WORKSPACES.get(key)
-    if ws is None:
-        _WORKSPACES.clear()  # one live workspace per process is enough; sizes rarely change
+    if ws is None or ws.numel() < nbytes:  # one live workspace per device, grown on demand and reused
+        _WORKSPACES.pop(key, None)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _WORKSPACES[key] = ws
     return ws

@@ -412,3 +412,30 @@ def test_full_size_parity_vs_c_oracle_1m():
         for f in ("pos_c", "vel", "force"):
             assert_close(getattr(gst, f), getattr(ost, f), np.float32, f)
     assert not bool(gsy.collider.overflow)
+
+
+def _run_slab_worker(world, *args):
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = os.path.join(root, "tests", "slab_worker.py")
+    if world == 1:
+        cmd = [sys.executable, worker, *map(str, args)]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", worker, *map(str, args)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SLAB-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
+def test_slab_system_single_rank(law):
+    """The slab driver with world_size 1 (CUDA engine, hook by hook) against System.step."""
+    _run_slab_worker(1, 60000, 8, law)
+
+
+@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
+def test_slab_system_two_gpus(law):
+    """Two slabs over NCCL against the single-GPU trajectory (skipped on 1-GPU boxes)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_slab_worker(2, 200000, 10, law)

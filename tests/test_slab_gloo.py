@@ -1,0 +1,181 @@
+"""Slab decomposition (jaxdem_b200/slab.py) on CPU: world_size-2 and -3 ``gloo`` groups.
+
+The host logic under test — cell-layer ownership, migration, halo exchange, in-place
+re-packing — is device-agnostic torch code.  The per-rank compute hooks are played by the
+numpy oracle here (an *engine* plugged in by this test; the product engine is CUDA-only), so
+the decomposed trajectory can be compared with the oracle's single-system trajectory:
+identical particle sets per slab, forces / velocities / positions to rounding."""
+
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from oracle import colliders as ocol, force_manager as ofm, integrators as oint
+from helpers import MATS, make_inputs
+
+
+class OracleEngine:
+    """The reference's hooks (oracle restatement) on the rank-local rows of a SlabSystem."""
+
+    def __init__(self, slab, *, box, law, lin, rot, dt, dtype, nmat=1, cell_size=None):
+        self.slab, self.box, self.law, self.lin, self.rot, self.dt, self.dtype = slab, box, law, lin, rot, dt, dtype
+        self.nmat, self.cell_size = nmat, cell_size
+
+    def _oracle(self, st):
+        np_ = lambda t: t.numpy().copy()
+        ost = oracle.create_state(np_(st.pos_c), vel=np_(st.vel), force=np_(st.force), ang_vel=np_(st.ang_vel),
+                                  torque=np_(st.torque), rad=np_(st.rad), mass=np_(st.mass),
+                                  inertia=np_(st.inertia), mat_id=np_(st.mat_id), fixed=np_(st.fixed),
+                                  q=np.concatenate([np_(st.q.w), np_(st.q.xyz)], axis=1), dtype=self.dtype)
+        osy = oracle.create_system(ost, dt=self.dt, linear_integrator_type=self.lin, rotation_integrator_type=self.rot,
+                                   collider_type="celllist", collider_kw=dict(cell_size=self.cell_size),
+                                   domain_type="periodic", domain_kw=dict(box_size=self.box),
+                                   force_model_type=self.law,
+                                   mat_table=oracle.make_material_table(MATS[:self.nmat], "harmonic"))
+        return ost, osy
+
+    @staticmethod
+    def _back(ost, st, fields):
+        for f in fields:
+            if f == "q":
+                st.q.w.copy_(torch.as_tensor(ost.q_w))
+                st.q.xyz.copy_(torch.as_tensor(ost.q_xyz))
+            else:
+                getattr(st, f).copy_(torch.as_tensor(getattr(ost, f)))
+
+    def before_force(self, st):
+        if st.N == 0:
+            return
+        ost, osy = self._oracle(st)
+        oint.LINEAR[self.lin][0](ost, osy)
+        oint.ROTATION[self.rot][0](ost, osy)
+        self._back(ost, st, ("pos_c", "vel", "ang_vel", "q"))
+
+    def compute_force(self, st):
+        if st.N == 0:
+            return
+        ost, osy = self._oracle(st)
+        ocol.celllist_compute_force(ost, osy)
+        self._back(ost, st, ("force", "torque"))
+
+    def after_force(self, st):
+        if st.N == 0:
+            return
+        ost, osy = self._oracle(st)
+        ofm.apply(ost, osy)
+        oint.LINEAR[self.lin][1](ost, osy)
+        oint.ROTATION[self.rot][1](ost, osy)
+        self._back(ost, st, ("force", "torque", "vel", "ang_vel"))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, cfg, out):
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(1)
+        from jaxdem_b200.slab import SlabSystem
+        dtype = cfg["dtype"]
+        F = torch.float32 if dtype == np.float32 else torch.float64
+        inp = cfg["inp"]
+        dim = inp["pos"].shape[1]
+        slab = SlabSystem(dim=dim, dtype=F, device="cpu", capacity=cfg["capacity"], box=inp["box"],
+                          anchor=np.zeros(dim), n_layers=cfg["n_layers"], search_range=1,
+                          ghost_capacity=cfg["capacity"], migrant_capacity=cfg["capacity"])
+        slab.load_global(dict(pos=inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"],
+                              mass=inp["mass"], mat_id=inp.get("mat_id", np.zeros(len(inp["rad"]), np.int64))))
+        slab.engine = OracleEngine(slab, box=inp["box"], law=cfg["law"], lin="verlet", rot=cfg["rot"], dt=cfg["dt"],
+                                   dtype=dtype, nmat=cfg["nmat"], cell_size=cfg["cell_size"])
+        owned0 = slab.n_own
+        slab.compute_force()  # loop-carried state.force of the first step
+        slab.step(cfg["steps"])
+        res = slab.gather(("pos_c", "vel", "force", "torque", "ang_vel"))
+        # every owned particle lies in this rank's layers; ghosts only within the halo
+        from jaxdem_b200.slab import cell_layer
+        lay = slab.layout
+        layer = cell_layer(slab.buf["pos_c"][:slab.n_own, -1], 0.0, float(inp["box"][-1]), lay.n_layers).numpy()
+        ok_own = bool((lay.owner[layer] == rank).all())
+        if rank == 0:
+            out.put(("ok", res, owned0, ok_own))
+        else:
+            out.put(("aux", None, owned0, ok_own))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # surface the traceback in the parent
+        out.put(("err", traceback.format_exc(), 0, False))
+
+
+def _run(world, cfg):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for g in got:
+        assert g[0] != "err", g[1]
+    res = [g for g in got if g[0] == "ok"][0][1]
+    assert sum(g[2] for g in got) == cfg["inp"]["pos"].shape[0]
+    assert all(g[3] for g in got)
+    return res
+
+
+def _reference(cfg):
+    inp, dtype = cfg["inp"], cfg["dtype"]
+    ost = oracle.create_state(inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"], mass=inp["mass"],
+                              mat_id=inp.get("mat_id"), dtype=dtype)
+    osy = oracle.create_system(ost, dt=cfg["dt"], linear_integrator_type="verlet", rotation_integrator_type=cfg["rot"],
+                               collider_type="celllist", collider_kw=dict(cell_size=cfg["cell_size"]),
+                               domain_type="periodic", domain_kw=dict(box_size=inp["box"]),
+                               force_model_type=cfg["law"],
+                               mat_table=oracle.make_material_table(MATS[:cfg["nmat"]], "harmonic"))
+    ocol.celllist_compute_force(ost, osy)
+    oracle.step(ost, osy, cfg["steps"])
+    return ost
+
+
+@pytest.mark.parametrize("world,dim,law,rot,dtype", [
+    (2, 3, "spring", "", np.float64),
+    (2, 3, "cundallstrack", "verletspiral", np.float64),
+    (3, 2, "hertz", "verletspiral", np.float32),
+])
+def test_slab_decomposition_matches_single_system(world, dim, law, rot, dtype):
+    n = 600 if dim == 3 else 400
+    nmat = 2 if law != "spring" else 1
+    inp = make_inputs(n, dim, seed=21, dtype=dtype, phi=0.5 if dim == 3 else 0.6, nmat=nmat)
+    inp["vel"] = inp["vel"] * 40.0  # fast enough for particles to change slab within the run
+    inp["pos"][::7, -1] -= inp["box"][-1]  # un-wrapped coordinates: ownership goes by the wrapped cell
+    cs = dtype(2.0 * inp["rad"].max())
+    n_layers = int(np.floor(dtype(inp["box"][-1]) / cs))
+    cfg = dict(inp=inp, dtype=dtype, law=law, rot=rot, dt=2e-3, steps=12, nmat=nmat, cell_size=cs,
+               n_layers=n_layers, capacity=n + 64)
+    got = _run(world, cfg)
+    ref = _reference(cfg)
+    assert np.array_equal(got["gid"], np.arange(n))
+    eps = np.finfo(dtype).eps
+    for f in ("pos_c", "vel", "force", "torque", "ang_vel"):
+        a, b = got[f], getattr(ref, f)
+        scale = max(1.0, float(np.abs(b).max()))
+        # same arithmetic per pair; only the order of a particle's contact sum may differ
+        assert np.abs(a - b).max() <= 4096 * eps * scale, (f, np.abs(a - b).max(), scale)
+    # particles did migrate
+    z0 = inp["pos"][:, -1]
+    moved = np.abs(ref.pos_c[:, -1] - z0).max()
+    assert moved > 0.5 * inp["box"][-1] / n_layers
