@@ -38,24 +38,28 @@ B_ALG_KERNEL = {
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def make_workload(n=N_PARTICLES, seed=1, phi=0.5, dtype=np.float32, packing="grid"):
-    """jittered simple-cubic ("grid") or uniform random ("random") packing."""
+def make_workload(n=N_PARTICLES, seed=1, phi=0.5, dtype=np.float32, packing="grid", stack=1):
+    """jittered simple-cubic ("grid") or uniform random ("random") packing.
+    ``stack`` > 1 (multi-GPU weak scaling): ``stack`` copies of the C2 cube on top of each other
+    along z — ONE periodic system of stack * n spheres in a box (L, L, stack * L)."""
     rng = np.random.default_rng(seed)
     r = 0.5
     L = (n * (4.0 / 3.0) * np.pi * r**3 / phi) ** (1.0 / 3.0)
+    nt = n * stack
     if packing == "grid":
         g = int(np.ceil(n ** (1.0 / 3.0)))
-        sites = rng.permutation(g**3)[:n]
+        sites = rng.permutation(g**3 * stack)[:nt]
         sites.sort()
-        ijk = np.stack(np.unravel_index(sites, (g, g, g)), axis=1).astype(np.float64)
-        pos = (ijk + 0.5) * (L / g) + rng.uniform(-0.1, 0.1, (n, 3)) * r
-        order = rng.permutation(n)  # particle index carries no spatial order
+        ijk = np.stack(np.unravel_index(sites, (g * stack, g, g)), axis=1)[:, ::-1].astype(np.float64)  # (x, y, z)
+        pos = (ijk + 0.5) * (L / g) + rng.uniform(-0.1, 0.1, (nt, 3)) * r
+        order = rng.permutation(nt)  # particle index carries no spatial order
         pos = pos[order]
     else:
-        pos = rng.uniform(0, L, (n, 3))
-    vel = rng.uniform(-1, 1, (n, 3))
-    return dict(pos=pos.astype(dtype), vel=vel.astype(dtype), rad=np.full(n, r, dtype),
-                mass=np.ones(n, dtype), box=np.full(3, L, dtype))
+        pos = rng.uniform(0, 1, (nt, 3)) * np.array([L, L, L * stack])
+    vel = rng.uniform(-1, 1, (nt, 3))
+    box = np.array([L, L, L * stack])
+    return dict(pos=pos.astype(dtype), vel=vel.astype(dtype), rad=np.full(nt, r, dtype),
+                mass=np.ones(nt, dtype), box=box.astype(dtype))
 
 
 # ---------------------------------------------------------------------------
@@ -207,10 +211,17 @@ def run_reference(args):
 
 
 def workload_config(args, n):
+    if args.gpus > 1 and args.mode == "slab":
+        par = (f"ONE periodic system of {args.gpus} x {n} spheres (box L x L x {args.gpus}L), z-slab decomposition, "
+               "one slab per GPU, NCCL halo + migration exchange every step")
+    elif args.gpus > 1:
+        par = "1 system per GPU (replicas)"
+    else:
+        par = "single GPU"
     return {"workload": f"C2: {n} monodisperse 3D spheres r=0.5, periodic cube phi=0.5, {args.packing} packing, "
                         "cell-list collider (27-cell stencil), spring contact young_eff=1e4, velocity Verlet, dt=1e-3",
             "n_particles": n, "l2": "flushed between timed steps (256 MiB write, then 256 MiB read to drain the dirty lines)",
-            "parallelism": "1 system per GPU (replicas)" if args.gpus > 1 else "single GPU"}
+            "parallelism": par}
 
 
 # ---------------------------------------------------------------------------
@@ -233,6 +244,8 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if world > 1 and args.mode == "slab":
+        return run_cuda_slab(args, world, rank, local, dev)
     wl = make_workload(seed=1 + rank, packing=args.packing)
     n = wl["pos"].shape[0]
     st = jd.State.create(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=torch.float32, device=dev)
@@ -386,6 +399,117 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+def run_cuda_slab(args, world, rank, local, dev):
+    """N > 1 GPUs: ONE periodic system of N x 2**20 spheres, z-slab decomposition (jaxdem_b200/slab.py).
+    Per-GPU work is fixed (weak scaling); every step exchanges halos and migrants over NCCL."""
+    import torch
+    import torch.distributed as dist
+
+    from jaxdem_b200 import _lib
+    from jaxdem_b200.slab import create_slab_system
+
+    lib = _lib.lib()
+    wl = make_workload(seed=1, packing=args.packing, stack=world)
+    n_total = wl["pos"].shape[0]
+    n = n_total // world
+    slab = create_slab_system(dict(pos=wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"]),
+                              box_size=wl["box"], dt=1e-3, force_model_type="spring",
+                              rotation_integrator_type="", dtype=torch.float32, device=dev, capacity_factor=1.35)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush.fill_(1)
+        flush_rd.sum()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    slab.compute_force()  # first force evaluation (loop-carried state.force)
+    for _ in range(args.warmup):
+        slab.step(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = lib.jdb200_launch_count()
+    barrier()
+    for a, b in ev:
+        flush_l2()
+        a.record()
+        slab.step(1)
+        b.record()
+    barrier()
+    launches = lib.jdb200_launch_count() - l0
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_total * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: every rank's owned rows host -> device before the step, device -> host after it ----
+    fields = ("pos_c", "vel", "force")
+    host = {k: torch.empty((slab.cap, 3), dtype=torch.float32).pin_memory() for k in fields}
+    e2e_steps = max(3, min(args.steps, 20))
+    h2d = d2h = 0
+
+    def e2e_step(first=False):
+        nonlocal h2d, d2h
+        m = slab.n_own
+        if not first:
+            for k in fields:
+                slab.buf[k][:m].copy_(host[k][:m], non_blocking=True)
+        slab.step(1)
+        m2 = slab.n_own
+        for k in fields:
+            host[k][:m2].copy_(slab.buf[k][:m2], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d += 0 if first else 3 * m * 12
+        d2h += 3 * m2 * 12
+
+    e2e_step(first=True)
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    tm = t.clone()
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e_value = n_total * e2e_steps / float(tm[0].item())
+    peak, peak_src = measured_peak()
+    step_gbs = B_ALG_STEP * n_total * args.steps / (ms_max * 1e-3) / 1e9
+    own = torch.tensor([slab.n_own, slab.n_ghost], dtype=torch.int64, device=dev)
+    owns = [torch.zeros_like(own) for _ in range(world)]
+    dist.all_gather(owns, own)
+    if rank == 0:
+        line = {
+            "metric": "particle-steps/sec at 1M 3D spheres", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, n), launch="stream launches, hook by hook",
+                           n_particles_total=n_total,
+                           owned_ghost_rows_per_rank=[[int(x) for x in o.tolist()] for o in owns]),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s",
+                    "h2d_bytes_per_step": int(t[1].item() / e2e_steps), "d2h_bytes_per_step": int(t[2].item() / e2e_steps),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": None,
+            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s",
+                              "frac": step_gbs / (peak * world), "algorithmic_bytes_per_particle_step": B_ALG_STEP,
+                              "peak_source": peak_src + f" x {world} GPUs"},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def step_launches(jd, st, sy, lib):
     """Kernels one step launches (counted on a throw-away stream-launched step)."""
     import torch
@@ -402,6 +526,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--packing", default="grid", choices=["grid", "random"])
+    ap.add_argument("--mode", default="slab", choices=["slab", "replicas"],
+                    help="N > 1 GPUs: one slab-decomposed system of N x 2^20 spheres (default) or N independent replicas")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (System.compile_step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=10)

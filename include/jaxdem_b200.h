@@ -212,6 +212,57 @@ JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const j
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
                        const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps);
 
+/* ---- slab decomposition: the per-step neighbour exchange ----------------------------- */
+/* No reference equivalent (the reference runs one system on one device,
+ * jaxdem/system.py:60-98); SURVEY.md 8(e).  One periodic sphere system is cut into slabs of
+ * cell layers along the LAST axis, one slab per rank (jaxdem_b200/slab.py).  After the drift
+ * (step_before_force) `jdb200_slab_pack` classifies the n owned rows of `src` by the cell
+ * layer of their last coordinate — the arithmetic of the collider's hash,
+ * colliders/cell_list.py:55-60, on the device copies of anchor / box_size / cell_size —
+ * compacts the rows that stay into `dst` (index order kept), writes the rows that left as
+ * full records into the message of their direction (and as ghost records into `kept`: they
+ * stay behind as ghosts) and the rows within `search_range` layers of a face as ghost
+ * records.  The caller exchanges the two messages with its neighbours (NCCL), reads the
+ * counts from the 64-byte headers (int64: [0] full records, [1] ghost records, [2] rows that
+ * moved further than the halo; `header_local`: [0] rows that stay, [1] left downwards,
+ * [2] left upwards, [3] strays) and calls `jdb200_slab_unpack`, which appends to `dst`, behind
+ * the n_stay compacted rows: arrivals from the lower, then the upper neighbour (owned rows),
+ * then the ghost rows (kept lower, kept upper, halo of the lower, halo of the upper neighbour).
+ * counts = {n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up}.  Same rules as every entry point:
+ * stream-ordered, no host synchronisation, no allocation; all lists keep index order. */
+typedef struct jdb200_slab_desc {
+  int64_t n;            /* owned rows in src */
+  int64_t cap_mig;      /* full-record capacity of one message */
+  int64_t cap_ghost;    /* ghost-record capacity of one message */
+  int32_t dim, dtype;   /* as jdb200_params */
+  int32_t n_layers;     /* cell layers along the last axis (static slab layout) */
+  int32_t lo_layer, up_layer; /* this rank owns layers [lo_layer, up_layer) */
+  int32_t search_range; /* halo width in layers (R of the collider's stencil) */
+  const void* anchor;   /* (D,) F  Domain.anchor       (device) */
+  const void* box_size; /* (D,) F  Domain.box_size     (device) */
+  const void* cell_size;/* ()   F  DynamicCellList.cell_size (device) */
+} jdb200_slab_desc;
+
+/* Per-particle rows of a slab (State leaves of a sphere system + the global particle id). */
+typedef struct jdb200_slab_rows {
+  void *pos_c, *vel, *force;        /* (cap,D) F */
+  void *ang_vel, *torque, *inertia; /* (cap,A) F */
+  void *q_w, *q_xyz;                /* (cap,1), (cap,3) F */
+  void *rad, *mass;                 /* (cap,) F */
+  void* mat_id;                     /* (cap,) I */
+  void* fixed;                      /* (cap,) uint8 */
+  void* gid;                        /* (cap,) int64 global particle id */
+} jdb200_slab_rows;
+
+JDB200_API size_t jdb200_slab_message_bytes(const jdb200_slab_desc* d);
+JDB200_API size_t jdb200_slab_kept_bytes(const jdb200_slab_desc* d);
+JDB200_API size_t jdb200_slab_scratch_bytes(const jdb200_slab_desc* d);
+JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* src,
+                                const jdb200_slab_rows* dst, void* msg_lo, void* msg_up, void* kept,
+                                void* header_local, void* scratch, size_t scratch_bytes);
+JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* dst,
+                                  const int64_t* counts, const void* from_lo, const void* from_up, const void* kept);
+
 /* Number of kernels the library has launched since load (diagnostic counter for
  * bench.py's `gpu_launches`; relaxed atomic, not part of the data path). */
 JDB200_API int64_t jdb200_launch_count(void);

@@ -50,7 +50,23 @@ class SystemView(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in SYSTEM_FIELDS]
 
 
+class SlabDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("cap_mig", C.c_int64), ("cap_ghost", C.c_int64), ("dim", C.c_int32),
+                ("dtype", C.c_int32), ("n_layers", C.c_int32), ("lo_layer", C.c_int32), ("up_layer", C.c_int32),
+                ("search_range", C.c_int32), ("anchor", C.c_void_p), ("box_size", C.c_void_p),
+                ("cell_size", C.c_void_p)]
+
+
+SLAB_ROW_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "inertia", "q_w", "q_xyz", "rad", "mass",
+                   "mat_id", "fixed", "gid")
+
+
+class SlabRows(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in SLAB_ROW_FIELDS]
+
+
 _PP, _PS, _PY = C.POINTER(Params), C.POINTER(StateView), C.POINTER(SystemView)
+_PD, _PR = C.POINTER(SlabDesc), C.POINTER(SlabRows)
 _V, _SZ = C.c_void_p, C.c_size_t
 
 # symbol -> (restype, argtypes); every symbol include/jaxdem_b200.h declares
@@ -71,6 +87,11 @@ SYMBOLS = {
     "jdb200_rotation_step_after_force": (C.c_int, [_V, _PP, _PS, _PY]),
     "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
+    "jdb200_slab_message_bytes": (_SZ, [_PD]),
+    "jdb200_slab_kept_bytes": (_SZ, [_PD]),
+    "jdb200_slab_scratch_bytes": (_SZ, [_PD]),
+    "jdb200_slab_pack": (C.c_int, [_V, _PD, _PR, _PR, _V, _V, _V, _V, _V, _SZ]),
+    "jdb200_slab_unpack": (C.c_int, [_V, _PD, _PR, C.POINTER(C.c_int64), _V, _V, _V]),
     "jdb200_timing_enable": (C.c_int, [C.c_int]),
     "jdb200_timing_collect": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

@@ -19,13 +19,17 @@ those hooks — the same CUDA entry points as the single-GPU path — on the par
 * ``collider.compute_force`` runs on owned + ghost rows (forces on owned rows are complete,
   ghost rows are discarded), the remaining hooks on owned rows.
 
+Classification, compaction and (un)packing are CUDA kernels (csrc/slab.cu, C ABI
+``jdb200_slab_pack`` / ``jdb200_slab_unpack``): three launches before the exchange, one after.
 Transport: ``torch.distributed`` point-to-point (NCCL over NVLink on GPUs; gloo in the CPU
-tests).  Messages have fixed capacities and carry their counts, so a step needs ONE host
-synchronisation (the new row counts, which are launch parameters).  Exceeding a capacity
-raises, in the spirit of ``Collider.overflow``.
+tests), one message per direction.  Messages have fixed capacities and carry their counts, so
+a step needs ONE host synchronisation (the new row counts, which are launch parameters).
+Exceeding a capacity raises, in the spirit of ``Collider.overflow``.
 
-The compute hooks are injected as an *engine* (``CudaEngine`` below is the product; the CPU
-tests plug the oracle in its place to exercise this file's host logic with gloo).
+The compute hooks and the exchange kernels are injected as an *engine* (``CudaEngine`` below
+is the product and has no CPU path; the CPU tests plug numpy stand-ins — the oracle for the
+hooks, a restatement of the pack / unpack kernels on the same message layout — to exercise
+this file's protocol with gloo).
 """
 
 from __future__ import annotations
@@ -69,11 +73,50 @@ def cell_layer(z: torch.Tensor, anchor: float, box: float, n_layers: int) -> tor
     return c.clamp_(0, n_layers - 1)
 
 
+ROW_FLOAT_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "inertia", "q_w", "q_xyz", "rad", "mass")
+GHOST_FLOAT_FIELDS = ("pos_c", "vel", "ang_vel", "rad", "mass")
+
+
+def message_layout(dim: int, fbytes: int, cap_m: int, cap_g: int) -> dict:
+    """Byte layout of one exchange message (csrc/slab.cu: SlabMsg): int64 header[8] — [0] full
+    records, [1] ghost records, [2] strays —, full records (floats in ROW_FLOAT_FIELDS order, then
+    int64 gid / mat_id / fixed), ghost records (floats in GHOST_FLOAT_FIELDS order, then int64
+    gid / mat_id); sections 16-byte aligned."""
+    A = _A(dim)
+    WF, WG = 3 * dim + 3 * A + 1 + 3 + 2, 2 * dim + A + 2
+    al = lambda x: (x + 15) & ~15
+    o = 64
+    L = dict(WF=WF, WG=WG, cap_m=cap_m, cap_g=cap_g, mig_f=o)
+    o = al(o + cap_m * WF * fbytes)
+    L["mig_i"] = o
+    o = al(o + cap_m * 3 * 8)
+    L["gh_f"] = o
+    o = al(o + cap_g * WG * fbytes)
+    L["gh_i"] = o
+    o = al(o + cap_g * 2 * 8)
+    L["bytes"] = o
+    return L
+
+
+def message_views(buf: torch.Tensor, L: dict, F: torch.dtype) -> dict:
+    fb = torch.empty((), dtype=F).element_size()
+    cm, cg, WF, WG = L["cap_m"], L["cap_g"], L["WF"], L["WG"]
+    return dict(
+        header=buf[0:64].view(torch.int64),
+        mig_f=buf[L["mig_f"]:L["mig_f"] + cm * WF * fb].view(F).view(cm, WF),
+        mig_i=buf[L["mig_i"]:L["mig_i"] + cm * 24].view(torch.int64).view(cm, 3),
+        gh_f=buf[L["gh_f"]:L["gh_f"] + cg * WG * fb].view(F).view(cg, WG),
+        gh_i=buf[L["gh_i"]:L["gh_i"] + cg * 16].view(torch.int64).view(cg, 2),
+    )
+
+
 class CudaEngine:
-    """The product engine: the reference's hooks through libjaxdem_b200.so (no CPU path)."""
+    """The product engine: the reference's hooks and the exchange kernels through
+    libjaxdem_b200.so (no CPU path)."""
 
     def __init__(self, system):
         self.system = system
+        self._scratch = None
 
     def before_force(self, state):
         sy = self.system
@@ -91,13 +134,61 @@ class CudaEngine:
         sy.linear_integrator.step_after_force(state, sy)
         sy.rotation_integrator.step_after_force(state, sy)
 
+    # -- exchange kernels (csrc/slab.cu) -----------------------------------------
+    def _desc(self, slab, n):
+        import ctypes as C
+        from . import _lib as L
+        sy = self.system
+        d = L.SlabDesc()
+        d.n, d.cap_mig, d.cap_ghost = int(n), slab.migrant_cap, slab.ghost_cap
+        d.dim = slab.dim
+        d.dtype = L.JDB200_F32 if slab.dtype == torch.float32 else L.JDB200_F64
+        d.n_layers = slab.layout.n_layers
+        d.lo_layer, d.up_layer = slab.layout.bounds[slab.rank], slab.layout.bounds[slab.rank + 1]
+        d.search_range = slab.layout.R
+        d.anchor, d.box_size = sy.domain.anchor.data_ptr(), sy.domain.box_size.data_ptr()
+        d.cell_size = sy.collider.cell_size.data_ptr()
+        return d
+
+    @staticmethod
+    def _rows(bufs):
+        from . import _lib as L
+        r = L.SlabRows()
+        for k in L.SLAB_ROW_FIELDS:
+            setattr(r, k, bufs[k].data_ptr())
+        return r
+
+    def pack(self, slab):
+        import ctypes as C
+        from . import _call, _lib as L
+        lib = L.lib()
+        d = self._desc(slab, slab.n_own)
+        need = lib.jdb200_slab_scratch_bytes(C.byref(d))
+        if self._scratch is None or self._scratch.numel() < need:
+            dcap = self._desc(slab, slab.cap)
+            self._scratch = torch.empty(lib.jdb200_slab_scratch_bytes(C.byref(dcap)), dtype=torch.uint8,
+                                        device=slab.device)
+        src, dst = self._rows(slab.buf), self._rows(slab.alt)
+        L.check(lib.jdb200_slab_pack(_call.stream_ptr(slab.device), C.byref(d), C.byref(src), C.byref(dst),
+                                     slab.send_lo.data_ptr(), slab.send_up.data_ptr(), slab.kept.data_ptr(),
+                                     slab.header_local.data_ptr(), self._scratch.data_ptr(),
+                                     self._scratch.numel()), "jdb200_slab_pack")
+
+    def unpack(self, slab, counts):
+        import ctypes as C
+        from . import _call, _lib as L
+        d = self._desc(slab, slab.n_own)
+        dst = self._rows(slab.alt)
+        arr = (C.c_int64 * 7)(*[int(c) for c in counts])
+        L.check(L.lib().jdb200_slab_unpack(_call.stream_ptr(slab.device), C.byref(d), C.byref(dst), arr,
+                                           slab.recv_lo.data_ptr(), slab.recv_up.data_ptr(), slab.kept.data_ptr()),
+                "jdb200_slab_unpack")
+
 
 class SlabSystem:
-    """Owned + ghost particles of one rank, in capacity-sized buffers; ``view(n)`` exposes the
-    first n rows as a ``State`` whose tensors alias the buffers (the C ABI works in place)."""
-
-    FLOAT_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "q_w", "q_xyz", "rad", "mass", "inertia")
-    GHOST_FLOAT_FIELDS = ("pos_c", "vel", "ang_vel", "rad", "mass")
+    """Owned + ghost particles of one rank, in capacity-sized row buffers (two sets: the
+    exchange compacts out of place); ``view(n)`` exposes the first n rows of the current set as
+    a ``State`` whose tensors alias the buffers (the C ABI works in place)."""
 
     def __init__(self, *, dim, dtype, device, capacity, box, anchor, n_layers, search_range, group=None,
                  ghost_capacity=None, migrant_capacity=None):
@@ -108,21 +199,22 @@ class SlabSystem:
         self.layout = SlabLayout(int(n_layers), self.world, int(search_range))
         self.box_last, self.anchor_last = float(box[-1]), float(anchor[-1])
         self.cap = int(capacity)
-        self.ghost_cap = int(ghost_capacity or max(1024, self.cap // 4))
-        self.migrant_cap = int(migrant_capacity or max(256, self.cap // 16))
         A, F, dev = _A(dim), dtype, self.device
         I = int_dtype_for(F)
-        shapes = dict(pos_c=(dim,), vel=(dim,), force=(dim,), ang_vel=(A,), torque=(A,), q_w=(1,), q_xyz=(3,),
-                      rad=(), mass=(), inertia=(A,))
+        shapes = dict(pos_c=(dim,), vel=(dim,), force=(dim,), ang_vel=(A,), torque=(A,), inertia=(A,), q_w=(1,),
+                      q_xyz=(3,), rad=(), mass=())
         self.widths = {k: int(np.prod(s)) if s else 1 for k, s in shapes.items()}
-        self.buf = {k: torch.zeros((self.cap, *s), dtype=F, device=dev) for k, s in shapes.items()}
-        self.buf["q_w"].fill_(1)
-        self.buf["rad"].fill_(1)
-        self.buf["mass"].fill_(1)
-        self.buf["inertia"].fill_(1)
-        self.buf["gid"] = torch.full((self.cap,), -1, dtype=torch.int64, device=dev)
-        self.buf["mat_id"] = torch.zeros(self.cap, dtype=I, device=dev)
-        self.buf["fixed"] = torch.zeros(self.cap, dtype=torch.bool, device=dev)
+
+        def make_set():
+            b = {k: torch.zeros((self.cap, *s), dtype=F, device=dev) for k, s in shapes.items()}
+            for k in ("q_w", "rad", "mass", "inertia"):
+                b[k].fill_(1)
+            b["gid"] = torch.full((self.cap,), -1, dtype=torch.int64, device=dev)
+            b["mat_id"] = torch.zeros(self.cap, dtype=I, device=dev)
+            b["fixed"] = torch.zeros(self.cap, dtype=torch.bool, device=dev)
+            return b
+
+        self.buf, self.alt = make_set(), make_set()
         # static rows of a sphere system: pos_p = 0, clump_id = arange, no bonds
         self.static = dict(
             pos_p=torch.zeros((self.cap, dim), dtype=F, device=dev),
@@ -135,18 +227,34 @@ class SlabSystem:
         self.n_ghost = 0
         self.engine: Any = None
         self.steps_done = 0
-        self._nbrs = self._neighbours()
+        lo, up = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self.lo_rank, self.up_rank = lo, up
+        self.header_local = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.set_capacities(int(ghost_capacity or max(1024, self.cap // 4)),
+                            int(migrant_capacity or max(256, self.cap // 16)))
+
+    def set_capacities(self, ghost_cap: int, migrant_cap: int) -> None:
+        """(Re)allocate the exchange messages: every rank must use the same capacities."""
+        self.ghost_cap, self.migrant_cap = int(ghost_cap), int(migrant_cap)
+        fb = torch.empty((), dtype=self.dtype).element_size()
+        self.msg_layout = message_layout(self.dim, fb, self.migrant_cap, self.ghost_cap)
+        self.kept_layout = message_layout(self.dim, fb, 0, 2 * self.migrant_cap)
+        mk = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.send_lo, self.send_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
+        self.recv_lo, self.recv_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
+        self.kept = mk(self.kept_layout["bytes"])
+
+    def tune_capacities(self, slack: float = 2.0) -> None:
+        """Shrink the messages to ``slack`` x the counts of one trial exchange (collective)."""
+        if self.world == 1:
+            return
+        self.exchange()
+        seen = torch.tensor(self.last_counts, dtype=torch.int64, device=self.device)
+        dist.all_reduce(seen, op=dist.ReduceOp.MAX, group=self.group)
+        mig, gh = int(seen[0]), int(seen[1])
+        self.set_capacities(max(1024, int(slack * gh)), max(1024, int(4 * slack * mig), int(slack * gh) // 16))
 
     # ------------------------------------------------------------------ set-up
-    def _neighbours(self):
-        """[(rank, faces)] with faces a subset of {"lo", "up"}; one entry per distinct neighbour."""
-        if self.world == 1:
-            return []
-        lo, up = (self.rank - 1) % self.world, (self.rank + 1) % self.world
-        if lo == up:
-            return [(lo, ("lo", "up"))]
-        return [(lo, ("lo",)), (up, ("up",))]
-
     def load_global(self, arrays: dict) -> None:
         """Take this rank's share of a global particle set (numpy arrays keyed like State.create:
         pos, vel, ang_vel, rad, mass, inertia, mat_id, fixed; every rank passes the same arrays)."""
@@ -188,130 +296,40 @@ class SlabSystem:
             clump_id=s["clump_id"][:n], bond_id=s["bond_id"][:n], mat_id=b["mat_id"][:n],
             species_id=s["species_id"][:n], fixed=b["fixed"][:n], _pos_p_rot=s["_pos_p_rot"][:n], has_clumps=False)
 
-    # ------------------------------------------------------------------ packing
-    def _pack(self, idx: torch.Tensor, fields) -> torch.Tensor:
-        return torch.cat([self.buf[k].index_select(0, idx).reshape(idx.numel(), self.widths[k]) for k in fields], dim=1)
-
-    def _unpack(self, block: torch.Tensor, fields, dst: slice) -> None:
-        c = 0
-        for k in fields:
-            w = self.widths[k]
-            self.buf[k][dst] = block[:, c:c + w].reshape(self.buf[k][dst].shape)
-            c += w
-
-    def _width(self, fields) -> int:
-        return sum(self.widths[k] for k in fields)
-
     # ------------------------------------------------------------------ the exchange
     def exchange(self) -> None:
-        """Migration + halo exchange after the drift: owned rows are re-packed in place
-        (holes left by leavers are filled by arrivals, then by rows from the tail), ghost rows
-        are rebuilt behind them."""
-        n, lay, R = self.n_own, self.layout, self.layout.R
-        dev = self.device
-        lo_l, up_l = lay.bounds[self.rank], lay.bounds[self.rank + 1]
-        g = lay.n_layers
-        layer = cell_layer(self.buf["pos_c"][:n, -1], self.anchor_last, self.box_last, g)
-        owner = torch.as_tensor(lay.owner, device=dev)[layer]
-        leave = owner != self.rank
-        FF, GF = self.FLOAT_FIELDS, self.GHOST_FLOAT_FIELDS
-        wF, wG = self._width(FF), self._width(GF)
-        sends, recvs, ops = [], [], []
-        kept_f, kept_i = [], []
-        # distance (in layers, periodic) below the lower face / above the upper face
-        below = (lo_l - layer) % g
-        above = (layer - (up_l - 1)) % g
-        stray = leave & (below > R) & (above > R)
-        for nb, faces in self._nbrs:
-            mig = leave & (owner == nb)
-            halo = torch.zeros_like(leave)
-            if "lo" in faces:
-                halo |= ~leave & (layer < lo_l + R)
-            if "up" in faces:
-                halo |= ~leave & (layer >= up_l - R)
-            mi, hi = torch.nonzero(mig).flatten(), torch.nonzero(halo).flatten()
-            mf = torch.zeros((self.migrant_cap, wF), dtype=self.dtype, device=dev)
-            mint = torch.zeros((self.migrant_cap, 3), dtype=torch.int64, device=dev)
-            hf = torch.zeros((self.ghost_cap, wG), dtype=self.dtype, device=dev)
-            hint = torch.zeros((self.ghost_cap, 2), dtype=torch.int64, device=dev)
-            cm, ch = min(mi.numel(), self.migrant_cap), min(hi.numel(), self.ghost_cap)
-            mf[:cm] = self._pack(mi[:cm], FF)
-            mint[:cm] = torch.stack([self.buf["gid"][mi[:cm]], self.buf["mat_id"][mi[:cm]].long(),
-                                     self.buf["fixed"][mi[:cm]].long()], dim=1)
-            hf[:ch] = self._pack(hi[:ch], GF)
-            hint[:ch] = torch.stack([self.buf["gid"][hi[:ch]], self.buf["mat_id"][hi[:ch]].long()], dim=1)
-            cnt = torch.tensor([mi.numel(), hi.numel(), int(stray.any())], dtype=torch.int64, device=dev)
-            # the leavers stay behind as ghosts (they sit within R layers of the face they crossed)
-            kept_f.append(self._pack(mi[:cm], GF))
-            kept_i.append(mint[:cm, :2])
-            rbuf = dict(cnt=torch.zeros(3, dtype=torch.int64, device=dev), mf=torch.empty_like(mf),
-                        mint=torch.empty_like(mint), hf=torch.empty_like(hf), hint=torch.empty_like(hint))
-            sbuf = dict(cnt=cnt, mf=mf, mint=mint, hf=hf, hint=hint)
-            sends.append(sbuf)
-            recvs.append(rbuf)
-            for k in ("cnt", "mf", "mint", "hf", "hint"):
-                ops.append(dist.P2POp(dist.isend, sbuf[k], nb, group=self.group))
-                ops.append(dist.P2POp(dist.irecv, rbuf[k], nb, group=self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        # ---- the one host synchronisation of the step: counts ----
-        counts = torch.stack([s["cnt"] for s in sends] + [r["cnt"] for r in recvs]).tolist() if sends else []
-        k = len(sends)
-        for (nb, _), c in zip(self._nbrs * 2, counts):
-            if c[0] > self.migrant_cap or c[1] > self.ghost_cap:
-                raise RuntimeError(f"slab exchange with rank {nb}: {c[0]} migrants / {c[1]} ghosts exceed the "
-                                   f"capacities {self.migrant_cap} / {self.ghost_cap}")
-            if c[2]:
-                raise RuntimeError("a particle moved further than the halo in one step (time step too large "
-                                   "for this slab decomposition)")
-        # ---- owned rows: fill the holes ----
-        leave_idx = torch.nonzero(leave).flatten()
-        n_leave = leave_idx.numel()
-        arr_f = [recvs[j]["mf"][:counts[k + j][0]] for j in range(k)]
-        arr_i = [recvs[j]["mint"][:counts[k + j][0]] for j in range(k)]
-        arr_f = torch.cat(arr_f) if arr_f else torch.zeros((0, wF), dtype=self.dtype, device=dev)
-        arr_i = torch.cat(arr_i) if arr_i else torch.zeros((0, 3), dtype=torch.int64, device=dev)
-        n_arr = arr_f.shape[0]
-        new_n = n - n_leave + n_arr
-        if new_n > self.cap:
-            raise RuntimeError(f"rank {self.rank}: {new_n} owned particles exceed the capacity {self.cap}")
-        fill = min(n_leave, n_arr)
-        dst = torch.cat([leave_idx[:fill], torch.arange(n, n + n_arr - fill, device=dev)])
-        self._write_rows(dst, arr_f, arr_i)
-        if n_leave > n_arr:  # more leavers than arrivals: pull rows from the tail into the remaining holes
-            holes = leave_idx[fill:]
-            holes_low = holes[holes < new_n]
-            tail = torch.arange(new_n, n, device=dev)
-            tail = tail[~leave[new_n:n]]
-            assert tail.numel() == holes_low.numel()
-            for name in (*FF, "gid", "mat_id", "fixed"):
-                self.buf[name][holes_low] = self.buf[name][tail]
-        self.n_own = new_n
-        # ---- ghost rows: leavers kept behind, then the neighbours' halos ----
-        gf = kept_f + [recvs[j]["hf"][:counts[k + j][1]] for j in range(k)]
-        gi = kept_i + [recvs[j]["hint"][:counts[k + j][1]] for j in range(k)]
-        gf = torch.cat(gf) if gf else torch.zeros((0, wG), dtype=self.dtype, device=dev)
-        gi = torch.cat(gi) if gi else torch.zeros((0, 2), dtype=torch.int64, device=dev)
-        ng = gf.shape[0]
-        if new_n + ng > self.cap:
-            raise RuntimeError(f"rank {self.rank}: {new_n} owned + {ng} ghost rows exceed the capacity {self.cap}")
-        sl = slice(new_n, new_n + ng)
-        self._unpack(gf, GF, sl)
-        self.buf["gid"][sl] = gi[:, 0]
-        self.buf["mat_id"][sl] = gi[:, 1].to(self.buf["mat_id"].dtype)
-        self.buf["fixed"][sl] = False
-        self.n_ghost = ng
-
-    def _write_rows(self, dst: torch.Tensor, f: torch.Tensor, i: torch.Tensor) -> None:
-        c = 0
-        for name in self.FLOAT_FIELDS:
-            w = self.widths[name]
-            self.buf[name][dst] = f[:, c:c + w].reshape(dst.numel(), *self.buf[name].shape[1:])
-            c += w
-        self.buf["gid"][dst] = i[:, 0]
-        self.buf["mat_id"][dst] = i[:, 1].to(self.buf["mat_id"].dtype)
-        self.buf["fixed"][dst] = i[:, 2].bool()
+        """Migration + halo exchange after the drift (one neighbour exchange, one host sync)."""
+        if self.world == 1:
+            self.n_ghost = 0
+            return
+        self.engine.pack(self)  # stayers -> alt rows; leavers / halo -> messages; counts -> headers
+        # sends in (lower, upper) order, receives in (upper, lower) order: with two ranks both
+        # messages travel between the same pair and are matched in posting order
+        ops = [dist.P2POp(dist.isend, self.send_lo, self.lo_rank, group=self.group),
+               dist.P2POp(dist.isend, self.send_up, self.up_rank, group=self.group),
+               dist.P2POp(dist.irecv, self.recv_up, self.up_rank, group=self.group),
+               dist.P2POp(dist.irecv, self.recv_lo, self.lo_rank, group=self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        # ---- the one host synchronisation of the step: the counts (they are launch parameters) ----
+        h = torch.stack([self.header_local, self.recv_lo[0:64].view(torch.int64),
+                         self.recv_up[0:64].view(torch.int64)]).tolist()
+        n_stay, k_lo, k_up, stray = h[0][0], h[0][1], h[0][2], h[0][3]
+        a_lo, g_lo, a_up, g_up = h[1][0], h[1][1], h[2][0], h[2][1]
+        if stray or h[1][2] or h[2][2]:
+            raise RuntimeError("slab exchange: a particle moved further than the halo in one step, or the box "
+                               "changed under the static slab layout")
+        if max(k_lo, k_up, a_lo, a_up) > self.migrant_cap or max(g_lo, g_up) > self.ghost_cap:
+            raise RuntimeError(f"slab exchange: {max(k_lo, k_up, a_lo, a_up)} migrants / {max(g_lo, g_up)} ghosts "
+                               f"exceed the message capacities {self.migrant_cap} / {self.ghost_cap}")
+        n_new = n_stay + a_lo + a_up
+        n_gh = k_lo + k_up + g_lo + g_up
+        if n_new + n_gh > self.cap:
+            raise RuntimeError(f"rank {self.rank}: {n_new} owned + {n_gh} ghost rows exceed the capacity {self.cap}")
+        self.engine.unpack(self, (n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up))
+        self.buf, self.alt = self.alt, self.buf
+        self.n_own, self.n_ghost = n_new, n_gh
+        self.last_counts = (max(k_lo, k_up, a_lo, a_up), max(g_lo, g_up))
 
     # ------------------------------------------------------------------ stepping
     def step(self, n: int = 1) -> None:
@@ -382,4 +400,5 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
                            force_manager_kw=dict(gravity=gravity), dtype=dtype, device=dev)
     slab.engine = CudaEngine(system)
     slab.system = system
+    slab.tune_capacities()
     return slab

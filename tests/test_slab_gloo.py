@@ -75,6 +75,74 @@ class OracleEngine:
         oint.ROTATION[self.rot][1](ost, osy)
         self._back(ost, st, ("force", "torque", "vel", "ang_vel"))
 
+    # ---- CPU restatement of the exchange kernels (csrc/slab.cu) on the same message layout ----
+    @staticmethod
+    def _cat(bufs, idx, fields, widths):
+        return torch.cat([bufs[k][idx].reshape(idx.numel(), widths[k]) for k in fields], dim=1)
+
+    def pack(self, slab):
+        from jaxdem_b200.slab import GHOST_FLOAT_FIELDS, ROW_FLOAT_FIELDS, cell_layer, message_views
+        n, lay, R, G = slab.n_own, slab.layout, slab.layout.R, slab.layout.n_layers
+        lo, up = lay.bounds[slab.rank], lay.bounds[slab.rank + 1]
+        b = slab.buf
+        layer = cell_layer(b["pos_c"][:n, -1], slab.anchor_last, slab.box_last, G)
+        inside = (layer >= lo) & (layer < up)
+        below, above = (lo - layer) % G, (layer - (up - 1)) % G
+        leave_lo = ~inside & (below >= 1) & (below <= R)
+        leave_up = ~inside & ~leave_lo & (above >= 1) & (above <= R)
+        stray = ~inside & ~leave_lo & ~leave_up
+        stay = inside | stray
+        halo_lo, halo_up = inside & (layer < lo + R), inside & (layer >= up - R)
+        nz = lambda m: torch.nonzero(m).flatten()
+        si = nz(stay)
+        for k in (*ROW_FLOAT_FIELDS, "gid", "mat_id", "fixed"):
+            slab.alt[k][:si.numel()] = b[k][si]
+        kept = message_views(slab.kept, slab.kept_layout, slab.dtype)
+        for msg, mi, hi, koff in ((slab.send_lo, nz(leave_lo), nz(halo_lo), 0),
+                                  (slab.send_up, nz(leave_up), nz(halo_up), slab.migrant_cap)):
+            v = message_views(msg, slab.msg_layout, slab.dtype)
+            cm, ch = min(mi.numel(), slab.migrant_cap), min(hi.numel(), slab.ghost_cap)
+            v["mig_f"][:cm] = self._cat(b, mi[:cm], ROW_FLOAT_FIELDS, slab.widths)
+            v["mig_i"][:cm] = torch.stack([b["gid"][mi[:cm]], b["mat_id"][mi[:cm]].long(), b["fixed"][mi[:cm]].long()], 1)
+            v["gh_f"][:ch] = self._cat(b, hi[:ch], GHOST_FLOAT_FIELDS, slab.widths)
+            v["gh_i"][:ch] = torch.stack([b["gid"][hi[:ch]], b["mat_id"][hi[:ch]].long()], 1)
+            v["header"][:3] = torch.tensor([mi.numel(), hi.numel(), int(stray.sum())])
+            kept["gh_f"][koff:koff + cm] = self._cat(b, mi[:cm], GHOST_FLOAT_FIELDS, slab.widths)
+            kept["gh_i"][koff:koff + cm] = torch.stack([b["gid"][mi[:cm]], b["mat_id"][mi[:cm]].long()], 1)
+        slab.header_local[:4] = torch.tensor([si.numel(), int(leave_lo.sum()), int(leave_up.sum()), int(stray.sum())])
+
+    def unpack(self, slab, counts):
+        from jaxdem_b200.slab import GHOST_FLOAT_FIELDS, ROW_FLOAT_FIELDS, message_views
+        n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up = counts
+        lo = message_views(slab.recv_lo, slab.msg_layout, slab.dtype)
+        up = message_views(slab.recv_up, slab.msg_layout, slab.dtype)
+        kp = message_views(slab.kept, slab.kept_layout, slab.dtype)
+        d, w = slab.alt, slab.widths
+        row = n_stay
+
+        def put(fields, f, iv, cnt, full):
+            nonlocal row
+            c = 0
+            sl = slice(row, row + cnt)
+            for k in fields:
+                d[k][sl] = f[:cnt, c:c + w[k]].reshape(d[k][sl].shape)
+                c += w[k]
+            d["gid"][sl] = iv[:cnt, 0]
+            d["mat_id"][sl] = iv[:cnt, 1].to(d["mat_id"].dtype)
+            d["fixed"][sl] = iv[:cnt, 2].bool() if full else False
+            if not full:
+                for k, val in (("force", 0), ("torque", 0), ("inertia", 1), ("q_w", 1), ("q_xyz", 0)):
+                    d[k][sl] = val
+            row += cnt
+
+        put(ROW_FLOAT_FIELDS, lo["mig_f"], lo["mig_i"], a_lo, True)
+        put(ROW_FLOAT_FIELDS, up["mig_f"], up["mig_i"], a_up, True)
+        cm = slab.migrant_cap
+        put(GHOST_FLOAT_FIELDS, kp["gh_f"], kp["gh_i"], k_lo, False)
+        put(GHOST_FLOAT_FIELDS, kp["gh_f"][cm:], kp["gh_i"][cm:], k_up, False)
+        put(GHOST_FLOAT_FIELDS, lo["gh_f"], lo["gh_i"], g_lo, False)
+        put(GHOST_FLOAT_FIELDS, up["gh_f"], up["gh_i"], g_up, False)
+
 
 def _free_port():
     with socket.socket() as s:
