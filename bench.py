@@ -34,6 +34,11 @@ B_ALG_STEP = 168.0  # algorithmic bytes per particle-step, config 2 (SURVEY.md Â
 # algorithmic bytes per particle of each kernel family (DESIGN.md Â§Kernels)
 B_ALG_KERNEL = {
     "k_pair_force": 28.0,   # R pos 12 + rad 4, W force 12
+    # fused sphere driver: + R (vel, mass) 16 of the sorted shadow record, W vel 12 (the after-force kick)
+    "k_pair_flat": 56.0,
+    "k_hash": 105.0,        # R pos 12 vel 12 force 12 rad 4 mass 4 fixed 1 + external buffers 36 + pos_p_rot 12 + bond 4; W pos 12
+    "k_finalize": 44.0,
+    "k_scatter": 20.0,
 }
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -90,6 +95,13 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        if not self.rows:  # timed region shorter than the sampling period: one synchronous sample
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=20).stdout
+                self.rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except (OSError, subprocess.SubprocessError):
+                pass
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
@@ -443,7 +455,8 @@ def run_cuda_slab(args, world, rank, local, dev):
         b.record()
     barrier()
     launches = lib.jdb200_launch_count() - l0
-    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms = float(sum(per_step))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -501,6 +514,7 @@ def run_cuda_slab(args, world, rank, local, dev):
                     "h2d_bytes_per_step": int(t[1].item() / e2e_steps), "d2h_bytes_per_step": int(t[2].item() / e2e_steps),
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
             "roofline": None,
             "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s",
                               "frac": step_gbs / (peak * world), "algorithmic_bytes_per_particle_step": B_ALG_STEP,
@@ -533,10 +547,17 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # the contract is ONE JSON line on stdout: libraries that print banners there (NCCL's version
+    # line) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

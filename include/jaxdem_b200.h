@@ -216,22 +216,23 @@ JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jd
 /* No reference equivalent (the reference runs one system on one device,
  * jaxdem/system.py:60-98); SURVEY.md 8(e).  One periodic sphere system is cut into slabs of
  * cell layers along the LAST axis, one slab per rank (jaxdem_b200/slab.py).  After the drift
- * (step_before_force) `jdb200_slab_pack` classifies the n owned rows of `src` by the cell
+ * (step_before_force) `jdb200_slab_pack` classifies the n owned rows by the cell
  * layer of their last coordinate — the arithmetic of the collider's hash,
  * colliders/cell_list.py:55-60, on the device copies of anchor / box_size / cell_size —
- * compacts the rows that stay into `dst` (index order kept), writes the rows that left as
- * full records into the message of their direction (and as ghost records into `kept`: they
- * stay behind as ghosts) and the rows within `search_range` layers of a face as ghost
- * records.  The caller exchanges the two messages with its neighbours (NCCL), reads the
- * counts from the 64-byte headers (int64: [0] full records, [1] ghost records, [2] rows that
- * moved further than the halo; `header_local`: [0] rows that stay, [1] left downwards,
- * [2] left upwards, [3] strays) and calls `jdb200_slab_unpack`, which appends to `dst`, behind
- * the n_stay compacted rows: arrivals from the lower, then the upper neighbour (owned rows),
- * then the ghost rows (kept lower, kept upper, halo of the lower, halo of the upper neighbour).
- * counts = {n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up}.  Same rules as every entry point:
- * stream-ordered, no host synchronisation, no allocation; all lists keep index order. */
+ * and writes the rows that left as full records into the message of their direction (and as
+ * ghost records into `kept`: they stay behind as ghosts; their row indices go to `holes`) and
+ * the rows within `search_range` layers of a face as ghost records.  The caller exchanges the
+ * two messages with its neighbours (NCCL), reads the counts from the 64-byte headers (int64:
+ * [0] full records, [1] ghost records, [2] rows that moved further than the halo;
+ * `header_local`: [0] rows that stay, [1] left downwards, [2] left upwards, [3] strays) and
+ * calls `jdb200_slab_unpack`, which repairs the owned rows IN PLACE — arrivals (from the lower,
+ * then the upper neighbour) fill the lowest holes or are appended, rows from the tail fill the
+ * holes that are left — and writes the ghost rows behind them (kept lower, kept upper, halo of
+ * the lower, halo of the upper neighbour).  counts = {n_old, a_lo, a_up, k_lo, k_up, g_lo,
+ * g_up}; afterwards n_own = n_old - k_lo - k_up + a_lo + a_up.  Same rules as every entry
+ * point: stream-ordered, no host synchronisation, no allocation; all lists keep index order. */
 typedef struct jdb200_slab_desc {
-  int64_t n;            /* owned rows in src */
+  int64_t n;            /* owned rows */
   int64_t cap_mig;      /* full-record capacity of one message */
   int64_t cap_ghost;    /* ghost-record capacity of one message */
   int32_t dim, dtype;   /* as jdb200_params */
@@ -257,11 +258,13 @@ typedef struct jdb200_slab_rows {
 JDB200_API size_t jdb200_slab_message_bytes(const jdb200_slab_desc* d);
 JDB200_API size_t jdb200_slab_kept_bytes(const jdb200_slab_desc* d);
 JDB200_API size_t jdb200_slab_scratch_bytes(const jdb200_slab_desc* d);
-JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* src,
-                                const jdb200_slab_rows* dst, void* msg_lo, void* msg_up, void* kept,
-                                void* header_local, void* scratch, size_t scratch_bytes);
-JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* dst,
-                                  const int64_t* counts, const void* from_lo, const void* from_up, const void* kept);
+JDB200_API size_t jdb200_slab_holes_bytes(const jdb200_slab_desc* d);
+JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, void* msg_lo,
+                                void* msg_up, void* kept, void* holes, void* header_local, void* scratch,
+                                size_t scratch_bytes);
+JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                  const int64_t* counts, const void* from_lo, const void* from_up, const void* kept,
+                                  void* holes);
 
 /* Number of kernels the library has launched since load (diagnostic counter for
  * bench.py's `gpu_launches`; relaxed atomic, not part of the data path). */

@@ -90,8 +90,9 @@ SYMBOLS = {
     "jdb200_slab_message_bytes": (_SZ, [_PD]),
     "jdb200_slab_kept_bytes": (_SZ, [_PD]),
     "jdb200_slab_scratch_bytes": (_SZ, [_PD]),
-    "jdb200_slab_pack": (C.c_int, [_V, _PD, _PR, _PR, _V, _V, _V, _V, _V, _SZ]),
-    "jdb200_slab_unpack": (C.c_int, [_V, _PD, _PR, C.POINTER(C.c_int64), _V, _V, _V]),
+    "jdb200_slab_holes_bytes": (_SZ, [_PD]),
+    "jdb200_slab_pack": (C.c_int, [_V, _PD, _PR, _V, _V, _V, _V, _V, _V, _SZ]),
+    "jdb200_slab_unpack": (C.c_int, [_V, _PD, _PR, C.POINTER(C.c_int64), _V, _V, _V, _V]),
     "jdb200_timing_enable": (C.c_int, [C.c_int]),
     "jdb200_timing_collect": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

@@ -5,18 +5,19 @@
 // After the drift every owned particle is classified by the cell layer of its last
 // coordinate — the SAME arithmetic as the collider's hash (cell_coord, cell_list.py:55-60) —
 // into: stays (and lies in the halo of the lower / upper face), leaves to the lower / upper
-// neighbour, or strays (moved further than the halo: reported, never lost).  Stayers are
-// compacted, in index order, into the alternate row buffers; leavers are written as full
-// records into the message of their direction and as ghost records into `kept` (they stay
-// behind as ghosts); halo particles are written as ghost records.  All lists keep the index
-// order (block counts -> one-block scan -> in-block ballot ranks): bitwise repeatable.
+// neighbour, or strays (moved further than the halo: reported, never lost).  Leavers are
+// written as full records into the message of their direction and as ghost records into `kept`
+// (they stay behind as ghosts), and their row indices are listed as holes; halo particles are
+// written as ghost records.  All lists keep the index order (block counts -> one-block scan ->
+// in-block ballot ranks): bitwise repeatable.  After the exchange the owned rows are repaired IN
+// PLACE — arrivals fill the lowest holes (or are appended), rows from the tail fill the holes
+// that are left — so a step moves O(leavers + halo) records, not the whole slab.
 #include "ctx.cuh"
 #include "launch.cuh"
 
 namespace jdb {
 
 constexpr int kSlabBlock = 256;
-constexpr int kSlabLists = 5;  // stay, leave-lo, leave-up, halo-lo, halo-up
 
 template <typename F>
 struct SlabRows {
@@ -218,128 +219,218 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, const
   }
 }
 
-// exclusive scan of the block counts (one block; the lists are short: n / 256 entries), totals
-// into the message headers and the local header
+// exclusive scan of the block counts (one block: thread t owns a contiguous chunk of blocks,
+// the 1024 chunk sums are scanned with shuffles), totals into the message headers and the
+// local header
 __global__ void __launch_bounds__(1024) k_slab_scan(int nblocks, int* __restrict__ bc, long long* __restrict__ hdr_lo,
                                                     long long* __restrict__ hdr_up, long long* __restrict__ hdr_local) {
   pdl_prologue();
-  __shared__ long long s_run[6];
   __shared__ int s_warp[32][6];
-  if (threadIdx.x < 6) s_run[threadIdx.x] = 0;
-  __syncthreads();
+  __shared__ int s_tot[6];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < nblocks; base += 1024) {
-    const int b = base + threadIdx.x;
-    int v[6], incl[6];
+  const int per = (nblocks + 1023) / 1024;
+  const int b0 = min((int)threadIdx.x * per, nblocks), b1 = min(b0 + per, nblocks);
+  int sum[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = b0; b < b1; ++b) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sum[j] += bc[(size_t)b * 8 + j];
+  }
+  int excl[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    int incl = sum[j];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp][j] = incl;
+    excl[j] = incl - sum[j];
+  }
+  __syncthreads();
+  if (warp == 0) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      v[j] = b < nblocks ? bc[(size_t)b * 8 + j] : 0;
-      incl[j] = v[j];
+      const int v = s_warp[lane][j];
+      int incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl[j], o);
-        if (lane >= o) incl[j] += t;
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
-      if (lane == 31) s_warp[warp][j] = incl[j];
+      s_warp[lane][j] = incl - v;
+      if (lane == 31) s_tot[j] = incl;
     }
-    __syncthreads();
-    long long tot[6];
+  }
+  __syncthreads();
+  int run[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) run[j] = excl[j] + s_warp[warp][j];
+  for (int b = b0; b < b1; ++b) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      long long woff = 0, all = 0;
-      for (int w = 0; w < 32; ++w) {
-        if (w < warp) woff += s_warp[w][j];
-        all += s_warp[w][j];
-      }
-      tot[j] = all;
-      if (b < nblocks) bc[(size_t)b * 8 + j] = (int)(s_run[j] + woff + incl[j] - v[j]);
+      const int v = bc[(size_t)b * 8 + j];
+      bc[(size_t)b * 8 + j] = run[j];
+      run[j] += v;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int j = 0; j < 6; ++j) s_run[j] += tot[j];
-    }
-    __syncthreads();
   }
   if (threadIdx.x == 0) {
     // header: [0] full records, [1] ghost records, [2] strays seen by the sender
-    hdr_lo[0] = s_run[1]; hdr_lo[1] = s_run[3]; hdr_lo[2] = s_run[5];
-    hdr_up[0] = s_run[2]; hdr_up[1] = s_run[4]; hdr_up[2] = s_run[5];
-    hdr_local[0] = s_run[0]; hdr_local[1] = s_run[1]; hdr_local[2] = s_run[2]; hdr_local[3] = s_run[5];
+    hdr_lo[0] = s_tot[1]; hdr_lo[1] = s_tot[3]; hdr_lo[2] = s_tot[5];
+    hdr_up[0] = s_tot[2]; hdr_up[1] = s_tot[4]; hdr_up[2] = s_tot[5];
+    hdr_local[0] = s_tot[0]; hdr_local[1] = s_tot[1]; hdr_local[2] = s_tot[2]; hdr_local[3] = s_tot[5];
   }
 }
 
+constexpr int kPackLists = 4;  // leave-lo, leave-up, halo-lo, halo-up (block-count columns 1..4)
+
 template <typename F, int D>
-__global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, SlabRows<F> dst,
-                                                           const uint8_t* __restrict__ cat, const int* __restrict__ bc,
-                                                           void* msg_lo, void* msg_up, void* kept) {
+__global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, const uint8_t* __restrict__ cat,
+                                                           const int* __restrict__ bc, void* msg_lo, void* msg_up,
+                                                           void* kept, int* __restrict__ holes) {
   pdl_prologue();
   using M = SlabMsg<F, D>;
-  __shared__ int s_w[kSlabBlock / 32][kSlabLists];
+  __shared__ int s_w[kSlabBlock / 32][kPackLists];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < gm.n;
   const int c8 = live ? cat[i] : 0;
   const bool stay = live && !(c8 & 12);
-  const bool fl[kSlabLists] = {stay, live && (c8 & 4) != 0, live && (c8 & 8) != 0, stay && (c8 & 1) != 0,
+  const bool fl[kPackLists] = {live && (c8 & 4) != 0, live && (c8 & 8) != 0, stay && (c8 & 1) != 0,
                                stay && (c8 & 2) != 0};
+  if (!__syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3])) return;  // interior block: nothing to pack
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int rank[kSlabLists];
+  int rank[kPackLists];
 #pragma unroll
-  for (int j = 0; j < kSlabLists; ++j) {
+  for (int j = 0; j < kPackLists; ++j) {
     const unsigned m = __ballot_sync(0xffffffffu, fl[j]);
     rank[j] = __popc(m & ((1u << lane) - 1u));
     if (lane == 0) s_w[warp][j] = __popc(m);
   }
   __syncthreads();
-  const int* base = bc + (size_t)blockIdx.x * 8;
+  const int* base = bc + (size_t)blockIdx.x * 8 + 1;
 #pragma unroll
-  for (int j = 0; j < kSlabLists; ++j) {
+  for (int j = 0; j < kPackLists; ++j) {
     int woff = 0;
     for (int w = 0; w < warp; ++w) woff += s_w[w][j];
     rank[j] += woff + base[j];
   }
   if (!live) return;
-  if (stay) {
-    F f[M::WF];
-    long long iv[3];
-    write_full<F, D>(src, i, f, iv);
-    read_full<F, D>(dst, rank[0], f, iv);
-  }
   const M lo(msg_lo, gm.cap_m, gm.cap_g), up(msg_up, gm.cap_m, gm.cap_g);
-  // kept: ghost records of the leavers, lower direction in rows [0, cap_m), upper in [cap_m, 2 cap_m)
+  // kept: ghost records of the leavers, lower direction in rows [0, cap_m), upper in [cap_m, 2 cap_m);
+  // holes: their row indices, same split
   const M kp(kept, 0, 2 * gm.cap_m);
+  if (fl[0] && rank[0] < gm.cap_m) {
+    write_full<F, D>(src, i, lo.mig_f + (size_t)rank[0] * M::WF, lo.mig_i + (size_t)rank[0] * 3);
+    write_ghost<F, D>(src, i, kp.gh_f + (size_t)rank[0] * M::WG, kp.gh_i + (size_t)rank[0] * 2);
+    holes[rank[0]] = (int)i;
+  }
   if (fl[1] && rank[1] < gm.cap_m) {
-    write_full<F, D>(src, i, lo.mig_f + (size_t)rank[1] * M::WF, lo.mig_i + (size_t)rank[1] * 3);
-    write_ghost<F, D>(src, i, kp.gh_f + (size_t)rank[1] * M::WG, kp.gh_i + (size_t)rank[1] * 2);
+    write_full<F, D>(src, i, up.mig_f + (size_t)rank[1] * M::WF, up.mig_i + (size_t)rank[1] * 3);
+    write_ghost<F, D>(src, i, kp.gh_f + (size_t)(gm.cap_m + rank[1]) * M::WG, kp.gh_i + (size_t)(gm.cap_m + rank[1]) * 2);
+    holes[gm.cap_m + rank[1]] = (int)i;
   }
-  if (fl[2] && rank[2] < gm.cap_m) {
-    write_full<F, D>(src, i, up.mig_f + (size_t)rank[2] * M::WF, up.mig_i + (size_t)rank[2] * 3);
-    write_ghost<F, D>(src, i, kp.gh_f + (size_t)(gm.cap_m + rank[2]) * M::WG, kp.gh_i + (size_t)(gm.cap_m + rank[2]) * 2);
-  }
+  if (fl[2] && rank[2] < gm.cap_g)
+    write_ghost<F, D>(src, i, lo.gh_f + (size_t)rank[2] * M::WG, lo.gh_i + (size_t)rank[2] * 2);
   if (fl[3] && rank[3] < gm.cap_g)
-    write_ghost<F, D>(src, i, lo.gh_f + (size_t)rank[3] * M::WG, lo.gh_i + (size_t)rank[3] * 2);
-  if (fl[4] && rank[4] < gm.cap_g)
-    write_ghost<F, D>(src, i, up.gh_f + (size_t)rank[4] * M::WG, up.gh_i + (size_t)rank[4] * 2);
+    write_ghost<F, D>(src, i, up.gh_f + (size_t)rank[3] * M::WG, up.gh_i + (size_t)rank[3] * 2);
 }
 
-// rows behind the stayers: arrivals from the lower, then the upper neighbour (owned), then the
-// ghosts: leavers kept behind (lower, upper), halo of the lower, halo of the upper neighbour
+// counts of one exchange, known on the host after it: owned rows before, arrivals from the
+// lower / upper neighbour, leavers to the lower / upper neighbour, halo of the lower / upper
 struct SlabCounts {
-  long long n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up;
+  long long n_old, a_lo, a_up, k_lo, k_up, g_lo, g_up;
 };
 
+// holes[0, k_lo) and holes[cap_m, cap_m + k_up) are sorted; merged (sorted) list -> holes[2 cap_m ...)
+__global__ void __launch_bounds__(kSlabBlock) k_slab_merge_holes(SlabGeom gm, SlabCounts cn, int* __restrict__ holes) {
+  pdl_prologue();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long l = cn.k_lo + cn.k_up;
+  if (t >= l) return;
+  const bool first = t < cn.k_lo;
+  const int* mine = first ? holes : holes + gm.cap_m;
+  const int* other = first ? holes + gm.cap_m : holes;
+  const long long r = first ? t : t - cn.k_lo, no = first ? cn.k_up : cn.k_lo;
+  const int v = mine[r];
+  long long lo = 0, hi = no;  // number of entries of the other list below v (indices are distinct)
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (other[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  holes[2 * gm.cap_m + r + lo] = v;
+}
+
+template <typename F, int D>
+__device__ __forceinline__ void copy_row(const SlabRows<F>& s, long long from, long long to) {
+  F f[SlabMsg<F, D>::WF];
+  long long iv[3];
+  write_full<F, D>(s, from, f, iv);
+  read_full<F, D>(s, to, f, iv);
+}
+
+// more leavers than arrivals: the holes the arrivals do not fill are R = sorted_holes[a, l); the new
+// row count is n' = n_old - (l - a).  Rows of the tail [n', n_old) that are not holes move, in index
+// order, into the holes below n' (a prefix of R).  One block: the tail is l - a rows long.
+template <typename F, int D>
+__global__ void __launch_bounds__(1024) k_slab_tail_move(SlabGeom gm, SlabRows<F> rows, SlabCounts cn,
+                                                         const int* __restrict__ holes) {
+  pdl_prologue();
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
+  const long long nr = l - a, n_new = cn.n_old - nr;
+  const int* R = holes + 2 * gm.cap_m + a;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long t0 = 0; t0 < nr; t0 += 1024) {
+    const long long row = n_new + t0 + threadIdx.x;
+    bool mover = false;
+    if (row < cn.n_old) {
+      long long lo = 0, hi = nr;  // is `row` one of the holes?
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (R[mid] < row) lo = mid + 1; else hi = mid;
+      }
+      mover = !(lo < nr && R[lo] == row);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mover);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) woff += s_warp[w];
+      tot += s_warp[w];
+    }
+    rank += woff + s_base;
+    if (mover) copy_row<F, D>(rows, row, R[rank]);
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += tot;
+    __syncthreads();
+  }
+}
+
+// arrivals from the lower, then the upper neighbour: into the lowest holes, the rest appended;
+// then the ghost rows behind the owned rows: leavers kept behind (lower, upper), halo of the
+// lower, halo of the upper neighbour
 template <typename F, int D>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(SlabGeom gm, SlabRows<F> dst, SlabCounts cn,
-                                                             const void* from_lo, const void* from_up, const void* kept) {
+                                                             const void* from_lo, const void* from_up, const void* kept,
+                                                             const int* __restrict__ holes) {
   pdl_prologue();
   using M = SlabMsg<F, D>;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const M lo((void*)from_lo, gm.cap_m, gm.cap_g), up((void*)from_up, gm.cap_m, gm.cap_g), kp((void*)kept, 0, 2 * gm.cap_m);
-  long long row = cn.n_stay + t;
-  if (t < cn.a_lo) { read_full<F, D>(dst, row, lo.mig_f + (size_t)t * M::WF, lo.mig_i + (size_t)t * 3); return; }
-  t -= cn.a_lo;
-  if (t < cn.a_up) { read_full<F, D>(dst, row, up.mig_f + (size_t)t * M::WF, up.mig_i + (size_t)t * 3); return; }
-  t -= cn.a_up;
+  const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
+  if (t < a) {
+    const long long row = t < l ? (long long)holes[2 * gm.cap_m + t] : cn.n_old + (t - l);
+    if (t < cn.a_lo) read_full<F, D>(dst, row, lo.mig_f + (size_t)t * M::WF, lo.mig_i + (size_t)t * 3);
+    else read_full<F, D>(dst, row, up.mig_f + (size_t)(t - cn.a_lo) * M::WF, up.mig_i + (size_t)(t - cn.a_lo) * 3);
+    return;
+  }
+  t -= a;
+  const long long row = cn.n_old - l + a + t;
   if (t < cn.k_lo) { read_ghost<F, D>(dst, row, kp.gh_f + (size_t)t * M::WG, kp.gh_i + (size_t)t * 2); return; }
   t -= cn.k_lo;
   if (t < cn.k_up) {
@@ -365,30 +456,34 @@ static inline SlabGeom slab_geom(const jdb200_slab_desc* d) {
 }
 
 template <typename F, int D>
-int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* src, const jdb200_slab_rows* dst,
-              void* msg_lo, void* msg_up, void* kept, void* header_local, void* scratch) {
+int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, void* msg_lo, void* msg_up,
+              void* kept, void* holes, void* header_local, void* scratch) {
   using M = SlabMsg<F, D>;
   const SlabGeom gm = slab_geom(d);
   const int nb = std::max(1, cdiv(d->n, kSlabBlock));
   uint8_t* cat = (uint8_t*)scratch;
   int* bc = (int*)((char*)scratch + (((size_t)nb * kSlabBlock + 255) & ~size_t(255)));
-  JDB_LAUNCH((k_slab_classify<F, D>), dim3(nb), kSlabBlock, s, gm, (const F*)src->pos_c, (const F*)d->anchor,
+  JDB_LAUNCH((k_slab_classify<F, D>), dim3(nb), kSlabBlock, s, gm, (const F*)rows->pos_c, (const F*)d->anchor,
              (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
   const M lo(msg_lo, gm.cap_m, gm.cap_g), up(msg_up, gm.cap_m, gm.cap_g);
   JDB_LAUNCH(k_slab_scan, dim3(1), 1024, s, nb, bc, lo.header, up.header, (long long*)header_local);
-  JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(src), slab_rows<F>(dst), cat, bc, msg_lo,
-             msg_up, kept);
+  JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, msg_lo, msg_up, kept,
+             (int*)holes);
   return 0;
 }
 
 template <typename F, int D>
-int slab_unpack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* dst, const int64_t* counts,
-                const void* from_lo, const void* from_up, const void* kept) {
+int slab_unpack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, const int64_t* counts,
+                const void* from_lo, const void* from_up, const void* kept, void* holes) {
   const SlabCounts cn{counts[0], counts[1], counts[2], counts[3], counts[4], counts[5], counts[6]};
-  const long long tot = cn.a_lo + cn.a_up + cn.k_lo + cn.k_up + cn.g_lo + cn.g_up;
-  if (tot == 0) return 0;
-  JDB_LAUNCH((k_slab_unpack<F, D>), dim3(cdiv(tot, kSlabBlock)), kSlabBlock, s, slab_geom(d), slab_rows<F>(dst), cn,
-             from_lo, from_up, kept);
+  const SlabGeom gm = slab_geom(d);
+  const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
+  if (l > 0) JDB_LAUNCH(k_slab_merge_holes, dim3(cdiv(l, kSlabBlock)), kSlabBlock, s, gm, cn, (int*)holes);
+  if (l > a) JDB_LAUNCH((k_slab_tail_move<F, D>), dim3(1), 1024, s, gm, slab_rows<F>(rows), cn, (const int*)holes);
+  const long long tot = a + cn.k_lo + cn.k_up + cn.g_lo + cn.g_up;
+  if (tot > 0)
+    JDB_LAUNCH((k_slab_unpack<F, D>), dim3(cdiv(tot, kSlabBlock)), kSlabBlock, s, gm, slab_rows<F>(rows), cn, from_lo,
+               from_up, kept, (const int*)holes);
   return 0;
 }
 
@@ -427,26 +522,32 @@ JDB200_API size_t jdb200_slab_scratch_bytes(const jdb200_slab_desc* d) {
   return ((nb * kSlabBlock + 255) & ~size_t(255)) + nb * 8 * sizeof(int) + 256;
 }
 
-JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* src,
-                                const jdb200_slab_rows* dst, void* msg_lo, void* msg_up, void* kept,
-                                void* header_local, void* scratch, size_t scratch_bytes) {
+JDB200_API size_t jdb200_slab_holes_bytes(const jdb200_slab_desc* d) {
+  if (slab_check(d)) return 0;
+  return (size_t)d->cap_mig * 4 * sizeof(int) + 64;
+}
+
+JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, void* msg_lo,
+                                void* msg_up, void* kept, void* holes, void* header_local, void* scratch,
+                                size_t scratch_bytes) {
   int rc = slab_check(d);
   if (rc) return rc;
-  if (!src || !dst || !msg_lo || !msg_up || !kept || !header_local || !scratch || !d->anchor || !d->box_size ||
+  if (!rows || !msg_lo || !msg_up || !kept || !holes || !header_local || !scratch || !d->anchor || !d->box_size ||
       !d->cell_size)
     return JDB200_ENULL;
   if (scratch_bytes < jdb200_slab_scratch_bytes(d)) return JDB200_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  SLAB_DISPATCH((slab_pack<F, D>(s, d, src, dst, msg_lo, msg_up, kept, header_local, scratch)))
+  SLAB_DISPATCH((slab_pack<F, D>(s, d, rows, msg_lo, msg_up, kept, holes, header_local, scratch)))
 }
 
-JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* dst,
-                                  const int64_t* counts, const void* from_lo, const void* from_up, const void* kept) {
+JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                  const int64_t* counts, const void* from_lo, const void* from_up, const void* kept,
+                                  void* holes) {
   int rc = slab_check(d);
   if (rc) return rc;
-  if (!dst || !counts || !from_lo || !from_up || !kept) return JDB200_ENULL;
+  if (!rows || !counts || !from_lo || !from_up || !kept || !holes) return JDB200_ENULL;
   cudaStream_t s = (cudaStream_t)stream;
-  SLAB_DISPATCH((slab_unpack<F, D>(s, d, dst, counts, from_lo, from_up, kept)))
+  SLAB_DISPATCH((slab_unpack<F, D>(s, d, rows, counts, from_lo, from_up, kept, holes)))
 }
 
 }  // extern "C"

@@ -168,27 +168,27 @@ class CudaEngine:
             dcap = self._desc(slab, slab.cap)
             self._scratch = torch.empty(lib.jdb200_slab_scratch_bytes(C.byref(dcap)), dtype=torch.uint8,
                                         device=slab.device)
-        src, dst = self._rows(slab.buf), self._rows(slab.alt)
-        L.check(lib.jdb200_slab_pack(_call.stream_ptr(slab.device), C.byref(d), C.byref(src), C.byref(dst),
+        rows = self._rows(slab.buf)
+        L.check(lib.jdb200_slab_pack(_call.stream_ptr(slab.device), C.byref(d), C.byref(rows),
                                      slab.send_lo.data_ptr(), slab.send_up.data_ptr(), slab.kept.data_ptr(),
-                                     slab.header_local.data_ptr(), self._scratch.data_ptr(),
+                                     slab.holes.data_ptr(), slab.header_local.data_ptr(), self._scratch.data_ptr(),
                                      self._scratch.numel()), "jdb200_slab_pack")
 
     def unpack(self, slab, counts):
         import ctypes as C
         from . import _call, _lib as L
         d = self._desc(slab, slab.n_own)
-        dst = self._rows(slab.alt)
+        rows = self._rows(slab.buf)
         arr = (C.c_int64 * 7)(*[int(c) for c in counts])
-        L.check(L.lib().jdb200_slab_unpack(_call.stream_ptr(slab.device), C.byref(d), C.byref(dst), arr,
-                                           slab.recv_lo.data_ptr(), slab.recv_up.data_ptr(), slab.kept.data_ptr()),
+        L.check(L.lib().jdb200_slab_unpack(_call.stream_ptr(slab.device), C.byref(d), C.byref(rows), arr,
+                                           slab.recv_lo.data_ptr(), slab.recv_up.data_ptr(), slab.kept.data_ptr(),
+                                           slab.holes.data_ptr()),
                 "jdb200_slab_unpack")
 
 
 class SlabSystem:
-    """Owned + ghost particles of one rank, in capacity-sized row buffers (two sets: the
-    exchange compacts out of place); ``view(n)`` exposes the first n rows of the current set as
-    a ``State`` whose tensors alias the buffers (the C ABI works in place)."""
+    """Owned + ghost particles of one rank, in capacity-sized row buffers; ``view(n)`` exposes the
+    first n rows as a ``State`` whose tensors alias the buffers (the C ABI works in place)."""
 
     def __init__(self, *, dim, dtype, device, capacity, box, anchor, n_layers, search_range, group=None,
                  ghost_capacity=None, migrant_capacity=None):
@@ -214,7 +214,7 @@ class SlabSystem:
             b["fixed"] = torch.zeros(self.cap, dtype=torch.bool, device=dev)
             return b
 
-        self.buf, self.alt = make_set(), make_set()
+        self.buf = make_set()
         # static rows of a sphere system: pos_p = 0, clump_id = arange, no bonds
         self.static = dict(
             pos_p=torch.zeros((self.cap, dim), dtype=F, device=dev),
@@ -230,6 +230,9 @@ class SlabSystem:
         lo, up = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         self.lo_rank, self.up_rank = lo, up
         self.header_local = torch.zeros(8, dtype=torch.int64, device=dev)
+        self._host_headers = torch.zeros((3, 8), dtype=torch.int64)
+        if dev.type == "cuda":
+            self._host_headers = self._host_headers.pin_memory()
         self.set_capacities(int(ghost_capacity or max(1024, self.cap // 4)),
                             int(migrant_capacity or max(256, self.cap // 16)))
 
@@ -243,6 +246,8 @@ class SlabSystem:
         self.send_lo, self.send_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
         self.recv_lo, self.recv_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
         self.kept = mk(self.kept_layout["bytes"])
+        # row indices of the leavers: [0, cap_m) downwards, [cap_m, 2 cap_m) upwards, [2 cap_m, 4 cap_m) merged
+        self.holes = torch.zeros(4 * self.migrant_cap + 16, dtype=torch.int32, device=self.device)
 
     def tune_capacities(self, slack: float = 2.0) -> None:
         """Shrink the messages to ``slack`` x the counts of one trial exchange (collective)."""
@@ -302,7 +307,7 @@ class SlabSystem:
         if self.world == 1:
             self.n_ghost = 0
             return
-        self.engine.pack(self)  # stayers -> alt rows; leavers / halo -> messages; counts -> headers
+        self.engine.pack(self)  # leavers / halo rows -> messages, leavers' rows -> holes, counts -> headers
         # sends in (lower, upper) order, receives in (upper, lower) order: with two ranks both
         # messages travel between the same pair and are matched in posting order
         ops = [dist.P2POp(dist.isend, self.send_lo, self.lo_rank, group=self.group),
@@ -312,9 +317,14 @@ class SlabSystem:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         # ---- the one host synchronisation of the step: the counts (they are launch parameters) ----
-        h = torch.stack([self.header_local, self.recv_lo[0:64].view(torch.int64),
-                         self.recv_up[0:64].view(torch.int64)]).tolist()
-        n_stay, k_lo, k_up, stray = h[0][0], h[0][1], h[0][2], h[0][3]
+        hh = self._host_headers
+        hh[0].copy_(self.header_local, non_blocking=True)
+        hh[1].copy_(self.recv_lo[0:64].view(torch.int64), non_blocking=True)
+        hh[2].copy_(self.recv_up[0:64].view(torch.int64), non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        h = hh.tolist()
+        k_lo, k_up, stray = h[0][1], h[0][2], h[0][3]
         a_lo, g_lo, a_up, g_up = h[1][0], h[1][1], h[2][0], h[2][1]
         if stray or h[1][2] or h[2][2]:
             raise RuntimeError("slab exchange: a particle moved further than the halo in one step, or the box "
@@ -322,12 +332,12 @@ class SlabSystem:
         if max(k_lo, k_up, a_lo, a_up) > self.migrant_cap or max(g_lo, g_up) > self.ghost_cap:
             raise RuntimeError(f"slab exchange: {max(k_lo, k_up, a_lo, a_up)} migrants / {max(g_lo, g_up)} ghosts "
                                f"exceed the message capacities {self.migrant_cap} / {self.ghost_cap}")
-        n_new = n_stay + a_lo + a_up
+        n_new = self.n_own - k_lo - k_up + a_lo + a_up
         n_gh = k_lo + k_up + g_lo + g_up
-        if n_new + n_gh > self.cap:
+        if max(n_new, self.n_own) + n_gh > self.cap:
             raise RuntimeError(f"rank {self.rank}: {n_new} owned + {n_gh} ghost rows exceed the capacity {self.cap}")
-        self.engine.unpack(self, (n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up))
-        self.buf, self.alt = self.alt, self.buf
+        # owned rows repaired in place (arrivals into the holes, tail rows into what is left), ghosts behind
+        self.engine.unpack(self, (self.n_own, a_lo, a_up, k_lo, k_up, g_lo, g_up))
         self.n_own, self.n_ghost = n_new, n_gh
         self.last_counts = (max(k_lo, k_up, a_lo, a_up), max(g_lo, g_up))
 

@@ -463,35 +463,43 @@ def test_slab_pack_unpack_kernels_bit_exact(dtype, dim):
     twin = copy.copy(slab)
     twin.device = torch.device("cpu")
     twin.buf = {k: v.cpu().clone() for k, v in slab.buf.items()}
-    twin.alt = {k: v.cpu().clone() for k, v in slab.alt.items()}
     twin.header_local = torch.zeros(8, dtype=torch.int64)
     twin.set_capacities(4096, 4096)
     ref = OracleEngine(twin, box=inp["box"], law="spring", lin="verlet", rot="", dt=1e-3, dtype=dtype)
-    slab.engine.pack(slab)
-    ref.pack(twin)
-    torch.cuda.synchronize()
-    hl, hr = slab.header_local.cpu(), twin.header_local
-    assert torch.equal(hl[:4], hr[:4]) and int(hl[1]) > 0 and int(hl[2]) > 0 and int(hl[3]) > 0, (hl, hr)
-    n_stay = int(hl[0])
-    for k in slab.alt:
-        assert torch.equal(slab.alt[k][:n_stay].cpu(), twin.alt[k][:n_stay]), k
-    for a, b in ((slab.send_lo, twin.send_lo), (slab.send_up, twin.send_up)):
-        va, vb = message_views(a.cpu(), slab.msg_layout, F), message_views(b, slab.msg_layout, F)
-        assert torch.equal(va["header"][:3], vb["header"][:3])
-        nm, ng = int(va["header"][0]), int(va["header"][1])
-        assert ng > 0
-        assert torch.equal(va["mig_f"][:nm], vb["mig_f"][:nm]) and torch.equal(va["mig_i"][:nm], vb["mig_i"][:nm])
-        assert torch.equal(va["gh_f"][:ng], vb["gh_f"][:ng]) and torch.equal(va["gh_i"][:ng], vb["gh_i"][:ng])
-    # self-exchange: what went down comes back from above and vice versa
-    for s in (slab, twin):
-        s.recv_up.copy_(s.send_lo)
-        s.recv_lo.copy_(s.send_up)
-    h = [message_views(twin.recv_lo, twin.msg_layout, F)["header"], message_views(twin.recv_up, twin.msg_layout, F)["header"]]
-    counts = (n_stay, int(h[0][0]), int(h[1][0]), int(hr[1]), int(hr[2]), int(h[0][1]), int(h[1][1]))
-    slab.engine.unpack(slab, counts)
-    ref.unpack(twin, counts)
-    torch.cuda.synchronize()
-    tot = sum(counts)
-    assert tot <= slab.cap
-    for k in slab.alt:
-        assert torch.equal(slab.alt[k][:tot].cpu(), twin.alt[k][:tot]), k
+    for arrivals_fewer in (False, True):
+        slab.engine.pack(slab)
+        ref.pack(twin)
+        torch.cuda.synchronize()
+        hl, hr = slab.header_local.cpu(), twin.header_local
+        assert torch.equal(hl[:4], hr[:4]) and int(hl[1]) > 0 and int(hl[2]) > 0 and int(hl[3]) > 0, (hl, hr)
+        k_lo, k_up = int(hl[1]), int(hl[2])
+        cm = slab.migrant_cap
+        assert torch.equal(slab.holes[:k_lo].cpu(), twin.holes[:k_lo])
+        assert torch.equal(slab.holes[cm:cm + k_up].cpu(), twin.holes[cm:cm + k_up])
+        for a, b in ((slab.send_lo, twin.send_lo), (slab.send_up, twin.send_up)):
+            va, vb = message_views(a.cpu(), slab.msg_layout, F), message_views(b, slab.msg_layout, F)
+            assert torch.equal(va["header"][:3], vb["header"][:3])
+            nm, ng = int(va["header"][0]), int(va["header"][1])
+            assert ng > 0
+            assert torch.equal(va["mig_f"][:nm], vb["mig_f"][:nm]) and torch.equal(va["mig_i"][:nm], vb["mig_i"][:nm])
+            assert torch.equal(va["gh_f"][:ng], vb["gh_f"][:ng]) and torch.equal(va["gh_i"][:ng], vb["gh_i"][:ng])
+        # self-exchange: what went down comes back from above and vice versa; second round: pretend
+        # that fewer particles arrive than left, so that rows from the tail must fill holes
+        for s in (slab, twin):
+            s.recv_up.copy_(s.send_lo)
+            s.recv_lo.copy_(s.send_up)
+        h = [message_views(twin.recv_lo, twin.msg_layout, F)["header"],
+             message_views(twin.recv_up, twin.msg_layout, F)["header"]]
+        a_lo, a_up = int(h[0][0]), int(h[1][0])
+        if arrivals_fewer:
+            a_lo, a_up = a_lo // 3, a_up // 2
+        counts = (slab.n_own, a_lo, a_up, k_lo, k_up, int(h[0][1]), int(h[1][1]))
+        slab.engine.unpack(slab, counts)
+        ref.unpack(twin, counts)
+        torch.cuda.synchronize()
+        n_new = slab.n_own - k_lo - k_up + a_lo + a_up
+        tot = n_new + k_lo + k_up + counts[5] + counts[6]
+        assert tot <= slab.cap
+        for k in slab.buf:
+            assert torch.equal(slab.buf[k][:tot].cpu(), twin.buf[k][:tot]), (k, arrivals_fewer)
+        slab.n_own = twin.n_own = n_new

@@ -1,7 +1,8 @@
 """Slab decomposition (jaxdem_b200/slab.py) on CPU: world_size-2 and -3 ``gloo`` groups.
 
-The host logic under test — cell-layer ownership, migration, halo exchange, in-place
-re-packing — is device-agnostic torch code.  The per-rank compute hooks are played by the
+The host logic under test — slab layout, message protocol, capacity and count book-keeping —
+is device-agnostic; the exchange kernels are played by a numpy/torch restatement on the same
+message layout.  The per-rank compute hooks are played by the
 numpy oracle here (an *engine* plugged in by this test; the product engine is CUDA-only), so
 the decomposed trajectory can be compared with the oracle's single-system trajectory:
 identical particle sets per slab, forces / velocities / positions to rounding."""
@@ -94,9 +95,6 @@ class OracleEngine:
         stay = inside | stray
         halo_lo, halo_up = inside & (layer < lo + R), inside & (layer >= up - R)
         nz = lambda m: torch.nonzero(m).flatten()
-        si = nz(stay)
-        for k in (*ROW_FLOAT_FIELDS, "gid", "mat_id", "fixed"):
-            slab.alt[k][:si.numel()] = b[k][si]
         kept = message_views(slab.kept, slab.kept_layout, slab.dtype)
         for msg, mi, hi, koff in ((slab.send_lo, nz(leave_lo), nz(halo_lo), 0),
                                   (slab.send_up, nz(leave_up), nz(halo_up), slab.migrant_cap)):
@@ -109,39 +107,52 @@ class OracleEngine:
             v["header"][:3] = torch.tensor([mi.numel(), hi.numel(), int(stray.sum())])
             kept["gh_f"][koff:koff + cm] = self._cat(b, mi[:cm], GHOST_FLOAT_FIELDS, slab.widths)
             kept["gh_i"][koff:koff + cm] = torch.stack([b["gid"][mi[:cm]], b["mat_id"][mi[:cm]].long()], 1)
-        slab.header_local[:4] = torch.tensor([si.numel(), int(leave_lo.sum()), int(leave_up.sum()), int(stray.sum())])
+            slab.holes[koff:koff + cm] = mi[:cm].to(torch.int32)
+        slab.header_local[:4] = torch.tensor([int(stay.sum()), int(leave_lo.sum()), int(leave_up.sum()),
+                                              int(stray.sum())])
 
     def unpack(self, slab, counts):
         from jaxdem_b200.slab import GHOST_FLOAT_FIELDS, ROW_FLOAT_FIELDS, message_views
-        n_stay, a_lo, a_up, k_lo, k_up, g_lo, g_up = counts
+        n_old, a_lo, a_up, k_lo, k_up, g_lo, g_up = counts
         lo = message_views(slab.recv_lo, slab.msg_layout, slab.dtype)
         up = message_views(slab.recv_up, slab.msg_layout, slab.dtype)
         kp = message_views(slab.kept, slab.kept_layout, slab.dtype)
-        d, w = slab.alt, slab.widths
-        row = n_stay
+        d, w, cm = slab.buf, slab.widths, slab.migrant_cap
+        l, a = k_lo + k_up, a_lo + a_up
+        holes = torch.sort(torch.cat([slab.holes[:k_lo], slab.holes[cm:cm + k_up]]).long()).values
+        slab.holes[2 * cm:2 * cm + l] = holes.to(torch.int32)
+        n_new = n_old - l + a
+        names = (*ROW_FLOAT_FIELDS, "gid", "mat_id", "fixed")
+        if l > a:  # rows of the tail that are not holes move, in order, into the holes below n_new
+            rest = holes[a:]
+            tail = torch.arange(n_new, n_old)
+            movers = tail[~torch.isin(tail, rest)]
+            low = rest[:movers.numel()]
+            assert movers.numel() == int((rest < n_new).sum())
+            for k in names:
+                d[k][low] = d[k][movers]
 
-        def put(fields, f, iv, cnt, full):
-            nonlocal row
+        def put(fields, f, iv, rows, full):
             c = 0
-            sl = slice(row, row + cnt)
+            cnt = rows.numel()
             for k in fields:
-                d[k][sl] = f[:cnt, c:c + w[k]].reshape(d[k][sl].shape)
+                d[k][rows] = f[:cnt, c:c + w[k]].reshape(cnt, *d[k].shape[1:])
                 c += w[k]
-            d["gid"][sl] = iv[:cnt, 0]
-            d["mat_id"][sl] = iv[:cnt, 1].to(d["mat_id"].dtype)
-            d["fixed"][sl] = iv[:cnt, 2].bool() if full else False
+            d["gid"][rows] = iv[:cnt, 0]
+            d["mat_id"][rows] = iv[:cnt, 1].to(d["mat_id"].dtype)
+            d["fixed"][rows] = iv[:cnt, 2].bool() if full else False
             if not full:
                 for k, val in (("force", 0), ("torque", 0), ("inertia", 1), ("q_w", 1), ("q_xyz", 0)):
-                    d[k][sl] = val
-            row += cnt
+                    d[k][rows] = val
 
-        put(ROW_FLOAT_FIELDS, lo["mig_f"], lo["mig_i"], a_lo, True)
-        put(ROW_FLOAT_FIELDS, up["mig_f"], up["mig_i"], a_up, True)
-        cm = slab.migrant_cap
-        put(GHOST_FLOAT_FIELDS, kp["gh_f"], kp["gh_i"], k_lo, False)
-        put(GHOST_FLOAT_FIELDS, kp["gh_f"][cm:], kp["gh_i"][cm:], k_up, False)
-        put(GHOST_FLOAT_FIELDS, lo["gh_f"], lo["gh_i"], g_lo, False)
-        put(GHOST_FLOAT_FIELDS, up["gh_f"], up["gh_i"], g_up, False)
+        dst = torch.cat([holes[:min(a, l)], torch.arange(n_old, n_old + max(a - l, 0))])
+        put(ROW_FLOAT_FIELDS, lo["mig_f"], lo["mig_i"], dst[:a_lo], True)
+        put(ROW_FLOAT_FIELDS, up["mig_f"], up["mig_i"], dst[a_lo:], True)
+        row = n_new
+        for f, iv, cnt in ((kp["gh_f"], kp["gh_i"], k_lo), (kp["gh_f"][cm:], kp["gh_i"][cm:], k_up),
+                           (lo["gh_f"], lo["gh_i"], g_lo), (up["gh_f"], up["gh_i"], g_up)):
+            put(GHOST_FLOAT_FIELDS, f, iv, torch.arange(row, row + cnt), False)
+            row += cnt
 
 
 def _free_port():
