@@ -212,6 +212,15 @@ JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const j
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
                        const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps);
 
+/* collider.compute_force -> force_manager.apply -> linear_integrator.step_after_force in one
+ * call for sphere systems (clumps == 0) with velocity Verlet and no rotation integrator: the
+ * tail of _step_once (system.py:75-80) behind a point where the caller has to intervene
+ * between the drift and the force evaluation (the slab exchange below).  Same arithmetic per
+ * particle as the three hooks in sequence (the pair kernel's epilogue applies the manager and
+ * the kick to the particle it owns).  JDB200_EINVAL for other configurations. */
+JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                                const jdb200_system* sys, void* ws, size_t ws_bytes);
+
 /* ---- slab decomposition: the per-step neighbour exchange ----------------------------- */
 /* No reference equivalent (the reference runs one system on one device,
  * jaxdem/system.py:60-98); SURVEY.md 8(e).  One periodic sphere system is cut into slabs of

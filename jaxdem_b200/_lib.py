@@ -87,6 +87,7 @@ SYMBOLS = {
     "jdb200_rotation_step_after_force": (C.c_int, [_V, _PP, _PS, _PY]),
     "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
+    "jdb200_celllist_force_step_after": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_slab_message_bytes": (_SZ, [_PD]),
     "jdb200_slab_kept_bytes": (_SZ, [_PD]),
     "jdb200_slab_scratch_bytes": (_SZ, [_PD]),

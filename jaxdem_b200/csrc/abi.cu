@@ -314,6 +314,26 @@ JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const j
   JDB_DISPATCH(domain_apply<F>(s, c))
 }
 
+JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                                const jdb200_system* sys, void* ws, size_t ws_bytes) {
+  JDB_ENTER(true)
+  if (p->clumps || p->linear_integrator != JDB200_LIN_VERLET || p->rotation_integrator != JDB200_ROT_NONE)
+    return JDB200_EINVAL;
+  if (p->dtype == JDB200_F32) {
+    using F = float;
+    Ctx<F> c;
+    make_ctx<F>(c, p, st, sys, ws);
+    c.fused = 1;
+    return celllist_force<F>(s, c, 4, false, true);
+  } else {
+    using F = double;
+    Ctx<F> c;
+    make_ctx<F>(c, p, st, sys, ws);
+    c.fused = 1;
+    return celllist_force<F>(s, c, 4, false, true);
+  }
+}
+
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
                        const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps) {
   JDB_ENTER(true)

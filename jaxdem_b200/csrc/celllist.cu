@@ -144,6 +144,9 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 //           (vx, vy, vz, mass) shadow record instead of State.vel (the pair kernel's epilogue
 //           writes the final velocity), and the external buffers / fixed flags are scanned
 //           so that epilogue knows whether it has to gather them at all
+//   MODE 4  slab driver: the drift was done before the neighbour exchange; hash only, but
+//           with the shadow record and the scans of MODE 3, so that the pair kernel's fused
+//           epilogue (force manager + step_after_force) can follow
 // EXT: the force manager reads and clears the external buffers (first application
 // after the call was entered); otherwise they are known to be zero.
 // References: velocity_verlet.py:57-61,92-95; force_manager.py:359-423;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       fixed = c.fixed[gidx] != 0;
     }
     for (int w = 0; w < c.W; ++w) bond |= c.bond_id[gidx * c.W + w] >= 0;
-    if (MODE == 3) {
+    if (MODE == 3 || MODE == 4) {
       fixed_any = fixed;
 #pragma unroll
       for (int d = 0; d < D; ++d)
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       box[d] = c.box[b * D + d];
     }
     // ---- arithmetic ----
-    if (MODE != 0) {
+    if (MODE != 0 && MODE != 4) {
       const F sc = T::div(T::mul(dt, F(0.5)), mass);  // dt * 0.5 / mass
       const F free = fixed ? F(0) : F(1);
 #pragma unroll
@@ -234,14 +237,14 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     }
     const I key = (I)h;
     // ---- stores ----
-    if (MODE != 0) {
+    if (MODE != 0 && MODE != 4) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         if (MODE != 3) c.vel[gidx * D + d] = v[d];
         c.pos_c[gidx * D + d] = pc[d];
       }
     }
-    if (MODE == 3) c.uvel[gidx] = Vec4<F>{v[0], v[1], v[2], mass};
+    if (MODE == 3 || MODE == 4) c.uvel[gidx] = Vec4<F>{v[0], v[1], v[2], mass};
     if (MODE == 2 && EXT) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   if (__any_sync(0xffffffffu, bond) && (threadIdx.x & 31) == 0) c.gi[b].any_bond = 1;
   if (__any_sync(0xffffffffu, ppr_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ppr = 1;
   if (__any_sync(0xffffffffu, edge) && (threadIdx.x & 31) == 0) c.gi[b].edge = 1;
-  if (MODE == 3) {
+  if (MODE == 3 || MODE == 4) {
     if (__any_sync(0xffffffffu, ext_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ext = 1;
     if (__any_sync(0xffffffffu, fixed_any) && (threadIdx.x & 31) == 0) c.gi[b].any_fixed = 1;
   }
@@ -550,6 +553,7 @@ static int launch_hash(cudaStream_t s, Ctx<F>& c, const F* cso, int mode, bool e
   if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0, false>), grid, 256, s, c, cso);
   else if (mode == 1) JDB_LAUNCH((k_hash<F, D, 1, false>), grid, 256, s, c, cso);
   else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3, false>), grid, 256, s, c, cso);
+  else if (mode == 4) JDB_LAUNCH((k_hash<F, D, 4, false>), grid, 256, s, c, cso);
   else if (ext) JDB_LAUNCH((k_hash<F, D, 2, true>), grid, 256, s, c, cso);
   else JDB_LAUNCH((k_hash<F, D, 2, false>), grid, 256, s, c, cso);
   return 0;

@@ -117,22 +117,76 @@ class CudaEngine:
     def __init__(self, system):
         self.system = system
         self._scratch = None
+        self._bound = None
+
+    # The row buffers never move (the exchange works in place), so the C-ABI argument structs are
+    # filled ONCE; per call only the row count changes.  This keeps the host side of a step at a few
+    # microseconds per hook instead of rebuilding ~40 ctypes fields from Python objects every time.
+    def bind(self, slab):
+        import ctypes as C
+        from . import _call, _lib as L
+        full = slab.view(slab.cap)
+        p = _call.params_for(full, self.system)
+        ws = _call.workspace(p, slab.device)
+        sy = self.system
+        # collider + force manager + after-kick in ONE call when the configuration allows it
+        self._fuse_after = (sy.linear_integrator.native_kind == "verlet" and not sy.rotation_integrator.native_kind
+                            and sy.domain.native_kind == "periodic")
+        self._bound = dict(p=p, sv=_call.state_view(full), yv=_call.system_view(self.system), ws=ws, lib=L.lib(),
+                           keep=full, dev=slab.device, C=C, check=L.check, stream=_call.stream_ptr)
+
+    def _hook(self, name, n, ws=True):
+        b = self._bound
+        C = b["C"]
+        b["p"].n = int(n)
+        args = [b["stream"](b["dev"]), C.byref(b["p"]), C.byref(b["sv"]), C.byref(b["yv"])]
+        if ws:
+            args += [C.c_void_p(b["ws"].data_ptr()), C.c_size_t(b["ws"].numel())]
+        b["check"](getattr(b["lib"], name)(*args), name)
 
     def before_force(self, state):
         sy = self.system
-        sy.domain.apply(state, sy)
+        if self._bound is None or sy.domain.native_kind != "periodic":
+            sy.domain.apply(state, sy)
+            torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
+            sy.linear_integrator.step_before_force(state, sy)
+            sy.rotation_integrator.step_before_force(state, sy)
+            return
+        n = state if isinstance(state, int) else state.N
         torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
-        sy.linear_integrator.step_before_force(state, sy)
-        sy.rotation_integrator.step_before_force(state, sy)
+        if sy.linear_integrator.native_kind:
+            self._hook("jdb200_linear_step_before_force", n, ws=False)
+        if sy.rotation_integrator.native_kind:
+            self._hook("jdb200_rotation_step_before_force", n, ws=False)
 
     def compute_force(self, state):
-        self.system.collider.compute_force(state, self.system)
+        if self._bound is None:
+            self.system.collider.compute_force(state, self.system)
+            return
+        self._hook("jdb200_celllist_compute_force", state if isinstance(state, int) else state.N)
+
+    def force_and_after(self, n_local: int, n_own: int):
+        """collider.compute_force on owned + ghost rows, then force manager + after-force hooks on
+        the owned rows; one fused call for sphere / Verlet / no-rotation systems."""
+        if self._bound is not None and self._fuse_after:
+            self._hook("jdb200_celllist_force_step_after", n_local)
+        else:
+            self.compute_force(n_local)
+            self.after_force(n_own)
 
     def after_force(self, state):
         sy = self.system
-        sy.force_manager.apply(state, sy)
-        sy.linear_integrator.step_after_force(state, sy)
-        sy.rotation_integrator.step_after_force(state, sy)
+        if self._bound is None:
+            sy.force_manager.apply(state, sy)
+            sy.linear_integrator.step_after_force(state, sy)
+            sy.rotation_integrator.step_after_force(state, sy)
+            return
+        n = state if isinstance(state, int) else state.N
+        self._hook("jdb200_force_manager_apply", n)
+        if sy.linear_integrator.native_kind:
+            self._hook("jdb200_linear_step_after_force", n, ws=False)
+        if sy.rotation_integrator.native_kind:
+            self._hook("jdb200_rotation_step_after_force", n, ws=False)
 
     # -- exchange kernels (csrc/slab.cu) -----------------------------------------
     def _desc(self, slab, n):
@@ -158,32 +212,40 @@ class CudaEngine:
             setattr(r, k, bufs[k].data_ptr())
         return r
 
-    def pack(self, slab):
+    def _exchange_args(self, slab):
+        """SlabDesc / SlabRows / scratch, built once per message capacity (pointers are stable)."""
         import ctypes as C
-        from . import _call, _lib as L
-        lib = L.lib()
-        d = self._desc(slab, slab.n_own)
-        need = lib.jdb200_slab_scratch_bytes(C.byref(d))
-        if self._scratch is None or self._scratch.numel() < need:
-            dcap = self._desc(slab, slab.cap)
-            self._scratch = torch.empty(lib.jdb200_slab_scratch_bytes(C.byref(dcap)), dtype=torch.uint8,
-                                        device=slab.device)
-        rows = self._rows(slab.buf)
-        L.check(lib.jdb200_slab_pack(_call.stream_ptr(slab.device), C.byref(d), C.byref(rows),
-                                     slab.send_lo.data_ptr(), slab.send_up.data_ptr(), slab.kept.data_ptr(),
-                                     slab.holes.data_ptr(), slab.header_local.data_ptr(), self._scratch.data_ptr(),
-                                     self._scratch.numel()), "jdb200_slab_pack")
+        from . import _lib as L
+        key = (slab.migrant_cap, slab.ghost_cap, slab.kept.data_ptr())
+        ex = getattr(self, "_ex", None)
+        if ex is None or ex["key"] != key:
+            lib = L.lib()
+            d = self._desc(slab, slab.cap)
+            if self._scratch is None:
+                self._scratch = torch.empty(lib.jdb200_slab_scratch_bytes(C.byref(d)), dtype=torch.uint8,
+                                            device=slab.device)
+            ex = self._ex = dict(key=key, d=d, rows=self._rows(slab.buf), lib=lib, C=C, check=L.check)
+        return ex
+
+    def pack(self, slab):
+        from . import _call
+        ex = self._exchange_args(slab)
+        C = ex["C"]
+        ex["d"].n = int(slab.n_own)
+        ex["check"](ex["lib"].jdb200_slab_pack(
+            _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), slab.send_ptr("lo"),
+            slab.send_ptr("up"), slab.kept.data_ptr(), slab.holes.data_ptr(), slab.header_local.data_ptr(),
+            self._scratch.data_ptr(), self._scratch.numel()), "jdb200_slab_pack")
 
     def unpack(self, slab, counts):
-        import ctypes as C
-        from . import _call, _lib as L
-        d = self._desc(slab, slab.n_own)
-        rows = self._rows(slab.buf)
+        from . import _call
+        ex = self._exchange_args(slab)
+        C = ex["C"]
+        ex["d"].n = int(slab.n_own)
         arr = (C.c_int64 * 7)(*[int(c) for c in counts])
-        L.check(L.lib().jdb200_slab_unpack(_call.stream_ptr(slab.device), C.byref(d), C.byref(rows), arr,
-                                           slab.recv_lo.data_ptr(), slab.recv_up.data_ptr(), slab.kept.data_ptr(),
-                                           slab.holes.data_ptr()),
-                "jdb200_slab_unpack")
+        ex["check"](ex["lib"].jdb200_slab_unpack(
+            _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), arr, slab.recv_lo.data_ptr(),
+            slab.recv_up.data_ptr(), slab.kept.data_ptr(), slab.holes.data_ptr()), "jdb200_slab_unpack")
 
 
 class SlabSystem:
@@ -191,9 +253,15 @@ class SlabSystem:
     first n rows as a ``State`` whose tensors alias the buffers (the C ABI works in place)."""
 
     def __init__(self, *, dim, dtype, device, capacity, box, anchor, n_layers, search_range, group=None,
-                 ghost_capacity=None, migrant_capacity=None):
+                 ghost_capacity=None, migrant_capacity=None, transport="auto"):
         self.dim, self.dtype, self.device = dim, dtype, torch.device(device)
         self.group = group
+        # "peer": the pack kernels store the messages straight into the neighbours' receive buffers
+        # (symmetric memory over NVLink, one device-side barrier per step, no NCCL call);
+        # "sendrecv": torch.distributed point-to-point (NCCL / gloo).  "auto": peer on CUDA when available.
+        self.transport = transport
+        self._symm = None
+        self._parity = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.layout = SlabLayout(int(n_layers), self.world, int(search_range))
@@ -237,17 +305,53 @@ class SlabSystem:
                             int(migrant_capacity or max(256, self.cap // 16)))
 
     def set_capacities(self, ghost_cap: int, migrant_cap: int) -> None:
-        """(Re)allocate the exchange messages: every rank must use the same capacities."""
+        """(Re)allocate the exchange messages: collective, every rank must use the same capacities."""
         self.ghost_cap, self.migrant_cap = int(ghost_cap), int(migrant_cap)
         fb = torch.empty((), dtype=self.dtype).element_size()
         self.msg_layout = message_layout(self.dim, fb, self.migrant_cap, self.ghost_cap)
         self.kept_layout = message_layout(self.dim, fb, 0, 2 * self.migrant_cap)
         mk = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-        self.send_lo, self.send_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
-        self.recv_lo, self.recv_up = mk(self.msg_layout["bytes"]), mk(self.msg_layout["bytes"])
+        nb = self.msg_layout["bytes"]
+        self._symm = None
+        if self.world > 1 and self.device.type == "cuda" and self.transport in ("auto", "peer"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                grp = self.group if self.group is not None else dist.group.WORLD
+                # [parity][lower / upper] receive buffers; the parity alternates every exchange so a
+                # neighbour never overwrites a message this rank may still be unpacking
+                pool = symm.empty(4 * nb, dtype=torch.uint8, device=self.device)
+                pool.zero_()
+                hdl = symm.rendezvous(pool, grp.group_name)
+                self._symm = dict(pool=pool, hdl=hdl, ptrs=list(hdl.buffer_ptrs), nb=nb)
+            except Exception:
+                if self.transport == "peer":
+                    raise
+                self._symm = None
+        if self._symm is None:
+            self.send_lo, self.send_up = mk(nb), mk(nb)
+            self.recv_lo, self.recv_up = mk(nb), mk(nb)
+        else:
+            self._select_parity()
         self.kept = mk(self.kept_layout["bytes"])
         # row indices of the leavers: [0, cap_m) downwards, [cap_m, 2 cap_m) upwards, [2 cap_m, 4 cap_m) merged
         self.holes = torch.zeros(4 * self.migrant_cap + 16, dtype=torch.int32, device=self.device)
+
+    def _select_parity(self) -> None:
+        sm, p = self._symm, self._parity
+        nb = sm["nb"]
+        self.recv_lo = sm["pool"][(2 * p) * nb:(2 * p + 1) * nb]
+        self.recv_up = sm["pool"][(2 * p + 1) * nb:(2 * p + 2) * nb]
+
+    def send_ptr(self, face: str) -> int:
+        """Where the pack kernels write the message for the lower / upper neighbour: a local send
+        buffer, or — peer transport — the neighbour's receive buffer itself (what goes down arrives
+        from above, and vice versa)."""
+        if self._symm is None:
+            return (self.send_lo if face == "lo" else self.send_up).data_ptr()
+        sm, p = self._symm, self._parity
+        if face == "lo":
+            return sm["ptrs"][self.lo_rank] + (2 * p + 1) * sm["nb"]
+        return sm["ptrs"][self.up_rank] + (2 * p) * sm["nb"]
 
     def tune_capacities(self, slack: float = 2.0) -> None:
         """Shrink the messages to ``slack`` x the counts of one trial exchange (collective)."""
@@ -307,15 +411,21 @@ class SlabSystem:
         if self.world == 1:
             self.n_ghost = 0
             return
-        self.engine.pack(self)  # leavers / halo rows -> messages, leavers' rows -> holes, counts -> headers
-        # sends in (lower, upper) order, receives in (upper, lower) order: with two ranks both
-        # messages travel between the same pair and are matched in posting order
-        ops = [dist.P2POp(dist.isend, self.send_lo, self.lo_rank, group=self.group),
-               dist.P2POp(dist.isend, self.send_up, self.up_rank, group=self.group),
-               dist.P2POp(dist.irecv, self.recv_up, self.up_rank, group=self.group),
-               dist.P2POp(dist.irecv, self.recv_lo, self.lo_rank, group=self.group)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+        if self._symm is not None:
+            self._select_parity()
+            self.engine.pack(self)  # messages are stored straight into the neighbours' receive buffers
+            self._symm["hdl"].barrier(channel=0)  # device-side: every rank's messages have landed
+            self._parity ^= 1
+        else:
+            self.engine.pack(self)  # leavers / halo rows -> messages, leavers' rows -> holes, counts -> headers
+            # sends in (lower, upper) order, receives in (upper, lower) order: with two ranks both
+            # messages travel between the same pair and are matched in posting order
+            ops = [dist.P2POp(dist.isend, self.send_lo, self.lo_rank, group=self.group),
+                   dist.P2POp(dist.isend, self.send_up, self.up_rank, group=self.group),
+                   dist.P2POp(dist.irecv, self.recv_up, self.up_rank, group=self.group),
+                   dist.P2POp(dist.irecv, self.recv_lo, self.lo_rank, group=self.group)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
         # ---- the one host synchronisation of the step: the counts (they are launch parameters) ----
         hh = self._host_headers
         hh[0].copy_(self.header_local, non_blocking=True)
@@ -345,11 +455,16 @@ class SlabSystem:
     def step(self, n: int = 1) -> None:
         """n x _step_once (system.py:60-82) on the decomposed system."""
         eng = self.engine
+        rows = (lambda k: k) if getattr(eng, "_bound", None) is not None else self.view
+        fused = getattr(eng, "_bound", None) is not None
         for _ in range(int(n)):
-            eng.before_force(self.view(self.n_own))
+            eng.before_force(rows(self.n_own))
             self.exchange()
-            eng.compute_force(self.view(self.n_own + self.n_ghost))
-            eng.after_force(self.view(self.n_own))
+            if fused:
+                eng.force_and_after(self.n_own + self.n_ghost, self.n_own)
+            else:
+                eng.compute_force(rows(self.n_own + self.n_ghost))
+                eng.after_force(rows(self.n_own))
             self.steps_done += 1
 
     def compute_force(self) -> None:
@@ -377,7 +492,7 @@ class SlabSystem:
 def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_model_type="spring",
                        linear_integrator_type="verlet", rotation_integrator_type="verletspiral", mat_table=None,
                        gravity=None, dtype=torch.float32, device=None, group=None, capacity_factor=1.6,
-                       cell_size=None):
+                       cell_size=None, transport="auto"):
     """Build the rank-local ``SlabSystem`` + the native ``System`` it drives (CUDA).  ``arrays`` is
     the GLOBAL particle set (same on every rank; numpy, keys as ``State.create``)."""
     from . import System  # local import: jaxdem_b200.__init__ imports this module
@@ -401,7 +516,7 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
     R = int(col.neighbor_mask.abs().max())
     cap = int(math.ceil(capacity_factor * n / world)) + 1024
     slab = SlabSystem(dim=dim, dtype=dtype, device=dev, capacity=cap, box=box, anchor=anc,
-                      n_layers=int(gd[-1]), search_range=R, group=group)
+                      n_layers=int(gd[-1]), search_range=R, group=group, transport=transport)
     slab.load_global(arrays)
     system = System.create((cap, dim), dt=dt, linear_integrator_type=linear_integrator_type,
                            rotation_integrator_type=rotation_integrator_type, collider=col,
@@ -411,4 +526,5 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
     slab.engine = CudaEngine(system)
     slab.system = system
     slab.tune_capacities()
+    slab.engine.bind(slab)
     return slab

@@ -25,6 +25,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     law = sys.argv[3] if len(sys.argv) > 3 else "spring"
+    transport = sys.argv[4] if len(sys.argv) > 4 else "auto"
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -42,7 +43,8 @@ def main():
         mt = jd.MaterialTable.from_materials(mats, matcher=jd.MaterialMatchmaker.create("harmonic"))
     arrays = dict(pos=wl["pos"], vel=wl["vel"], ang_vel=wl["ang_vel"], rad=wl["rad"], mass=wl["mass"])
     slab = create_slab_system(arrays, box_size=wl["box"], dt=1e-3, force_model_type=law,
-                              rotation_integrator_type=rot, mat_table=mt, dtype=torch.float32, device=dev)
+                              rotation_integrator_type=rot, mat_table=mt, dtype=torch.float32, device=dev,
+                              transport=transport)
     slab.compute_force()
     slab.step(steps)
     torch.cuda.synchronize()
@@ -69,6 +71,7 @@ def main():
             print(f"[slab] {f}: max |diff| {err:.3e} (scale {scale:.3e})")
             ok &= err <= tol
         moved = float(np.abs(res["pos_c"][:, 2] - wl["pos"][:, 2]).max())
+        print(f"[slab] transport {'peer memory' if slab._symm is not None else 'send/recv'}")
         print(f"[slab] world {world}, n {n}, steps {steps}, law {law}: max z displacement {moved:.3f}, "
               f"owned on rank 0: {slab.n_own}, ghosts: {slab.n_ghost}")
         print("SLAB-OK" if ok else "SLAB-MISMATCH")

@@ -433,12 +433,13 @@ def test_slab_system_single_rank(law):
     _run_slab_worker(1, 60000, 8, law)
 
 
-@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
-def test_slab_system_two_gpus(law):
-    """Two slabs over NCCL against the single-GPU trajectory (skipped on 1-GPU boxes)."""
+@pytest.mark.parametrize("law,transport", [("spring", "peer"), ("cundallstrack", "peer"), ("spring", "sendrecv")])
+def test_slab_system_two_gpus(law, transport):
+    """Two slabs against the single-GPU trajectory (skipped on 1-GPU boxes): messages stored
+    straight into the neighbour's memory over NVLink ("peer"), or NCCL send/recv."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    _run_slab_worker(2, 200000, 10, law)
+    _run_slab_worker(2, 200000, 10, law, transport)
 
 
 @pytest.mark.parametrize("dtype", DT)
