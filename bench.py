@@ -187,7 +187,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = make_workload(packing=args.packing)
+    wl = make_workload(n=args.n_per_gpu, packing=args.packing)
     n = wl["pos"].shape[0]
     jr = try_jax_reference(wl, max(1, min(args.steps, 20)))
     if jr is not None:
@@ -258,7 +258,7 @@ def run_cuda(args):
 
     if world > 1 and args.mode == "slab":
         return run_cuda_slab(args, world, rank, local, dev)
-    wl = make_workload(seed=1 + rank, packing=args.packing)
+    wl = make_workload(n=args.n_per_gpu, seed=1 + rank, packing=args.packing)
     n = wl["pos"].shape[0]
     st = jd.State.create(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=torch.float32, device=dev)
     sy = jd.System.create(st.shape, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
@@ -421,12 +421,18 @@ def run_cuda_slab(args, world, rank, local, dev):
     from jaxdem_b200.slab import create_slab_system
 
     lib = _lib.lib()
-    wl = make_workload(seed=1, packing=args.packing, stack=world)
-    n_total = wl["pos"].shape[0]
-    n = n_total // world
+    # every rank generates the C2 cube of its own slab (seed 1 + rank) and shifts it to its place in
+    # the stack; rows that fall into a neighbour's boundary layer migrate in the first exchange
+    n = args.n_per_gpu
+    wl = make_workload(n=n, seed=1 + rank, packing=args.packing)
+    L = float(wl["box"][0])
+    wl["pos"][:, 2] += np.float32(rank * L)
+    box = np.array([L, L, L * world], dtype=np.float32)
+    n_total = n * world
     slab = create_slab_system(dict(pos=wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"]),
-                              box_size=wl["box"], dt=1e-3, force_model_type="spring",
-                              rotation_integrator_type="", dtype=torch.float32, device=dev, capacity_factor=1.35)
+                              box_size=box, dt=1e-3, force_model_type="spring", rotation_integrator_type="",
+                              dtype=torch.float32, device=dev, capacity_factor=1.35,
+                              local_gid=rank * n + np.arange(n), n_total=n_total, rad_range=(0.5, 0.5))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -542,6 +548,8 @@ def main():
     ap.add_argument("--packing", default="grid", choices=["grid", "random"])
     ap.add_argument("--mode", default="slab", choices=["slab", "replicas"],
                     help="N > 1 GPUs: one slab-decomposed system of N x 2^20 spheres (default) or N independent replicas")
+    ap.add_argument("--n-per-gpu", type=int, default=N_PARTICLES,
+                    help="spheres per GPU (default 2**20 = BASELINE config 2; 2**23 x 8 GPUs = the 64M system of config 3)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (System.compile_step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=10)

@@ -396,6 +396,30 @@ class SlabSystem:
             self.buf["fixed"][:m] = torch.as_tensor(np.asarray(arrays["fixed"])[mine], dtype=torch.bool).to(self.device)
         self.n_own, self.n_ghost = m, 0
 
+    def load_local(self, arrays: dict, gid) -> None:
+        """Take rows this rank generated itself (they should lie in or next to its slab: rows that
+        belong to a neighbour migrate in the first exchange) with their global ids."""
+        pos = np.asarray(arrays["pos"])
+        m, dim = pos.shape
+        if m > self.cap:
+            raise RuntimeError(f"rank {self.rank}: {m} particles exceed the capacity {self.cap}")
+        A = _A(dim)
+        rad = np.asarray(arrays.get("rad", np.ones(m)))
+        mass = np.asarray(arrays.get("mass", np.ones(m)))
+        coeff = 0.5 if dim == 2 else 0.4
+        vals = dict(pos_c=pos, vel=arrays.get("vel", np.zeros((m, dim))), ang_vel=arrays.get("ang_vel", np.zeros((m, A))),
+                    rad=rad, mass=mass, inertia=arrays.get("inertia", (coeff * mass * rad**2)[:, None] * np.ones((1, A))))
+        for k, v in vals.items():
+            t = torch.as_tensor(np.asarray(v)).to(self.dtype)
+            self.buf[k][:m] = t.reshape(self.buf[k][:m].shape).to(self.device)
+        for k in ("force", "torque", "q_xyz"):
+            self.buf[k][:m] = 0
+        self.buf["q_w"][:m] = 1
+        self.buf["gid"][:m] = torch.as_tensor(np.asarray(gid), dtype=torch.int64).to(self.device)
+        self.buf["mat_id"][:m] = 0
+        self.buf["fixed"][:m] = False
+        self.n_own, self.n_ghost = m, 0
+
     def view(self, n: int) -> State:
         b, s = self.buf, self.static
         return State(
@@ -492,9 +516,11 @@ class SlabSystem:
 def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_model_type="spring",
                        linear_integrator_type="verlet", rotation_integrator_type="verletspiral", mat_table=None,
                        gravity=None, dtype=torch.float32, device=None, group=None, capacity_factor=1.6,
-                       cell_size=None, transport="auto"):
+                       cell_size=None, transport="auto", local_gid=None, n_total=None, rad_range=None):
     """Build the rank-local ``SlabSystem`` + the native ``System`` it drives (CUDA).  ``arrays`` is
-    the GLOBAL particle set (same on every rank; numpy, keys as ``State.create``)."""
+    the GLOBAL particle set (same on every rank; numpy, keys as ``State.create``) — or, with
+    ``local_gid`` (global ids of the rows), ``n_total`` and ``rad_range`` = (min, max) radius of
+    the whole system, only the rows this rank generated for its own slab."""
     from . import System  # local import: jaxdem_b200.__init__ imports this module
     from .components import Collider
     from .state import default_device
@@ -502,12 +528,15 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
     dev = torch.device(device) if device is not None else default_device()
     pos = np.asarray(arrays["pos"])
     n, dim = pos.shape
+    if local_gid is not None:
+        n = int(n_total)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     box = np.asarray(box_size, dtype=np.float64)
     anc = np.zeros(dim) if anchor is None else np.asarray(anchor, dtype=np.float64)
     # the collider is configured from the GLOBAL radii, identically on every rank
     rad = np.asarray(arrays.get("rad", np.ones(n)))
-    probe = State.create(np.zeros((2, dim)), rad=[rad.min(), rad.max()], dtype=dtype, device="cpu")
+    rmin, rmax = (rad.min(), rad.max()) if rad_range is None else rad_range
+    probe = State.create(np.zeros((2, dim)), rad=[rmin, rmax], dtype=dtype, device="cpu")
     col = Collider.create("CellList", state=probe, cell_size=cell_size)
     F = dtype
     cs = torch.as_tensor(col.cell_size, dtype=F)
@@ -517,7 +546,10 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
     cap = int(math.ceil(capacity_factor * n / world)) + 1024
     slab = SlabSystem(dim=dim, dtype=dtype, device=dev, capacity=cap, box=box, anchor=anc,
                       n_layers=int(gd[-1]), search_range=R, group=group, transport=transport)
-    slab.load_global(arrays)
+    if local_gid is None:
+        slab.load_global(arrays)
+    else:
+        slab.load_local(arrays, local_gid)
     system = System.create((cap, dim), dt=dt, linear_integrator_type=linear_integrator_type,
                            rotation_integrator_type=rotation_integrator_type, collider=col,
                            domain_type="periodic", domain_kw=dict(box_size=box, anchor=anc),
