@@ -170,6 +170,17 @@ JDB200_API int jdb200_celllist_create_neighbor_list(void* stream, const jdb200_p
                                          void* ws, size_t ws_bytes, const void* cutoff,
                                          void* neighbor_list, void* overflow);
 
+/* DynamicCellList.create_cross_neighbor_list (colliders/cell_list.py:600-715): for every
+ * query point pos_a (B, N_A, D) the database points — the State's positions pos_c + pos_p_rot,
+ * p->n of them — within `cutoff` (B,), through the partition of the DATABASE with the cell size
+ * inflated to cover the cutoff; no clump / bond mask; rows (B, N_A, K) in stencil x sorted-run
+ * order, original database indices, -1 padded; overflow (B,) uint8.  Only pos_c, pos_p_rot and
+ * rad of `st` are read (bond_width may be 0). */
+JDB200_API int jdb200_celllist_create_cross_neighbor_list(void* stream, const jdb200_params* p,
+                                                          const jdb200_state* st, const jdb200_system* sys, void* ws,
+                                                          size_t ws_bytes, const void* pos_a, int64_t n_a,
+                                                          const void* cutoff, void* neighbor_list, void* overflow);
+
 /* NaiveSimulator.compute_force / compute_potential_energy
  * (jaxdem/colliders/naive.py:187-235, 73-113): O(N^2), the reference's default
  * collider (README config). */
@@ -251,6 +262,8 @@ typedef struct jdb200_slab_desc {
   const void* anchor;   /* (D,) F  Domain.anchor       (device) */
   const void* box_size; /* (D,) F  Domain.box_size     (device) */
   const void* cell_size;/* ()   F  DynamicCellList.cell_size (device) */
+  const void* dt;       /* ()   F  System.dt (device), or NULL.  Non-NULL: jdb200_slab_pack first applies
+                           VelocityVerlet.step_before_force (velocity_verlet.py:57-61) to the owned rows */
 } jdb200_slab_desc;
 
 /* Per-particle rows of a slab (State leaves of a sphere system + the global particle id). */

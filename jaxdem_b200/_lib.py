@@ -54,7 +54,7 @@ class SlabDesc(C.Structure):
     _fields_ = [("n", C.c_int64), ("cap_mig", C.c_int64), ("cap_ghost", C.c_int64), ("dim", C.c_int32),
                 ("dtype", C.c_int32), ("n_layers", C.c_int32), ("lo_layer", C.c_int32), ("up_layer", C.c_int32),
                 ("search_range", C.c_int32), ("anchor", C.c_void_p), ("box_size", C.c_void_p),
-                ("cell_size", C.c_void_p)]
+                ("cell_size", C.c_void_p), ("dt", C.c_void_p)]
 
 
 SLAB_ROW_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "inertia", "q_w", "q_xyz", "rad", "mass",
@@ -78,6 +78,7 @@ SYMBOLS = {
     "jdb200_celllist_compute_force": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_celllist_compute_potential_energy": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V]),
     "jdb200_celllist_create_neighbor_list": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V, _V, _V]),
+    "jdb200_celllist_create_cross_neighbor_list": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V, C.c_int64, _V, _V, _V]),
     "jdb200_naive_compute_force": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_naive_compute_potential_energy": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V]),
     "jdb200_force_manager_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),

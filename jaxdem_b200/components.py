@@ -265,6 +265,35 @@ class DynamicCellList(Collider):
         return state, system, nl, ovf
 
     @staticmethod
+    def create_cross_neighbor_list(pos_a, pos_b, system, cutoff, max_neighbors: int):
+        """-> jdb200_celllist_create_cross_neighbor_list (cell_list.py:600-715): for every query
+        point of ``pos_a`` the points of ``pos_b`` within ``cutoff``.  Returns ((.., N_A, K) int
+        list of indices into pos_b, padded with -1; overflow flag)."""
+        import ctypes as C
+        pos_a, pos_b = pos_a.contiguous(), pos_b.contiguous()
+        lead = pos_b.shape[:-2]
+        n_a, n_b, F = pos_a.shape[-2], pos_b.shape[-2], pos_b.dtype
+        I = int_dtype_for(F)
+        dev = pos_b.device
+        nl = torch.full((*lead, n_a, max_neighbors), -1, dtype=I, device=dev)
+        ovf = torch.zeros(lead, dtype=torch.bool, device=dev)
+        if n_a == 0 or n_b == 0 or max_neighbors == 0:
+            return nl, ovf
+        z = lambda *s, dt=F: torch.zeros((*lead, *s), dtype=dt, device=dev)
+        from .state import Quaternion
+        A = 1 if pos_b.shape[-1] == 2 else 3
+        zi = z(n_b, dt=I)
+        db = State(pos_c=pos_b, pos_p=z(n_b, pos_b.shape[-1]), vel=pos_b, force=pos_b, q=Quaternion(z(n_b, 1), z(n_b, 3)),
+                   ang_vel=z(n_b, A), torque=z(n_b, A), rad=z(n_b), _rad=z(n_b), volume=z(n_b), mass=z(n_b),
+                   inertia=z(n_b, A), clump_id=zi, bond_id=torch.full((*lead, n_b, 1), -1, dtype=I, device=dev),
+                   mat_id=zi, species_id=zi, fixed=z(n_b, dt=torch.bool), _pos_p_rot=z(n_b, pos_b.shape[-1]),
+                   has_clumps=False)
+        cut = torch.as_tensor(cutoff, dtype=F).to(dev).expand(lead).contiguous()
+        _call.call("jdb200_celllist_create_cross_neighbor_list", db, system, pos_a, C.c_int64(n_a), cut, nl, ovf,
+                   max_neighbors=max_neighbors)
+        return nl, ovf
+
+    @staticmethod
     def partition(state, system):
         """Cell permutation, sorted hashes, de-duplicated neighbour-cell hashes and the
         strategy used (-> jdb200_celllist_partition; _get_spatial_partition,

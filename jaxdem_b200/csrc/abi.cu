@@ -39,6 +39,7 @@ template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*, int, 
 template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, int, bool, bool);
 template <typename F> int celllist_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int celllist_neighbor_list(cudaStream_t, Ctx<F>&, const F*, typename RT<F>::I*, uint8_t*);
+template <typename F> int celllist_cross_neighbor_list(cudaStream_t, Ctx<F>&, const F*, long long, const F*, typename RT<F>::I*, uint8_t*);
 template <typename F> int naive_force(cudaStream_t, Ctx<F>&);
 template <typename F> int naive_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int force_manager_apply(cudaStream_t, Ctx<F>&);
@@ -253,6 +254,17 @@ JDB200_API int jdb200_celllist_create_neighbor_list(void* stream, const jdb200_p
   if (!cutoff || !overflow || (!neighbor_list && p->max_neighbors > 0 && p->n > 0)) return JDB200_ENULL;
   JDB_DISPATCH(celllist_neighbor_list<F>(s, c, (const F*)cutoff, (RT<F>::I*)neighbor_list,
                                          (uint8_t*)overflow))
+}
+
+JDB200_API int jdb200_celllist_create_cross_neighbor_list(void* stream, const jdb200_params* p,
+                                                          const jdb200_state* st, const jdb200_system* sys, void* ws,
+                                                          size_t ws_bytes, const void* pos_a, int64_t n_a,
+                                                          const void* cutoff, void* neighbor_list, void* overflow) {
+  JDB_ENTER(true)
+  if (n_a < 0) return JDB200_EINVAL;
+  if (!cutoff || !overflow || ((!neighbor_list || !pos_a) && p->max_neighbors > 0 && n_a > 0)) return JDB200_ENULL;
+  JDB_DISPATCH(celllist_cross_neighbor_list<F>(s, c, (const F*)pos_a, (long long)n_a, (const F*)cutoff,
+                                               (RT<F>::I*)neighbor_list, (uint8_t*)overflow))
 }
 
 JDB200_API int jdb200_naive_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,

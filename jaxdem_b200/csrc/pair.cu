@@ -72,14 +72,12 @@ __device__ __forceinline__ bool pair_valid(const Ctx<F>& c, size_t off, int owne
 // row whose target cell is looked up (rows removed by the periodic de-dup are skipped;
 // the reference turns them into hash -1, which no periodic cell carries).
 template <typename F, typename Vis>
-__device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, const F* cell_size_override,
-                                             Vis& vis) {
+__device__ __forceinline__ void walk_stencil_at(const Ctx<F>& c, int b, const F* pp, const F* cell_size_override,
+                                                Vis& vis) {
   using I = typename RT<F>::I;
   const GridInfo<I> g = c.gi[b];
   const size_t off = (size_t)b * c.n;
   const bool dense = use_dense(g);
-  const Vec4<F> p = c.spos[off + k];
-  const F pp[3] = {p.x, p.y, p.z};
   const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
   I cc[3] = {0, 0, 0};
   for (int d = 0; d < c.dim; ++d)
@@ -118,6 +116,14 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
     }
     if (e > s) vis.cell(m, s, e);
   }
+}
+
+template <typename F, typename Vis>
+__device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, const F* cell_size_override,
+                                             Vis& vis) {
+  const Vec4<F> p = c.spos[(size_t)b * c.n + k];
+  const F pp[3] = {p.x, p.y, p.z};
+  walk_stencil_at<F>(c, b, pp, cell_size_override, vis);
 }
 
 // ---------------------------------------------------------------------------
@@ -919,6 +925,66 @@ __global__ void k_nl_flag(Ctx<F> c, uint8_t* __restrict__ overflow) {
   overflow[b] = (uint8_t)(c.gi[b].nl_overflow || c.gi[b].hash_overflow);
 }
 
+// create_cross_neighbor_list (cell_list.py:600-715): queries pos_a (N_A, D) against the partition
+// of the database points (the State's positions); no clump / bond mask; same chunked counting and
+// prefix-sum packing as K6, entries are original database indices.
+template <typename F>
+struct CrossVis {
+  using I = typename RT<F>::I;
+  const Ctx<F>& c;
+  const LawCtx<F>& lc;
+  size_t off;
+  Body<F> a;
+  F cutoff_sq;
+  I* row;
+  long long row_off;
+  bool stencil_overflow;
+  __device__ __forceinline__ void cell(int, int s, int e) {
+    const int cap = c.K;
+    int cnt = 0;
+    for (int k0 = s; k0 < e && cnt < cap + 1; k0 += 4) {  // cond_fun: in_cell * has_space
+      for (int u = 0; u < 4; ++u) {
+        const int kj = k0 + u;
+        if (kj >= e) break;
+        const Body<F> bj = load_sorted(c, off, kj, false);
+        F r[3];
+        displacement_div(lc, a, bj, r);
+        const F d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        if (!(d2 <= cutoff_sq)) continue;
+        const long long dest = row_off + cnt;
+        if (cnt < cap && dest < cap) row[dest] = (I)c.perm[off + kj];
+        ++cnt;
+      }
+      stencil_overflow |= cnt > cap;
+    }
+    row_off += cnt;
+  }
+};
+
+template <typename F>
+__global__ void __launch_bounds__(128) k_cross_neighbor_list(Ctx<F> c, const F* __restrict__ pos_a, long long n_a,
+                                                              const F* __restrict__ cell_size_nl,
+                                                              const F* __restrict__ cutoff,
+                                                              typename RT<F>::I* __restrict__ nl) {
+  pdl_prologue();
+  using I = typename RT<F>::I;
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_a) return;
+  const LawCtx<F> lc = make_law_ctx(c, b);
+  CrossVis<F> vis{c, lc, (size_t)b * c.n};
+  const F* pa = pos_a + ((size_t)b * n_a + i) * c.dim;
+  F pp[3] = {pa[0], pa[1], c.dim == 3 ? pa[2] : F(0)};
+  vis.a.x = pp[0]; vis.a.y = pp[1]; vis.a.z = pp[2];
+  vis.cutoff_sq = cutoff[b] * cutoff[b];
+  vis.row = nl + ((size_t)b * n_a + i) * c.K;
+  for (int q = 0; q < c.K; ++q) vis.row[q] = I(-1);
+  vis.row_off = 0;
+  vis.stencil_overflow = false;
+  walk_stencil_at<F>(c, b, pp, cell_size_nl, vis);
+  if (vis.stencil_overflow || vis.row_off > c.K) c.gi[b].nl_overflow = 1;
+}
+
 // ---------------------------------------------------------------------------
 // naive O(N^2) collider (naive.py:187-235, 73-113): thread per particle, all j in
 // index order straight from the State arrays.
@@ -1064,6 +1130,22 @@ int celllist_neighbor_list(cudaStream_t s, Ctx<F>& c, const F* cutoff, typename 
 }
 
 template <typename F>
+int celllist_cross_neighbor_list(cudaStream_t s, Ctx<F>& c, const F* pos_a, long long n_a, const F* cutoff,
+                                 typename RT<F>::I* nl, uint8_t* overflow) {
+  if (cudaMemsetAsync(overflow, 0, c.batch, s) != cudaSuccess) return JDB200_ECUDA;
+  if (n_a == 0 || c.K == 0) return 0;
+  if (c.n == 0)  // empty database: every row is padding
+    return cudaMemsetAsync(nl, 0xff, sizeof(typename RT<F>::I) * c.batch * n_a * c.K, s) == cudaSuccess ? 0 : JDB200_ECUDA;
+  F* cs_nl = c.partial;  // [B] scratch for the inflated cell size
+  JDB_LAUNCH(k_nl_cell_size<F>, dim3(cdiv(c.batch, 64)), 64, s, c, cutoff, cs_nl);
+  int rc = build_partition<F>(s, c, cs_nl, 0, false);
+  if (rc) return rc;
+  JDB_LAUNCH(k_cross_neighbor_list<F>, dim3(cdiv(n_a, 128), c.batch), 128, s, c, pos_a, n_a, cs_nl, cutoff, nl);
+  JDB_LAUNCH(k_nl_flag<F>, dim3(cdiv(c.batch, 64)), 64, s, c, overflow);
+  return 0;
+}
+
+template <typename F>
 int naive_force(cudaStream_t s, Ctx<F>& c) {
   if (c.n == 0) return 0;
   const dim3 grid(cdiv(c.n, 128), c.batch);
@@ -1084,6 +1166,7 @@ int naive_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
   template int celllist_force<F>(cudaStream_t, Ctx<F>&, int, bool, bool);                          \
   template int celllist_energy<F>(cudaStream_t, Ctx<F>&, F*);                           \
   template int celllist_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, RT<F>::I*, uint8_t*); \
+  template int celllist_cross_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, long long, const F*, RT<F>::I*, uint8_t*); \
   template int naive_force<F>(cudaStream_t, Ctx<F>&);                                   \
   template int naive_energy<F>(cudaStream_t, Ctx<F>&, F*);
 JDB_INST(float)

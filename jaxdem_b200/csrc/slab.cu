@@ -174,17 +174,37 @@ struct SlabGeom {
 };
 
 // category bits: 1 halo-lo, 2 halo-up, 4 leave-lo, 8 leave-up, 16 stray
-template <typename F, int D>
-__global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, const F* __restrict__ pos_c,
+// INTEGRATE: VelocityVerlet.step_before_force (velocity_verlet.py:57-61; the arithmetic of
+// k_linear) rides along, so the drift and the classification read the positions once.
+template <typename F, int D, bool INTEGRATE>
+__global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, SlabRows<F> rows, const F* __restrict__ dtp,
                                                                const F* __restrict__ anchor, const F* __restrict__ box,
                                                                const F* __restrict__ cell_size,
                                                                uint8_t* __restrict__ cat, int* __restrict__ bc) {
   pdl_prologue();
   using I = typename RT<F>::I;
+  using T = RT<F>;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int c8 = 0;
   bool live = i < gm.n;
   if (live) {
+    F* pos_c = rows.pos_c;
+    if (INTEGRATE) {
+      const F dt = dtp[0];
+      const F sc = T::div(T::mul(dt, F(0.5)), rows.mass[i]);  // dt * 0.5 / mass
+      const F free = rows.fixed[i] ? F(0) : F(1);
+      F v[D], p[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        v[d] = T::add(rows.vel[i * D + d], T::mul(T::mul(rows.force[i * D + d], sc), free));
+        p[d] = T::add(pos_c[i * D + d], T::mul(dt, v[d]));
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        rows.vel[i * D + d] = v[d];
+        pos_c[i * D + d] = p[d];
+      }
+    }
     const F B = box[D - 1];
     // grid size of the last axis, as _grid_params computes it (periodic: floor(B / cs), >= 1)
     I g = RT<F>::to_int(RT<F>::floor(RT<F>::div(B, cell_size[0])));
@@ -463,8 +483,12 @@ int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows*
   const int nb = std::max(1, cdiv(d->n, kSlabBlock));
   uint8_t* cat = (uint8_t*)scratch;
   int* bc = (int*)((char*)scratch + (((size_t)nb * kSlabBlock + 255) & ~size_t(255)));
-  JDB_LAUNCH((k_slab_classify<F, D>), dim3(nb), kSlabBlock, s, gm, (const F*)rows->pos_c, (const F*)d->anchor,
-             (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
+  if (d->dt)
+    JDB_LAUNCH((k_slab_classify<F, D, true>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)d->dt,
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
+  else
+    JDB_LAUNCH((k_slab_classify<F, D, false>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)nullptr,
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
   const M lo(msg_lo, gm.cap_m, gm.cap_g), up(msg_up, gm.cap_m, gm.cap_g);
   JDB_LAUNCH(k_slab_scan, dim3(1), 1024, s, nb, bc, lo.header, up.header, (long long*)header_local);
   JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, msg_lo, msg_up, kept,

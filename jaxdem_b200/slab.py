@@ -132,6 +132,8 @@ class CudaEngine:
         # collider + force manager + after-kick in ONE call when the configuration allows it
         self._fuse_after = (sy.linear_integrator.native_kind == "verlet" and not sy.rotation_integrator.native_kind
                             and sy.domain.native_kind == "periodic")
+        # ... and the before-force kick + drift inside the exchange's classify kernel
+        self.fuse_before = self._fuse_after and slab.world > 1
         self._bound = dict(p=p, sv=_call.state_view(full), yv=_call.system_view(self.system), ws=ws, lib=L.lib(),
                            keep=full, dev=slab.device, C=C, check=L.check, stream=_call.stream_ptr)
 
@@ -154,6 +156,8 @@ class CudaEngine:
             return
         n = state if isinstance(state, int) else state.N
         torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
+        if getattr(self, "fuse_before", False):
+            return  # done by jdb200_slab_pack (SlabSystem.step passes integrate=True)
         if sy.linear_integrator.native_kind:
             self._hook("jdb200_linear_step_before_force", n, ws=False)
         if sy.rotation_integrator.native_kind:
@@ -202,6 +206,7 @@ class CudaEngine:
         d.search_range = slab.layout.R
         d.anchor, d.box_size = sy.domain.anchor.data_ptr(), sy.domain.box_size.data_ptr()
         d.cell_size = sy.collider.cell_size.data_ptr()
+        d.dt = None
         return d
 
     @staticmethod
@@ -227,11 +232,13 @@ class CudaEngine:
             ex = self._ex = dict(key=key, d=d, rows=self._rows(slab.buf), lib=lib, C=C, check=L.check)
         return ex
 
-    def pack(self, slab):
+    def pack(self, slab, integrate=False):
         from . import _call
         ex = self._exchange_args(slab)
         C = ex["C"]
         ex["d"].n = int(slab.n_own)
+        # the before-force kick + drift of velocity Verlet rides along with the classification
+        ex["d"].dt = self.system.dt.data_ptr() if integrate else None
         ex["check"](ex["lib"].jdb200_slab_pack(
             _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), slab.send_ptr("lo"),
             slab.send_ptr("up"), slab.kept.data_ptr(), slab.holes.data_ptr(), slab.header_local.data_ptr(),
@@ -430,18 +437,20 @@ class SlabSystem:
             species_id=s["species_id"][:n], fixed=b["fixed"][:n], _pos_p_rot=s["_pos_p_rot"][:n], has_clumps=False)
 
     # ------------------------------------------------------------------ the exchange
-    def exchange(self) -> None:
-        """Migration + halo exchange after the drift (one neighbour exchange, one host sync)."""
+    def exchange(self, integrate: bool = False) -> None:
+        """Migration + halo exchange after the drift (one neighbour exchange, one host sync).
+        ``integrate``: the engine's pack also applies the before-force kick + drift (fused step)."""
         if self.world == 1:
             self.n_ghost = 0
             return
+        pack = (lambda: self.engine.pack(self, integrate=True)) if integrate else (lambda: self.engine.pack(self))
         if self._symm is not None:
             self._select_parity()
-            self.engine.pack(self)  # messages are stored straight into the neighbours' receive buffers
+            pack()  # messages are stored straight into the neighbours' receive buffers
             self._symm["hdl"].barrier(channel=0)  # device-side: every rank's messages have landed
             self._parity ^= 1
         else:
-            self.engine.pack(self)  # leavers / halo rows -> messages, leavers' rows -> holes, counts -> headers
+            pack()  # leavers / halo rows -> messages, leavers' rows -> holes, counts -> headers
             # sends in (lower, upper) order, receives in (upper, lower) order: with two ranks both
             # messages travel between the same pair and are matched in posting order
             ops = [dist.P2POp(dist.isend, self.send_lo, self.lo_rank, group=self.group),
@@ -483,7 +492,7 @@ class SlabSystem:
         fused = getattr(eng, "_bound", None) is not None
         for _ in range(int(n)):
             eng.before_force(rows(self.n_own))
-            self.exchange()
+            self.exchange(integrate=bool(getattr(eng, "fuse_before", False)))
             if fused:
                 eng.force_and_after(self.n_own + self.n_ghost, self.n_own)
             else:

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from .state import int_dtype_for
+
 from . import linalg as la
 from .forces import LAWS
 
@@ -315,6 +317,67 @@ def celllist_create_neighbor_list(state, system, cutoff, max_neighbors):
         total += c
     count_ovf = bool(np.any(total > max_neighbors))
     return nl, bool(any_stencil_ovf or count_ovf or hash_ovf)
+
+
+def celllist_create_cross_neighbor_list(pos_a, pos_b, system, cutoff, max_neighbors, idtype=None):
+    """create_cross_neighbor_list (cell_list.py:600-715): for every query point of pos_a the
+    points of pos_b within ``cutoff``; pos_b is partitioned into cells, the stencil comes from
+    the query point's own cell; no clump / bond mask; rows in stencil x sorted-run order, mapped
+    back to original B indices, padded with -1.  Returns (list (N_A, K) int, overflow bool)."""
+    col = system.collider
+    pos_a, pos_b = np.asarray(pos_a), np.asarray(pos_b)
+    F = pos_b.dtype
+    I = np.dtype(idtype) if idtype is not None else int_dtype_for(F)
+    n_a, n_b = pos_a.shape[0], pos_b.shape[0]
+    if n_a == 0:
+        return np.empty((0, max_neighbors), I), False
+    if n_b == 0:
+        return np.full((n_a, max_neighbors), -1, I), False
+    if max_neighbors == 0:
+        return np.empty((n_a, 0), I), False
+    cutoff = F.type(cutoff)
+    cutoff_sq = cutoff**2
+    search_range = max(int(np.max(col.neighbor_mask)), 1)
+    cell_size = np.maximum(col.cell_size, cutoff / F.type(search_range))
+    perm_b, sh, _, ovf_b, _ = get_spatial_partition(pos_b, system, cell_size, col.neighbor_mask, I)
+    _, _, nh, ovf_a, _ = get_spatial_partition(pos_a, system, cell_size, col.neighbor_mask, I)
+    if system.domain.periodic:
+        nh = dedup_stencil_hashes(nh)
+    dom = system.domain
+    cap = max_neighbors
+    nl = np.full((n_a, max_neighbors), -1, dtype=I)
+    row_off = np.zeros(n_a, np.int64)
+    total = np.zeros(n_a, np.int64)
+    any_stencil_ovf = False
+    for m in range(nh.shape[1]):
+        target = nh[:, m]
+        k = np.searchsorted(sh, target, side="left").astype(np.int64)
+        c = np.zeros(n_a, np.int64)
+        while True:
+            safe_k = np.minimum(k, n_b - 1)
+            alive = (k < n_b) & (sh[safe_k] == target) & (c < cap + 1)  # cond_fun of _make_stencil_body
+            if not alive.any():
+                break
+            sel = np.nonzero(alive)[0]
+            for u in range(PAIR_UNROLL):
+                ak = k[sel] + u
+                sk = np.minimum(ak, n_b - 1)
+                in_cell = (ak < n_b) & (sh[sk] == target[sel])
+                j = perm_b[sk].astype(np.int64)
+                dr = dom.displacement(pos_a[sel], pos_b[j])  # division form
+                valid = (la.norm2(dr) <= cutoff_sq) & in_cell
+                w = sel[valid]
+                slot = c[w]
+                dest = row_off[w] + slot
+                ok = (slot < cap) & (dest < max_neighbors)
+                nl[w[ok], dest[ok]] = j[valid][ok].astype(I)
+                c[w] += 1
+            any_stencil_ovf |= bool(np.any(c[sel] > cap))
+            k[sel] += PAIR_UNROLL
+        row_off += c
+        total += c
+    count_ovf = bool(np.any(total > max_neighbors))
+    return nl, bool(any_stencil_ovf or count_ovf or ovf_a or ovf_b)
 
 
 def compute_force(state, system):

@@ -504,3 +504,24 @@ def test_slab_pack_unpack_kernels_bit_exact(dtype, dim):
         for k in slab.buf:
             assert torch.equal(slab.buf[k][:tot].cpu(), twin.buf[k][:tot]), (k, arrivals_fewer)
         slab.n_own = twin.n_own = n_new
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("domain", ["periodic", "reflect"])
+@pytest.mark.parametrize("K", [48, 5])
+def test_cross_neighbor_list_bit_exact(dtype, dim, domain, K):
+    """create_cross_neighbor_list: rows, padding and overflow flag bit for bit against the oracle."""
+    inp = make_inputs(3000, dim, seed=6, dtype=dtype, phi=0.55, poly=1.3)
+    ost, osy = build_oracle(inp, dtype=dtype, domain=domain)
+    gst, gsy = build_gpu(inp, dtype=dtype, domain=domain)
+    rng = np.random.default_rng(12)
+    pos_a = (rng.uniform(0.0, 0.999, (777, dim)) * inp["box"]).astype(dtype)
+    if domain == "periodic":
+        pos_a[::5] += inp["box"].astype(dtype)  # un-wrapped queries
+    cutoff = 1.2
+    want, wovf = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos, osy, cutoff, K)
+    got, govf = gsy.collider.create_cross_neighbor_list(torch.as_tensor(pos_a, device="cuda"), gst.pos, gsy, cutoff, K)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert bool(govf) == bool(wovf)
+    assert (K == 5) == bool(wovf)

@@ -202,3 +202,30 @@ def test_f32_dtypes_preserved():
     for f in ("pos_c", "vel", "force", "ang_vel", "torque", "q_w", "q_xyz", "_pos_p_rot"):
         assert getattr(st, f).dtype == np.float32, f
     assert st.clump_id.dtype == np.int32 and sy.collider.neighbor_mask.dtype == np.int32
+
+
+@pytest.mark.parametrize("dim,domain", [(3, "periodic"), (2, "periodic"), (3, "free")])
+def test_cross_neighbor_list_against_brute_force(dim, domain):
+    """create_cross_neighbor_list (cell_list.py:600-715): as sets, the rows equal the brute-force
+    answer ||displacement(a, b)||^2 <= cutoff^2; the empty-input conventions of :627-636 hold."""
+    from oracle import colliders as ocol
+    from helpers import build_oracle, make_inputs
+    inp = make_inputs(500, dim, seed=4, dtype=np.float64, phi=0.5)
+    ost, osy = build_oracle(inp, dtype=np.float64, domain=domain)
+    rng = np.random.default_rng(8)
+    pos_a = rng.uniform(-0.1, 1.1, (137, dim)) * inp["box"]  # some queries outside the box
+    if domain != "periodic":
+        pos_a = np.clip(pos_a, 0.0, inp["box"] * 0.999)
+    cutoff = 1.3
+    nl, ovf = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos, osy, cutoff, 64)
+    assert not ovf and nl.shape == (137, 64)
+    for i in range(137):
+        d = osy.domain.displacement(pos_a[i][None, :], ost.pos)
+        want = set(np.nonzero((d * d).sum(-1) <= cutoff**2)[0].tolist())
+        got = [j for j in nl[i].tolist() if j >= 0]
+        assert len(got) == len(set(got)) and set(got) == want, i
+    nl2, ovf2 = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos, osy, cutoff, 2)
+    assert ovf2 and nl2.shape == (137, 2)
+    assert ocol.celllist_create_cross_neighbor_list(pos_a[:0], ost.pos, osy, cutoff, 8)[0].shape == (0, 8)
+    e = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos[:0], osy, cutoff, 8)
+    assert (e[0] == -1).all() and not e[1]
