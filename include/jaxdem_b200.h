@@ -73,6 +73,13 @@ typedef struct jdb200_params {
   int64_t batch;          /* leading vmap axis, >= 1 */
   int64_t n;              /* particles per system */
   int64_t max_cells;      /* dense cell-table capacity per system (0 => SORTED) */
+  int64_t key_window_lo[2];  /* optional: the caller promises that every cell hash — of the particles AND of */
+  int64_t key_window_len[2]; /* their stencil cells — lies in [lo[w], lo[w] + len[w]) for w = 0 or 1 (slab
+                                decomposition: the layers of one rank, two windows where they wrap around the
+                                periodic box); only those rows of the dense table are zeroed and scanned.
+                                len[0] == 0: the whole table.  With two windows len[0] is a multiple of 4096
+                                and the windows are disjoint and ascending.  A hash outside the windows sends
+                                the system to the sorted fallback (AUTO) or raises Collider.overflow (DENSE). */
   int32_t dim;            /* 2 or 3 */
   int32_t dtype;          /* JDB200_F32 / JDB200_F64 */
   int32_t domain;         /* JDB200_DOMAIN_* (periodic <=> Domain.periodic) */

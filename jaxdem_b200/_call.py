@@ -43,6 +43,10 @@ def params_for(state, system, *, max_neighbors: int = 0) -> L.Params:
     p.max_neighbors = int(max_neighbors)
     p.grid_mode = L.GRID[getattr(col, "grid_mode", "auto")]
     p.max_cells = int(getattr(col, "max_cells", 0) or 0)
+    kw = getattr(col, "key_windows", None)  # ((lo, len), (lo, len)): rows of the dense table in use (slab.py)
+    if kw:
+        for w, (lo, ln) in enumerate(kw):
+            p.key_window_lo[w], p.key_window_len[w] = int(lo), int(ln)
     p.clumps = 1 if state.has_clumps else 0
     return p
 

@@ -27,6 +27,7 @@ ERRORS = {-1: "JDB200_EINVAL (bad params)", -2: "JDB200_ENULL (NULL pointer)",
 class Params(C.Structure):
     _fields_ = [
         ("batch", C.c_int64), ("n", C.c_int64), ("max_cells", C.c_int64),
+        ("key_window_lo", C.c_int64 * 2), ("key_window_len", C.c_int64 * 2),
         ("dim", C.c_int32), ("dtype", C.c_int32), ("domain", C.c_int32), ("law", C.c_int32),
         ("collider", C.c_int32), ("linear_integrator", C.c_int32), ("rotation_integrator", C.c_int32),
         ("stencil_m", C.c_int32), ("bond_width", C.c_int32), ("n_materials", C.c_int32),

@@ -45,12 +45,21 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
     s_bound = dense ? (long long)bound : 0;
   }
   __syncthreads();
-  if (s_dense) {  // zero count rows [0, bound] (the table stride is padded to 64 ints)
-    int4* cnt = reinterpret_cast<int4*>(c.cell_count + (size_t)b * c.cell_stride);
-    const long long rows4 = (s_bound + 1 + 3) / 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows4;
-         i += (long long)gridDim.x * blockDim.x)
-      cnt[i] = make_int4(0, 0, 0, 0);
+  if (s_dense) {  // zero count rows [0, bound] (the table stride is padded to 64 ints), or the windows in use
+    for (int w = 0; w < 2; ++w) {
+      long long lo = 0, len = s_bound + 1;
+      if (c.win_len[0] > 0) {
+        lo = c.win_lo[w] & ~3ll;
+        len = c.win_len[w] > 0 ? min(c.win_lo[w] + c.win_len[w], s_bound + 1) - lo : 0;
+      } else if (w == 1) {
+        len = 0;
+      }
+      int4* cnt = reinterpret_cast<int4*>(c.cell_count + (size_t)b * c.cell_stride + lo);
+      const long long rows4 = (len + 3) / 4;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows4;
+           i += (long long)gridDim.x * blockDim.x)
+        cnt[i] = make_int4(0, 0, 0, 0);
+    }
     unsigned long long* ts = c.tile_state + (size_t)b * c.scan_tiles;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.scan_tiles; i += gridDim.x * blockDim.x)
       ts[i] = 0ull;
@@ -257,7 +266,13 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     c.key[gidx] = key;
     c.upos[gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
-      if (key >= 0 && (long long)key < g.bound) {
+      bool in_table = key >= 0 && (long long)key < g.bound;
+      if (in_table && c.win_len[0] > 0) {
+        const long long k = (long long)key;
+        in_table = (k >= c.win_lo[0] && k < c.win_lo[0] + c.win_len[0]) ||
+                   (k >= c.win_lo[1] && k < c.win_lo[1] + c.win_len[1]);
+      }
+      if (in_table) {
         c.rank[gidx] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + key, 1);
       } else {
         c.gi[b].dense_fail = 1;  // hash outside the dense table: the sorted fallback takes over
@@ -286,9 +301,19 @@ __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
   GridInfo<I>& g = c.gi[b];
   if (!g.dense) return;
   const size_t co = (size_t)b * c.cell_stride;
-  const bool too_many = scan_tile(c.cell_count + co, c.cell_start + co, g.bound + 1,
-                                  c.tile_state + (size_t)b * c.scan_tiles, &c.tile_counter[b],
-                                  JDB200_DENSE_MAX_OCC);
+  bool too_many;
+  if (c.win_len[0] > 0) {  // only the windows of the table in use (slab decomposition): scanned as one array
+    const long long end0 = min(c.win_lo[0] + c.win_len[0], (long long)g.bound + 1);
+    const long long len_a = c.win_len[1] > 0 ? c.win_len[0] : max(end0 - c.win_lo[0], 0ll);
+    const long long len_b = c.win_len[1] > 0 ? max(min(c.win_lo[1] + c.win_len[1], (long long)g.bound + 1) - c.win_lo[1], 0ll) : 0;
+    too_many = scan_tile(c.cell_count + co, c.cell_start + co, len_a + len_b,
+                         c.tile_state + (size_t)b * c.scan_tiles, &c.tile_counter[b], JDB200_DENSE_MAX_OCC,
+                         len_a, c.win_lo[0], c.win_lo[1]);
+  } else {
+    too_many = scan_tile(c.cell_count + co, c.cell_start + co, g.bound + 1,
+                         c.tile_state + (size_t)b * c.scan_tiles, &c.tile_counter[b],
+                         JDB200_DENSE_MAX_OCC);
+  }
   if (too_many) g.dense_fail = 1;
 }
 

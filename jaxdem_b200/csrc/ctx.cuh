@@ -12,6 +12,7 @@ struct Ctx {
   long long max_cells;
   long long cell_stride;  // ints per system in the dense cell tables (max_cells + 1 rounded up to 64)
   int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
+  long long win_lo[2], win_len[2];  // dense cell-table windows in use (jdb200_params.key_window_*; len 0: whole table)
   int fused;  // fused sphere step driver (abi.cu system_step): hash kernel integrates, pair kernel finishes the step
   // state (in place)
   F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;
@@ -121,6 +122,10 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
   c.grid_mode = p->grid_mode;
   c.clumps = p->clumps;
   c.lin = p->linear_integrator;
+  for (int w = 0; w < 2; ++w) {
+    c.win_lo[w] = p->key_window_lo[w];
+    c.win_len[w] = p->key_window_len[w];
+  }
   c.rot = p->rotation_integrator;
   if (st) {
     c.pos_c = (F*)st->pos_c; c.pos_p = (F*)st->pos_p; c.vel = (F*)st->vel; c.force = (F*)st->force;
@@ -153,6 +158,10 @@ inline int check_params(const jdb200_params* p) {
   if (p->domain < 0 || p->domain > 2 || p->law < 0 || p->law > 2) return JDB200_EINVAL;
   if (p->grid_mode < 0 || p->grid_mode > 2 || p->max_cells < 0 || p->max_cells > 0x7ffffff0LL) return JDB200_EINVAL;
   if (p->bond_width < 0 || p->n_materials < 0 || p->stencil_m < 0 || p->max_neighbors < 0)
+    return JDB200_EINVAL;
+  for (int w = 0; w < 2; ++w)
+    if (p->key_window_lo[w] < 0 || p->key_window_len[w] < 0) return JDB200_EINVAL;
+  if (p->key_window_len[1] > 0 && (p->key_window_len[0] % 4096 != 0 || p->key_window_lo[1] < p->key_window_lo[0] + p->key_window_len[0]))
     return JDB200_EINVAL;
   return 0;
 }

@@ -10,9 +10,12 @@ namespace jdb {
 // deadlock.  Warp 0 inspects 32 predecessor descriptors per round.  Descriptor = status
 // (0 invalid, 1 aggregate, 2 inclusive prefix) << 32 | value.  Returns true if any element
 // exceeded `limit`.
+// The scanned array may be the concatenation of two windows of in / out: virtual elements
+// [0, len_a) live at [a_lo, a_lo + len_a), the rest at [b_lo, ...); len_a is a multiple of
+// kScanTile, so a tile never straddles the seam.  One window: len_a = rows, a_lo = 0.
 __device__ __forceinline__ bool scan_tile(const int* __restrict__ in, int* __restrict__ out, long long rows,
                                           unsigned long long* __restrict__ ts, int* tile_counter,
-                                          int limit) {
+                                          int limit, long long len_a = -1, long long a_lo = 0, long long b_lo = 0) {
   const int ntiles = (int)((rows + kScanTile - 1) / kScanTile);
   __shared__ int s_tile;
   __shared__ int s_warp[16];
@@ -22,6 +25,12 @@ __device__ __forceinline__ bool scan_tile(const int* __restrict__ in, int* __res
   const int tile = s_tile;
   if (tile >= ntiles) return false;
   const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * 8;
+  {  // window of this tile
+    const long long t0 = (long long)tile * kScanTile;
+    const long long shift = (len_a < 0 || t0 < len_a) ? a_lo : b_lo - len_a;
+    in += shift;
+    out += shift;
+  }
   int v[8];
   int sum = 0;
   bool too_many = false;

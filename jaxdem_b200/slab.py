@@ -110,6 +110,28 @@ def message_views(buf: torch.Tensor, L: dict, F: torch.dtype) -> dict:
     )
 
 
+def key_windows(lo: int, up: int, R: int, n_layers: int, layer_cells: int, table_rows: int):
+    """Rows of the dense cell table one rank can touch: the hashes of its owned + ghost rows and of
+    their stencil cells lie in the layers [lo - 2R - 1, up + 2R + 1]; with the x-fastest hash that
+    is one window of the table, or two where the layers wrap around the periodic box
+    (``jdb200_params.key_window_*``).  None: the whole table."""
+    pad = 2 * R + 1
+    L0, L1 = lo - pad, up + pad + 1
+    G, S = n_layers, layer_cells
+    if L1 - L0 >= G:
+        return None
+    if L0 >= 0 and L1 <= G:
+        return ((L0 * S, (L1 - L0) * S + 1), (0, 0))
+    if L0 < 0:  # wraps below: layers [0, L1) and [G + L0, G)
+        a_len, b_lo = L1 * S, (G + L0) * S
+    else:       # wraps above: layers [0, L1 - G) and [L0, G)
+        a_len, b_lo = (L1 - G) * S, L0 * S
+    a_len = (a_len + 1 + 4095) // 4096 * 4096
+    if a_len >= b_lo:
+        return None
+    return ((0, a_len), (b_lo, table_rows - b_lo))
+
+
 class CudaEngine:
     """The product engine: the reference's hooks and the exchange kernels through
     libjaxdem_b200.so (no CPU path)."""
@@ -552,6 +574,11 @@ def create_slab_system(arrays: dict, *, box_size, anchor=None, dt=0.005, force_m
     gd = torch.clamp(torch.floor(torch.as_tensor(box, dtype=F) / cs).to(torch.int64), min=1)
     col.max_cells = int(torch.prod(gd).item() + int(gd[:-1].prod().item()) * 2 + 1024)
     R = int(col.neighbor_mask.abs().max())
+    if world > 1:  # only the layers this rank can touch are zeroed and scanned every step
+        rank = dist.get_rank(group)
+        lay = SlabLayout(int(gd[-1]), world, R)
+        col.key_windows = key_windows(lay.bounds[rank], lay.bounds[rank + 1], R, int(gd[-1]),
+                                      int(gd[:-1].prod().item()), col.max_cells + 1)
     cap = int(math.ceil(capacity_factor * n / world)) + 1024
     slab = SlabSystem(dim=dim, dtype=dtype, device=dev, capacity=cap, box=box, anchor=anc,
                       n_layers=int(gd[-1]), search_range=R, group=group, transport=transport)

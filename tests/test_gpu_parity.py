@@ -525,3 +525,30 @@ def test_cross_neighbor_list_bit_exact(dtype, dim, domain, K):
     assert np.array_equal(got.cpu().numpy(), want)
     assert bool(govf) == bool(wovf)
     assert (K == 5) == bool(wovf)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_dense_table_key_windows(dtype):
+    """jdb200_params.key_window_*: zeroing / scanning only windows of the dense cell table gives
+    the same partition and forces as the whole table (one window, and two windows scanned as one
+    array); a hash outside the windows falls back to the sorted strategy (same results)."""
+    inp = make_inputs(30000, 3, seed=23, dtype=dtype, phi=0.5)
+    gst, gsy = build_gpu(inp, dtype=dtype)
+    perm0, sh0, _, dense0 = gsy.collider.partition(gst, gsy)
+    gsy.collider.compute_force(gst, gsy)
+    f0 = gst.force.clone()
+    assert bool(dense0)
+    big = int(gsy.collider.max_cells) + 1  # the kernels clamp a window to the rows of the table in use
+    for windows, expect_dense in ((((0, big), (0, 0)), True),
+                                  (((0, 8192), (8192, big - 8192)), True),
+                                  (((0, 4096), (8192, big - 8192)), False)):
+        gsy.collider.key_windows = windows
+        perm, sh, _, dense = gsy.collider.partition(gst, gsy)
+        assert bool(dense) == expect_dense
+        assert torch.equal(perm, perm0) and torch.equal(sh, sh0)
+        gst.force.zero_()
+        gsy.collider.compute_force(gst, gsy)
+        if expect_dense:
+            assert torch.equal(gst.force, f0)
+        else:  # sorted fallback: another kernel, another summation order
+            assert_close(gst.force, f0.cpu().numpy(), dtype, "force", factor=4)

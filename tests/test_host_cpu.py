@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_params_struct_layout_matches_header():
     header = open(os.path.join(ROOT, "include", "jaxdem_b200.h")).read()
     body = re.search(r"typedef struct jdb200_params \{(.*?)\} jdb200_params;", header, re.S).group(1)
-    names = re.findall(r"int(?:32|64)_t\s+(\w+);", body)
+    names = re.findall(r"int(?:32|64)_t\s+(\w+)(?:\[\d+\])?;", body)
     assert names == [f[0] for f in _lib.Params._fields_]
     for struct, tag in ((_lib.StateView, "jdb200_state"), (_lib.SystemView, "jdb200_system")):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (tag, tag), header, re.S).group(1)
