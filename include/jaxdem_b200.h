@@ -138,6 +138,8 @@ typedef struct jdb200_system {
   void* mat_mu;                /* (B,Mt) F */
   void* mat_mu_r;              /* (B,Mt) F */
   void* mat_young_eff;         /* (B,Mt,Mt) F MaterialTable.young_eff */
+  void* time;                  /* (B,) F      System.time       } optional (NULL: the caller keeps them): advanced by */
+  void* step_count;            /* (B,) int64  System.step_count } jdb200_system_step, once per step (system.py:62-63)  */
 } jdb200_system;
 
 JDB200_API int jdb200_abi_version(void);

@@ -103,6 +103,7 @@ def system_view(system) -> L.SystemView:
     v.mat_mu = mt.mu.data_ptr()
     v.mat_mu_r = mt.mu_r.data_ptr()
     v.mat_young_eff = mt.young_eff.data_ptr()
+    v.time = v.step_count = None  # the caller keeps the clock (jdb200_system_step sets them when asked)
     return v
 
 
@@ -110,12 +111,15 @@ def stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def call(name: str, state, system, *extra, needs_ws: bool = True, max_neighbors: int = 0):
-    """Invoke one C-ABI entry point on the current CUDA stream (asynchronous)."""
+def call(name: str, state, system, *extra, needs_ws: bool = True, max_neighbors: int = 0, clock: bool = False):
+    """Invoke one C-ABI entry point on the current CUDA stream (asynchronous).  ``clock``: hand
+    System.time / step_count to the library (jdb200_system_step advances them on the device)."""
     require_cuda(state)
     lib = L.lib()
     p = params_for(state, system, max_neighbors=max_neighbors)
     sv, yv = state_view(state), system_view(system)
+    if clock:
+        yv.time, yv.step_count = system.time.data_ptr(), system.step_count.data_ptr()
     args = [stream_ptr(state.device), C.byref(p), C.byref(sv), C.byref(yv)]
     if needs_ws:
         ws = workspace(p, state.device)

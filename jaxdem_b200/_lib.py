@@ -40,7 +40,7 @@ STATE_FIELDS = ("pos_c", "pos_p", "vel", "force", "q_w", "q_xyz", "ang_vel", "to
 SYSTEM_FIELDS = ("dt", "box_size", "inv_box_size", "anchor", "restitution", "cell_size",
                  "neighbor_mask", "collider_overflow", "interact_same_bond_id", "gravity",
                  "external_force", "external_force_com", "external_torque", "mat_young",
-                 "mat_poisson", "mat_e", "mat_mu", "mat_mu_r", "mat_young_eff")
+                 "mat_poisson", "mat_e", "mat_mu", "mat_mu_r", "mat_young_eff", "time", "step_count")
 
 
 class StateView(C.Structure):

@@ -112,6 +112,25 @@ int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
   return 0;
 }
 
+template <typename F>
+__global__ void k_advance_clock(Ctx<F> c, long long n_steps) {
+  pdl_prologue();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= c.batch) return;
+  if (c.time) {
+    F t = c.time[b];
+    const F dt = c.dt[b];
+    for (long long i = 0; i < n_steps; ++i) t = RT<F>::add(t, dt);  // one rounding per step, as the reference
+    c.time[b] = t;
+  }
+  if (c.step_count) c.step_count[b] += n_steps;
+}
+template <typename F>
+int advance_clock(cudaStream_t s, Ctx<F>& c, long long n_steps) {
+  JDB_LAUNCH(k_advance_clock<F>, dim3(cdiv(c.batch, 64)), 64, s, c, n_steps);
+  return 0;
+}
+
 // _step_once (system.py:60-82), identity user hooks.  time/step_count are host-side
 // bookkeeping of the caller.
 template <typename F>
@@ -128,9 +147,14 @@ int system_step(cudaStream_t s, Ctx<F>& c, int collider, long long n_steps) {
                      c.rot == JDB200_ROT_NONE && c.domain == JDB200_DOMAIN_PERIODIC && c.n > 0;
   if (fused) {
     c.fused = 1;
+    c.tick = 1;  // the setup kernel of every step advances System.time / step_count
     for (long long it = 0; it < n_steps && !rc; ++it)
       rc = celllist_force<F>(s, c, 3, false, it == n_steps - 1);
     return rc;
+  }
+  if (c.time || c.step_count) {  // hook-by-hook flow: one tiny launch per call
+    rc = advance_clock<F>(s, c, n_steps);
+    if (rc) return rc;
   }
   if (c.domain != JDB200_DOMAIN_FREE && n_steps > 0) rc = refresh_inv_box<F>(s, c);  // box is constant
   for (long long it = 0; it < n_steps && !rc; ++it) {

@@ -68,6 +68,11 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
   // fused driver: the _step_once refresh of inv_box_size (system.py:69-74) rides along
   if (c.fused && (int)threadIdx.x < c.dim)
     c.inv_box[b * c.dim + threadIdx.x] = RT<F>::div(F(1), c.box[b * c.dim + threadIdx.x]);
+  // ... and so does the clock of _step_once (system.py:62-63): time += dt, step_count += 1
+  if (c.tick && threadIdx.x == 0) {
+    if (c.time) c.time[b] = RT<F>::add(c.time[b], c.dt[b]);
+    if (c.step_count) c.step_count[b] += 1;
+  }
   // ---- stencil classification (block 0 of each system) ----
   const I* mask = c.mask + (size_t)b * c.M * c.dim;
   // canonical cube: M == (2R+1)^D and row m == digits of m in base (2R+1), last axis fastest
@@ -606,10 +611,28 @@ int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override, int 
     const int limit = coop_grid_limit((const void*)k_radix_sort<F>, 256);
     if (limit <= 0) return JDB200_ECUDA;
     const int blocks = std::max(1, std::min(limit, c.radix_blocks));
-    void* args[] = {(void*)&c};
     const bool timed = g_timing.load(std::memory_order_relaxed) != 0;
     if (timed) timing_begin("k_radix_sort", s);
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_radix_sort<F>, dim3(blocks), dim3(256), args, 0, s);
+    // cooperative (grid syncs inside) AND programmatic stream serialization, like every other launch of
+    // the library: the kernel begins with pdl_prologue(), so the launch chain is not broken around it
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_radix_sort<F>, c);
+    if (e != cudaSuccess) {  // the combination is refused: plain cooperative launch
+      (void)cudaGetLastError();
+      void* args[] = {(void*)&c};
+      e = cudaLaunchCooperativeKernel((const void*)k_radix_sort<F>, dim3(blocks), dim3(256), args, 0, s);
+    }
     if (timed) timing_end(s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return JDB200_ECUDA;

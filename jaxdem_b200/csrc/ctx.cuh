@@ -24,6 +24,9 @@ struct Ctx {
   F *young, *poisson, *e, *mu, *mu_r, *young_eff;
   I* mask;
   uint8_t *overflow, *interact;
+  F* time;               // System.time / step_count, advanced by the n-step driver when given
+  long long* step_count;
+  int tick;              // host flag: this partition build opens a step of jdb200_system_step
   // workspace
   GridInfo<I>* gi;            // [B]
   I *key, *key_b, *key_c;      // [B*N] unsorted hashes + radix ping-pong
@@ -145,6 +148,7 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
     c.mu = (F*)sys->mat_mu; c.mu_r = (F*)sys->mat_mu_r; c.young_eff = (F*)sys->mat_young_eff;
     c.mask = (I*)sys->neighbor_mask;
     c.overflow = (uint8_t*)sys->collider_overflow; c.interact = (uint8_t*)sys->interact_same_bond_id;
+    c.time = (F*)sys->time; c.step_count = (long long*)sys->step_count;
   }
   carve(c, ws);
   return 0;

@@ -113,9 +113,8 @@ class System:
         if fused is None:
             fused = system._is_native()
         if fused:
-            _call.call("jdb200_system_step", state, system, C.c_int64(n))
-            system.time += system.dt * n
-            system.step_count += n
+            # time and step_count advance on the device, once per step, inside the same call
+            _call.call("jdb200_system_step", state, system, C.c_int64(n), clock=True)
         else:
             for _ in range(n):
                 state, system = System._step_once(state, system)

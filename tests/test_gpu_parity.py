@@ -552,3 +552,19 @@ def test_dense_table_key_windows(dtype):
             assert torch.equal(gst.force, f0)
         else:  # sorted fallback: another kernel, another summation order
             assert_close(gst.force, f0.cpu().numpy(), dtype, "force", factor=4)
+
+
+@pytest.mark.parametrize("domain,rot", [("periodic", ""), ("reflect", "verletspiral")])
+def test_system_clock_advances_on_device(domain, rot):
+    """System.time / step_count (system.py:62-63) after the single-call driver: the fused sphere
+    flow advances them in its setup kernel, the hook-by-hook flow in one tiny launch."""
+    inp = make_inputs(2000, 3, seed=2, dtype=np.float32, phi=0.5)
+    gst, gsy = build_gpu(inp, dtype=np.float32, domain=domain, rot=rot, dt=1e-3)
+    jd_step = __import__("jaxdem_b200").System.step
+    jd_step(gst, gsy, n=3)
+    jd_step(gst, gsy, n=1)
+    want = np.float32(0)
+    for _ in range(4):
+        want = np.float32(want + np.float32(1e-3))
+    assert int(gsy.step_count) == 4
+    assert float(gsy.time) == float(want)
