@@ -112,3 +112,28 @@ def test_celllist_create_matches_oracle_create():
         gc = jd.Collider.create("CellList", state=jd.State.create(ost.pos_c, rad=rad, device="cpu"), box_size=box)
         assert np.array_equal(gc.neighbor_mask.numpy(), oc.neighbor_mask)
         assert float(gc.cell_size) == float(oc.cell_size)
+
+
+def test_slab_layout_and_key_windows():
+    """Slab layout (whole cell layers per rank) and the dense-table windows a rank may touch."""
+    import numpy as np
+    from jaxdem_b200.slab import SlabLayout, key_windows, message_layout
+    lay = SlabLayout(412, 4, 1)
+    assert lay.bounds == [0, 103, 206, 309, 412] and (np.bincount(lay.owner) == 103).all()
+    with pytest.raises(ValueError):
+        SlabLayout(10, 4, 1)  # slabs thinner than 2 R + 1 layers
+    S, G, rows = 103 * 103, 412, 412 * 103 * 103 + 2 * 103 * 103 + 1025
+    # interior rank: one window, 2 R + 1 layers of margin on both sides (+ the end-of-run entry)
+    assert key_windows(103, 206, 1, G, S, rows) == (((103 - 3) * S, (103 + 7) * S + 1), (0, 0))
+    # first / last rank: the margin wraps around the periodic box -> two windows, the first
+    # a multiple of the scan tile (4096), disjoint and ascending
+    for lo, up in ((0, 103), (309, 412)):
+        (a_lo, a_len), (b_lo, b_len) = key_windows(lo, up, 1, G, S, rows)
+        assert a_lo == 0 and a_len % 4096 == 0 and a_len < b_lo and b_lo + b_len == rows
+    assert key_windows(0, 5, 1, 10, 100, 1100) is None  # the layers cover the whole grid
+    # message layout: sections 16-byte aligned, sized by the capacities
+    L = message_layout(3, 4, 1000, 5000)
+    assert L["WF"] == 24 and L["WG"] == 11
+    for k in ("mig_f", "mig_i", "gh_f", "gh_i", "bytes"):
+        assert L[k] % 16 == 0
+    assert L["bytes"] >= 64 + 1000 * (24 * 4 + 24) + 5000 * (11 * 4 + 16)
