@@ -336,8 +336,7 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   const size_t gidx = (size_t)b * c.n + i;
   const int key = (int)c.key[gidx];
   const size_t slot = (size_t)b * c.n + c.cell_start[(size_t)b * c.cell_stride + key] + c.rank[gidx];
-  c.perm_b[slot] = (int)i;
-  c.tmp_key[slot] = key;
+  c.slot_rec[slot] = make_int2((int)i, key);  // one 8-byte store: half the partial sectors of two 4-byte stores
 }
 
 // ---------------------------------------------------------------------------
@@ -527,12 +526,14 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   bool dense = use_dense(g);
   if (dense) {
     const int* cs = c.cell_start + (size_t)b * c.cell_stride;
-    const int* tmp = c.perm_b + off;
-    i = tmp[k];
-    const int key = c.tmp_key[off + k];
+    const int2* __restrict__ tmp = c.slot_rec + off;
+    const int2 me = tmp[k];
+    i = me.x;
+    const int key = me.y;
+    c.tmp_key[off + k] = key;  // cells stay in place: the key of arrival slot k is the key of final slot k
     const int s = cs[key], e = cs[key + 1];
     int r = 0;
-    for (int kk = s; kk < e; ++kk) r += tmp[kk] < i;
+    for (int kk = s; kk < e; ++kk) r += tmp[kk].x < i;
     dest = s + r;
   } else if (sorted_perm) {
     i = sorted_perm[off + k];

@@ -36,6 +36,7 @@ struct Ctx {
   int* cell_count;             // [B*(max_cells+1)] per-cell counts (dense; zeroed by every build)
   int* cell_start;             // [B*(max_cells+1)] exclusive starts (dense)
   int* tmp_key;                // [B*N] dense key of the particle in arrival slot k
+  int2* slot_rec;              // [B*N] (particle index, key) of arrival slot k: ONE 8-byte random store per particle
   Vec4<F>* upos;               // [B*N] (x, y, z, rad) in ORIGINAL order (pos = pos_c + pos_p_rot)
   Vec4<F>* uvel;               // [B*N] (vx, vy, vz, mass) in ORIGINAL order, after the before-force kick (fused driver)
   unsigned* coop_bar;          // [4] software state of the cooperative sort fallback
@@ -83,6 +84,7 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_count = b.take<int>(B * (size_t)c.cell_stride);
   c.cell_start = b.take<int>(B * (size_t)c.cell_stride);
   c.tmp_key = b.take<int>(BN);
+  c.slot_rec = b.take<int2>(BN);
   c.upos = b.take<Vec4<F>>(BN);
   c.uvel = b.take<Vec4<F>>(BN);
   c.coop_bar = b.take<unsigned>(4);
