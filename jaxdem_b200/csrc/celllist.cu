@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
         c.pos_c[gidx * D + d] = pc[d];
       }
     }
-    if (MODE == 3 || MODE == 4) c.uvel[gidx] = Vec4<F>{v[0], v[1], v[2], mass};
+    const size_t us = (MODE == 3 || MODE == 4) ? 2 : 1;  // fused flows interleave (pos, rad) and (vel, mass)
+    if (MODE == 3 || MODE == 4) c.urec[2 * gidx + 1] = Vec4<F>{v[0], v[1], v[2], mass};
     if (MODE == 2 && EXT) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       for (int a = 0; a < A; ++a) c.ext_torque[gidx * A + a] = F(0);
     }
     c.key[gidx] = key;
-    c.upos[gidx] = Vec4<F>{p[0], p[1], p[2], rad};
+    c.urec[us * gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
       bool in_table = key >= 0 && (long long)key < g.bound;
       if (in_table && c.win_len[0] > 0) {
@@ -548,7 +549,8 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   const size_t gi = off + i, gd = off + dest;
   c.perm[gd] = i;
   if (!dense || c.want_skey) c.skey[gd] = c.key[gi];
-  c.spos[gd] = c.upos[gi];
+  const size_t us = c.fused ? 2 : 1;
+  c.spos[gd] = c.urec[us * gi];
   if (c.clumps || g.any_bond) {
     bool has_bond = false;
     if (g.any_bond)
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
     c.sclump[gd] = (int)c.clump_id[gi] | (has_bond ? 0x80000000 : 0);
   }
   if (c.nmat > 1) c.smat[gd] = (int)c.mat_id[gi];
-  if (c.fused) c.svel[gd] = c.uvel[gi];
+  if (c.fused) c.svel[gd] = c.urec[2 * gi + 1];
   if (c.law == JDB200_LAW_CUNDALLSTRACK) {
     const F* v = c.vel + gi * c.dim;
     if (!c.fused) c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};

@@ -37,8 +37,10 @@ struct Ctx {
   int* cell_start;             // [B*(max_cells+1)] exclusive starts (dense)
   int* tmp_key;                // [B*N] dense key of the particle in arrival slot k
   int2* slot_rec;              // [B*N] (particle index, key) of arrival slot k: ONE 8-byte random store per particle
-  Vec4<F>* upos;               // [B*N] (x, y, z, rad) in ORIGINAL order (pos = pos_c + pos_p_rot)
-  Vec4<F>* uvel;               // [B*N] (vx, vy, vz, mass) in ORIGINAL order, after the before-force kick (fused driver)
+  // [2*B*N] shadow records in ORIGINAL order: (x, y, z, rad) with pos = pos_c + pos_p_rot, and — fused driver —
+  // (vx, vy, vz, mass) after the before-force kick.  Fused: the two records of a particle are interleaved
+  // (stride 2), so the gather of k_finalize touches ONE full 32-byte sector (f32); otherwise stride 1.
+  Vec4<F>* urec;
   unsigned* coop_bar;          // [4] software state of the cooperative sort fallback
   int want_skey;               // host flag: dense builds also fill skey (partition export)
   unsigned long long* tile_state;  // [B*scan_tiles] decoupled look-back descriptors
@@ -85,8 +87,7 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start = b.take<int>(B * (size_t)c.cell_stride);
   c.tmp_key = b.take<int>(BN);
   c.slot_rec = b.take<int2>(BN);
-  c.upos = b.take<Vec4<F>>(BN);
-  c.uvel = b.take<Vec4<F>>(BN);
+  c.urec = b.take<Vec4<F>>(2 * BN);
   c.coop_bar = b.take<unsigned>(4);
   c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);
   c.tile_counter = b.take<int>(B);
