@@ -330,6 +330,7 @@ class SlabSystem:
         self._host_headers = torch.zeros((3, 8), dtype=torch.int64)
         if dev.type == "cuda":
             self._host_headers = self._host_headers.pin_memory()
+        self._hh_np = self._host_headers.numpy()  # shares the (pinned) memory
         self.set_capacities(int(ghost_capacity or max(1024, self.cap // 4)),
                             int(migrant_capacity or max(256, self.cap // 16)))
 
@@ -483,11 +484,21 @@ class SlabSystem:
                 w.wait()
         # ---- the one host synchronisation of the step: the counts (they are launch parameters) ----
         hh = self._host_headers
+        if self.device.type == "cuda":
+            # the headers land in pinned memory; the host spins on a sentinel in the LAST one instead of
+            # blocking in cudaStreamSynchronize (whose wake-up costs tens of microseconds of idle GPU)
+            self._hh_np[2, 7] = -1
         hh[0].copy_(self.header_local, non_blocking=True)
         hh[1].copy_(self.recv_lo[0:64].view(torch.int64), non_blocking=True)
         hh[2].copy_(self.recv_up[0:64].view(torch.int64), non_blocking=True)
         if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
+            flag, spins = self._hh_np, 0
+            while flag[2, 7] == -1:  # header word 7 is never written by the kernels: it arrives as 0
+                spins += 1
+                if spins > 20_000_000:
+                    torch.cuda.current_stream(self.device).synchronize()
+                    if flag[2, 7] == -1:
+                        raise RuntimeError("slab exchange: the headers never arrived")
         h = hh.tolist()
         k_lo, k_up, stray = h[0][1], h[0][2], h[0][3]
         a_lo, g_lo, a_up, g_up = h[1][0], h[1][1], h[2][0], h[2][1]
