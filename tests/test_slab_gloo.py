@@ -181,6 +181,15 @@ def _worker(rank, world, port, cfg, out):
                                    dtype=dtype, nmat=cfg["nmat"], cell_size=cfg["cell_size"])
         owned0 = slab.n_own
         slab.compute_force()  # loop-carried state.force of the first step
+        if cfg.get("expect_error"):
+            try:
+                slab.step(cfg["steps"])
+                out.put(("ok", "no error raised", owned0, False))
+            except RuntimeError as e:  # every rank sees the stray flag (its own or a neighbour's header)
+                out.put(("ok", str(e), owned0, True))
+            dist.barrier()
+            dist.destroy_process_group()
+            return
         slab.step(cfg["steps"])
         res = slab.gather(("pos_c", "vel", "force", "torque", "ang_vel"))
         # every owned particle lies in this rank's layers; ghosts only within the halo
@@ -258,3 +267,31 @@ def test_slab_decomposition_matches_single_system(world, dim, law, rot, dtype):
     z0 = inp["pos"][:, -1]
     moved = np.abs(ref.pos_c[:, -1] - z0).max()
     assert moved > 0.5 * inp["box"][-1] / n_layers
+
+
+def test_slab_step_too_large_raises():
+    """A particle that moves further than the halo in one step cannot be handed over by the
+    single neighbour exchange: the exchange reports it (every rank raises) instead of losing it."""
+    dtype = np.float64
+    inp = make_inputs(1200, 3, seed=3, dtype=dtype, phi=0.4)
+    cs = dtype(2.0 * inp["rad"].max())
+    n_layers = int(np.floor(dtype(inp["box"][-1]) / cs))
+    inp["vel"][:] = 0.0
+    lz = float(inp["box"][-1])
+    j = int(np.argmin(np.abs(inp["pos"][:, -1] - 0.25 * lz)))  # a particle in the middle of rank 0's slab ...
+    inp["vel"][j, -1] = 0.5 * lz / 1e-2                        # ... jumps half a box in one step of dt = 1e-2
+    cfg = dict(inp=inp, dtype=dtype, law="spring", rot="", dt=1e-2, steps=1, nmat=1, cell_size=cs,
+               n_layers=n_layers, capacity=1264, expect_error=True)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for g in got:
+        assert g[0] != "err", g[1]
+    # the rank that owned the particle and its neighbour both see the flag
+    assert sum(1 for g in got if g[3] and "further than the halo" in g[1]) == 2, got
