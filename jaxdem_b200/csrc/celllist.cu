@@ -185,11 +185,12 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      pc[d] = c.pos_c[gidx * D + d];
-      pr[d] = c.pos_p_rot[gidx * D + d];
+      pc[d] = __ldcs(&c.pos_c[gidx * D + d]);  // State leaves are streamed once: evict-first, so the
+      // shadow records written below stay in L2 for k_scatter / k_finalize / the pair kernel
+      pr[d] = __ldcs(&c.pos_p_rot[gidx * D + d]);
       if (MODE != 0) {
-        f[d] = c.force[gidx * D + d];
-        v[d] = c.vel[gidx * D + d];
+        f[d] = __ldcs(&c.force[gidx * D + d]);
+        v[d] = __ldcs(&c.vel[gidx * D + d]);
       }
       if (MODE == 2) {
         grav[d] = c.gravity[b * D + d];
@@ -199,22 +200,22 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
         }
       }
     }
-    const F rad = c.rad[gidx];
+    const F rad = __ldcs(&c.rad[gidx]);
     F dt = F(0), mass = F(1);
     bool fixed = false;
     if (MODE != 0) {
       dt = c.dt[b];
-      mass = c.mass[gidx];
-      fixed = c.fixed[gidx] != 0;
+      mass = __ldcs(&c.mass[gidx]);
+      fixed = __ldcs(&c.fixed[gidx]) != 0;
     }
-    for (int w = 0; w < c.W; ++w) bond |= c.bond_id[gidx * c.W + w] >= 0;
+    for (int w = 0; w < c.W; ++w) bond |= __ldcs(&c.bond_id[gidx * c.W + w]) >= 0;
     if (MODE == 3 || MODE == 4) {
       fixed_any = fixed;
 #pragma unroll
       for (int d = 0; d < D; ++d)
-        ext_nz |= (c.ext_force[gidx * D + d] != F(0)) | (c.ext_force_com[gidx * D + d] != F(0));
+        ext_nz |= (__ldcs(&c.ext_force[gidx * D + d]) != F(0)) | (__ldcs(&c.ext_force_com[gidx * D + d]) != F(0));
 #pragma unroll
-      for (int a = 0; a < A; ++a) ext_nz |= c.ext_torque[gidx * A + a] != F(0);
+      for (int a = 0; a < A; ++a) ext_nz |= __ldcs(&c.ext_torque[gidx * A + a]) != F(0);
     }
     const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
     F anchor[3] = {0, 0, 0}, box[3] = {1, 1, 1};
