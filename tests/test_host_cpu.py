@@ -137,3 +137,52 @@ def test_slab_layout_and_key_windows():
     for k in ("mig_f", "mig_i", "gh_f", "gh_i", "bytes"):
         assert L[k] % 16 == 0
     assert L["bytes"] >= 64 + 1000 * (24 * 4 + 24) + 5000 * (11 * 4 + 16)
+
+
+@pytest.mark.parametrize("dim,f64", [(3, False), (3, True), (2, False), (2, True)])
+def test_slab_abi_layout_and_argument_errors(dim, f64):
+    """The C side and the Python side agree on the exchange-message layout byte for byte
+    (jdb200_slab_message_bytes / _kept_bytes vs slab.message_layout), and the slab entry points
+    reject bad descriptors / NULL pointers without touching a device."""
+    from jaxdem_b200.slab import message_layout
+    lib = _lib.lib()
+    d = _lib.SlabDesc()
+    d.n, d.cap_mig, d.cap_ghost, d.dim = 1000, 300, 7000, dim
+    d.dtype = _lib.JDB200_F64 if f64 else _lib.JDB200_F32
+    d.n_layers, d.lo_layer, d.up_layer, d.search_range = 40, 10, 20, 1
+    fb = 8 if f64 else 4
+    assert lib.jdb200_slab_message_bytes(ctypes.byref(d)) == message_layout(dim, fb, 300, 7000)["bytes"]
+    assert lib.jdb200_slab_kept_bytes(ctypes.byref(d)) == message_layout(dim, fb, 0, 600)["bytes"]
+    assert lib.jdb200_slab_scratch_bytes(ctypes.byref(d)) >= 1000 + 4 * 8 * 4
+    assert lib.jdb200_slab_holes_bytes(ctypes.byref(d)) >= 4 * 300 * 4
+    rows = _lib.SlabRows()
+    # NULL messages / buffers
+    assert lib.jdb200_slab_pack(None, ctypes.byref(d), ctypes.byref(rows), None, None, None, None, None, None, 0) == -2
+    cnt = (ctypes.c_int64 * 7)(0, 0, 0, 0, 0, 0, 0)
+    assert lib.jdb200_slab_unpack(None, ctypes.byref(d), ctypes.byref(rows), cnt, None, None, None, None) == -2
+    # bad descriptors
+    d.lo_layer, d.up_layer = 20, 10
+    assert lib.jdb200_slab_message_bytes(ctypes.byref(d)) == 0
+    assert lib.jdb200_slab_pack(None, ctypes.byref(d), ctypes.byref(rows), None, None, None, None, None, None, 0) == -1
+    d.lo_layer, d.up_layer, d.dim = 10, 20, 4
+    assert lib.jdb200_slab_scratch_bytes(ctypes.byref(d)) == 0
+
+
+def test_params_argument_errors_of_new_fields():
+    """key_window_* validation (check_params) and the fused force+after entry point's
+    configuration check run on the host, before any launch."""
+    lib = _lib.lib()
+    st = jd.utils.grid_state(n_per_axis=(6, 6, 6), spacing=1.0, radius=0.5, device="cpu")
+    sy = jd.System.create(st.shape, collider_type="CellList", collider_kw=dict(state=st), domain_type="periodic",
+                          domain_kw=dict(box_size=[6.0] * 3), device="cpu")
+    p = _call.params_for(st, sy)
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) > 0
+    p.key_window_lo[0], p.key_window_len[0] = 0, 100      # two windows need a first window of k * 4096 rows
+    p.key_window_lo[1], p.key_window_len[1] = 4096, 50
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
+    p.key_window_len[0] = 4096
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) > 0
+    p.key_window_lo[1] = 100                              # overlapping / descending windows
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
+    p.key_window_lo[1], p.key_window_len[0] = 4096, -1
+    assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
