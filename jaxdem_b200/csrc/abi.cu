@@ -43,7 +43,6 @@ template <typename F> int celllist_cross_neighbor_list(cudaStream_t, Ctx<F>&, co
 template <typename F> int naive_force(cudaStream_t, Ctx<F>&);
 template <typename F> int naive_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int force_manager_apply(cudaStream_t, Ctx<F>&);
-template <typename F> int fm_after_fused(cudaStream_t, Ctx<F>&, bool);
 template <typename F> int domain_apply(cudaStream_t, Ctx<F>&);
 template <typename F> int refresh_inv_box(cudaStream_t, Ctx<F>&);
 template <typename F> int linear_before(cudaStream_t, Ctx<F>&);

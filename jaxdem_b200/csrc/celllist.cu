@@ -151,9 +151,6 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 // K1  cell hash (+ dense histogram with arrival rank), optionally fused with the
 // linear velocity-Verlet updates of the fused step driver (sphere systems):
 //   MODE 0  hash only                                  (collider hooks)
-//   MODE 1  VelocityVerlet.step_before_force, then hash (first step of the driver)
-//   MODE 2  ForceManager.apply (spheres) + VelocityVerlet.step_after_force of the previous
-//           step, then step_before_force of this one, then hash
 //   MODE 3  fused driver: step_before_force, then hash; the kicked velocity goes to the
 //           (vx, vy, vz, mass) shadow record instead of State.vel (the pair kernel's epilogue
 //           writes the final velocity), and the external buffers / fixed flags are scanned
@@ -161,12 +158,10 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 //   MODE 4  slab driver: the drift was done before the neighbour exchange; hash only, but
 //           with the shadow record and the scans of MODE 3, so that the pair kernel's fused
 //           epilogue (force manager + step_after_force) can follow
-// EXT: the force manager reads and clears the external buffers (first application
-// after the call was entered); otherwise they are known to be zero.
 // References: velocity_verlet.py:57-61,92-95; force_manager.py:359-423;
 // cell_list.py:51-62; state.py:295-304.
 // ---------------------------------------------------------------------------
-template <typename F, int D, int MODE, bool EXT>
+template <typename F, int D, int MODE>
 __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ cell_size_override) {
   pdl_prologue();
   using T = RT<F>;
@@ -182,7 +177,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     // ---- all loads first (stores below may alias as far as the compiler knows) ----
     const GridInfo<I> g = c.gi[b];
     F pc[3] = {0, 0, 0}, pr[3] = {0, 0, 0}, f[3] = {0, 0, 0}, v[3] = {0, 0, 0};
-    F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       pc[d] = __ldcs(&c.pos_c[gidx * D + d]);  // State leaves are streamed once: evict-first, so the
@@ -191,13 +185,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       if (MODE != 0) {
         f[d] = __ldcs(&c.force[gidx * D + d]);
         v[d] = __ldcs(&c.vel[gidx * D + d]);
-      }
-      if (MODE == 2) {
-        grav[d] = c.gravity[b * D + d];
-        if (EXT) {
-          fp[d] = c.ext_force[gidx * D + d];
-          fc[d] = c.ext_force_com[gidx * D + d];
-        }
       }
     }
     const F rad = __ldcs(&c.rad[gidx]);
@@ -230,12 +217,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
       const F free = fixed ? F(0) : F(1);
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        if (MODE == 2) {
-          // ForceManager.apply, clump_id == arange(N): count == 1, segment ops are identities
-          const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
-          f[d] = T::add(T::add(f[d], fp[d]), fcom);
-          v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_after_force of the previous step
-        }
         v[d] = T::add(v[d], T::mul(T::mul(f[d], sc), free));  // step_before_force: kick ...
         pc[d] = T::add(pc[d], T::mul(dt, v[d]));              // ... and drift
       }
@@ -261,15 +242,6 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     }
     const size_t us = (MODE == 3 || MODE == 4) ? 2 : 1;  // fused flows interleave (pos, rad) and (vel, mass)
     if (MODE == 3 || MODE == 4) c.urec[2 * gidx + 1] = Vec4<F>{v[0], v[1], v[2], mass};
-    if (MODE == 2 && EXT) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        c.ext_force[gidx * D + d] = F(0);
-        c.ext_force_com[gidx * D + d] = F(0);
-      }
-#pragma unroll
-      for (int a = 0; a < A; ++a) c.ext_torque[gidx * A + a] = F(0);
-    }
     c.key[gidx] = key;
     c.urec[us * gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
@@ -584,12 +556,10 @@ static int coop_grid_limit(const void* fn, int block) {
 template <typename F, int D>
 static int launch_hash(cudaStream_t s, Ctx<F>& c, const F* cso, int mode, bool ext) {
   const dim3 grid(cdiv(c.n, 256), c.batch);
-  if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0, false>), grid, 256, s, c, cso);
-  else if (mode == 1) JDB_LAUNCH((k_hash<F, D, 1, false>), grid, 256, s, c, cso);
-  else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3, false>), grid, 256, s, c, cso);
-  else if (mode == 4) JDB_LAUNCH((k_hash<F, D, 4, false>), grid, 256, s, c, cso);
-  else if (ext) JDB_LAUNCH((k_hash<F, D, 2, true>), grid, 256, s, c, cso);
-  else JDB_LAUNCH((k_hash<F, D, 2, false>), grid, 256, s, c, cso);
+  if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0>), grid, 256, s, c, cso);
+  else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3>), grid, 256, s, c, cso);
+  else if (mode == 4) JDB_LAUNCH((k_hash<F, D, 4>), grid, 256, s, c, cso);
+  else return JDB200_EINVAL;
   return 0;
 }
 

@@ -429,83 +429,6 @@ __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
   }
 }
 
-// Fused-driver epilogue for sphere systems: ForceManager.apply (force_manager.py:359-423 with
-// clump_id == arange(N)) + VelocityVerlet.step_after_force (velocity_verlet.py:92-95) in one
-// pass.  EXT = false: the external buffers are known to be zero (cleared earlier in the call).
-template <typename F, int D, bool EXT>
-__global__ void __launch_bounds__(256) k_fm_after(Ctx<F> c) {
-  pdl_prologue();
-  using T = RT<F>;
-  constexpr int A = D == 3 ? 3 : 1;
-  const int b = blockIdx.y;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
-  const size_t gi = (size_t)b * c.n + i;
-  // ---- all loads first (the stores below may alias as far as the compiler knows) ----
-  const F mass = c.mass[gi], dt = c.dt[b];
-  const bool fixed = c.fixed[gi] != 0;
-  F fo[3] = {0, 0, 0}, v[3] = {0, 0, 0}, fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0};
-  F grav[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, et[3] = {0, 0, 0};
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    fo[d] = c.force[gi * D + d];
-    v[d] = c.vel[gi * D + d];
-    grav[d] = c.gravity[b * D + d];
-    if (EXT) {
-      fp[d] = c.ext_force[gi * D + d];
-      fc[d] = c.ext_force_com[gi * D + d];
-      r[d] = c.pos_p_rot[gi * D + d];
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < A; ++a) {
-    tq[a] = c.torque[gi * A + a];
-    if (EXT) et[a] = c.ext_torque[gi * A + a];
-  }
-  // ---- arithmetic + stores ----
-  const F sc = T::div(T::mul(dt, F(0.5)), mass);
-  const F free = fixed ? F(0) : F(1);
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
-    const F ft = T::add(T::add(fo[d], fp[d]), fcom);
-    c.force[gi * D + d] = ft;
-    c.vel[gi * D + d] = T::add(v[d], T::mul(T::mul(ft, sc), free));
-    if (EXT) {
-      c.ext_force[gi * D + d] = F(0);
-      c.ext_force_com[gi * D + d] = F(0);
-    }
-  }
-  F cr[3] = {0, 0, 0};
-  if (EXT) {
-    if (D == 3) {
-      const V3<F> x = xcross(V3<F>{r[0], r[1], r[2]}, V3<F>{fp[0], fp[1], fp[2]});
-      cr[0] = x.x; cr[1] = x.y; cr[2] = x.z;
-    } else {
-      cr[0] = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < A; ++a) {
-    c.torque[gi * A + a] = T::add(tq[a], T::add(et[a], cr[a]));
-    if (EXT) c.ext_torque[gi * A + a] = F(0);
-  }
-}
-
-template <typename F>
-int fm_after_fused(cudaStream_t s, Ctx<F>& c, bool ext) {
-  if (c.n == 0) return 0;
-  const dim3 gp(cdiv(c.n, 256), c.batch);
-  if (c.dim == 3) {
-    if (ext) JDB_LAUNCH((k_fm_after<F, 3, true>), gp, 256, s, c);
-    else JDB_LAUNCH((k_fm_after<F, 3, false>), gp, 256, s, c);
-  } else {
-    if (ext) JDB_LAUNCH((k_fm_after<F, 2, true>), gp, 256, s, c);
-    else JDB_LAUNCH((k_fm_after<F, 2, false>), gp, 256, s, c);
-  }
-  return 0;
-}
-
 template <typename F>
 int force_manager_apply(cudaStream_t s, Ctx<F>& c) {
   if (c.n == 0) return 0;
@@ -995,7 +918,6 @@ int rotation_after(cudaStream_t s, Ctx<F>& c) {
 
 #define JDB_INST(F)                                                   \
   template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
-  template int fm_after_fused<F>(cudaStream_t, Ctx<F>&, bool);        \
   template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
   template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \
   template int linear_before<F>(cudaStream_t, Ctx<F>&);               \
