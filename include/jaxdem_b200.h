@@ -9,8 +9,11 @@
  * Rules every entry point obeys:
  *  - stream-ordered and asynchronous: work is enqueued on `stream`, the call
  *    never synchronises with the host, never allocates, never throws, and
- *    touches no global mutable state => legal inside jit / lax.scan /
- *    lax.fori_loop and CUDA-graph capture, re-entrant across threads;
+ *    keeps no state of the data path in globals => legal inside jit / lax.scan /
+ *    lax.fori_loop and CUDA-graph capture, re-entrant across threads.  (The only
+ *    globals are diagnostic: a relaxed launch counter and, while
+ *    jdb200_timing_enable(1) is on, a mutex-guarded list of timing events;
+ *    neither influences any result);
  *  - all buffers are caller-owned DEVICE pointers, dense row-major, exactly
  *    the State / System pytree leaves of the reference (jaxdem/state.py:103-228),
  *    with an optional leading batch axis of size `params.batch` (vmap);
@@ -39,7 +42,7 @@
 extern "C" {
 #endif
 
-#define JDB200_ABI_VERSION 1
+#define JDB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define JDB200_API __attribute__((visibility("default")))
@@ -94,7 +97,17 @@ typedef struct jdb200_params {
   int32_t grid_mode;      /* JDB200_GRID_* */
   int32_t clumps;         /* 0: caller promises clump_id == arange(N) (spheres only; the
                              clump reductions are identities), 1: general clump ids */
+  int32_t promises;       /* JDB200_PROMISE_* bits: facts about the VALUES of some leaves that the caller
+                             knows on the host (it created the arrays) and that let the kernels skip whole
+                             streams.  0 is always legal; a broken promise gives wrong results, not a crash. */
 } jdb200_params;
+
+/* jdb200_params.promises */
+#define JDB200_PROMISE_NO_EXT 1    /* external_force / external_force_com / external_torque are all zero on entry
+                                      (ForceManager: nothing was added since the last apply cleared them) */
+#define JDB200_PROMISE_NO_BONDS 2  /* every bond_id entry is -1 */
+#define JDB200_PROMISE_NO_FIXED 4  /* no particle is fixed */
+#define JDB200_PROMISE_NO_POS_P 8  /* pos_p == 0, hence pos_p_rot == 0 and pos == pos_c (sphere systems) */
 
 /* State leaves (jaxdem/state.py:103-228).  F = float/double, I = int32/int64.
  * A = 3 in 3D, 1 in 2D.  NULL is allowed for leaves an entry point does not use. */
@@ -231,6 +244,24 @@ JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const j
  * no host round trip.  Identity user pre/post hooks only. */
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
                        const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps);
+
+/* ---- trajectory output: the default save_fn of System.trajectory_rollout ------------------- */
+/* Replaces the per-frame copy of the State pytree (jaxdem/system.py:55-57 `_save_state_system`, stacked by the
+ * scan of `_trajectory_rollout`, :101-120).  One launch packs the selected leaves of a frame into a contiguous
+ * record per system, (B, frame_len) F, in the order pos_c (N,D) | vel (N,D) | force (N,D) | ang_vel (N,A) |
+ * torque (N,A) | q_w (N) | q_xyz (N,3) | pos = pos_c + pos_p_rot (N,D); `fields` bit f selects the f-th of them
+ * (JDB200_FRAME_*).  `out` may be a slot of a device ring buffer that the caller drains to pinned host memory on a
+ * second stream (jaxdem_b200/system.py FrameRing), or a row of a device-resident trajectory. */
+#define JDB200_FRAME_POS_C 1
+#define JDB200_FRAME_VEL 2
+#define JDB200_FRAME_FORCE 4
+#define JDB200_FRAME_ANG_VEL 8
+#define JDB200_FRAME_TORQUE 16
+#define JDB200_FRAME_Q_W 32
+#define JDB200_FRAME_Q_XYZ 64
+#define JDB200_FRAME_POS 128
+JDB200_API int jdb200_frame_pack(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                 const jdb200_system* sys, int32_t fields, void* out);
 
 /* collider.compute_force -> force_manager.apply -> linear_integrator.step_after_force in one
  * call for sphere systems (clumps == 0) with velocity Verlet and no rotation integrator: the

@@ -48,19 +48,28 @@ def params_for(state, system, *, max_neighbors: int = 0) -> L.Params:
         for w, (lo, ln) in enumerate(kw):
             p.key_window_lo[w], p.key_window_len[w] = int(lo), int(ln)
     p.clumps = 1 if state.has_clumps else 0
+    p.promises = state.promise_bits()
+    fm = getattr(system, "force_manager", None)
+    # never baked into a CUDA graph: a replay cannot see forces added after the capture
+    if (fm is not None and fm.buffers_clean() and state.pos_c.device.type == "cuda"
+            and not torch.cuda.is_current_stream_capturing()):
+        p.promises |= L.PROMISE_NO_EXT
     return p
 
 
-def workspace(p: L.Params, device) -> torch.Tensor:
+def workspace(p: L.Params, device, owner=None) -> torch.Tensor:
+    """Scratch for one entry-point call, owned by ``owner`` (the System): no state is shared between Systems or
+    streams.  It grows on demand; an outgrown tensor is only dropped here, so whoever still references it (a
+    captured CUDA graph keeps its own reference, System.compile_step) keeps it alive."""
     nbytes = L.lib().jdb200_workspace_bytes(C.byref(p))
     if nbytes == 0:
         raise RuntimeError("jdb200_workspace_bytes rejected the parameters (JDB200_EINVAL)")
-    key = str(device)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:  # one live workspace per device, grown on demand and reused
-        _WORKSPACES.pop(key, None)
+    store = owner.__dict__ if owner is not None else _WORKSPACES
+    key = "_workspace" if owner is not None else str(device)
+    ws = store.get(key)
+    if ws is None or ws.numel() < nbytes or ws.device != torch.device(device):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
+        store[key] = ws
     return ws
 
 
@@ -97,12 +106,10 @@ def system_view(system) -> L.SystemView:
     v.external_force = fm.external_force.data_ptr()
     v.external_force_com = fm.external_force_com.data_ptr()
     v.external_torque = fm.external_torque.data_ptr()
-    v.mat_young = mt.young.data_ptr()
-    v.mat_poisson = mt.poisson.data_ptr()
-    v.mat_e = mt.e.data_ptr()
-    v.mat_mu = mt.mu.data_ptr()
-    v.mat_mu_r = mt.mu_r.data_ptr()
-    v.mat_young_eff = mt.young_eff.data_ptr()
+    for field, key in (("mat_young", "young"), ("mat_poisson", "poisson"), ("mat_e", "e"), ("mat_mu", "mu"),
+                       ("mat_mu_r", "mu_r"), ("mat_young_eff", "young_eff")):
+        t = getattr(mt, key, None)  # NULL for tables the materials do not define (System.create checked the law's needs)
+        setattr(v, field, None if t is None else t.data_ptr())
     v.time = v.step_count = None  # the caller keeps the clock (jdb200_system_step sets them when asked)
     return v
 
@@ -122,7 +129,7 @@ def call(name: str, state, system, *extra, needs_ws: bool = True, max_neighbors:
         yv.time, yv.step_count = system.time.data_ptr(), system.step_count.data_ptr()
     args = [stream_ptr(state.device), C.byref(p), C.byref(sv), C.byref(yv)]
     if needs_ws:
-        ws = workspace(p, state.device)
+        ws = workspace(p, state.device, system)
         args += [C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())]
     args += [(_ptr(e) if isinstance(e, torch.Tensor) or e is None else e) for e in extra]
     L.check(getattr(lib, name)(*args), name)

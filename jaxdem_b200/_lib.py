@@ -20,6 +20,10 @@ LIN = {"": 0, "verlet": 1, "euler": 2}
 ROT = {"": 0, "verletspiral": 1, "spiral": 2}
 COLLIDER = {"": 0, "celllist": 1, "naive": 2}
 GRID = {"auto": 0, "dense": 1, "sorted": 2}
+# jdb200_params.promises (include/jaxdem_b200.h)
+PROMISE_NO_EXT, PROMISE_NO_BONDS, PROMISE_NO_FIXED, PROMISE_NO_POS_P = 1, 2, 4, 8
+ABI_VERSION = 2
+FRAME_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "q_w", "q_xyz", "pos")  # bit f of jdb200_frame_pack's `fields`
 ERRORS = {-1: "JDB200_EINVAL (bad params)", -2: "JDB200_ENULL (NULL pointer)",
           -3: "JDB200_EWORKSPACE (workspace too small)", -4: "JDB200_ECUDA (kernel launch failed)"}
 
@@ -32,6 +36,7 @@ class Params(C.Structure):
         ("collider", C.c_int32), ("linear_integrator", C.c_int32), ("rotation_integrator", C.c_int32),
         ("stencil_m", C.c_int32), ("bond_width", C.c_int32), ("n_materials", C.c_int32),
         ("max_neighbors", C.c_int32), ("grid_mode", C.c_int32), ("clumps", C.c_int32),
+        ("promises", C.c_int32),
     ]
 
 
@@ -90,6 +95,7 @@ SYMBOLS = {
     "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
     "jdb200_celllist_force_step_after": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_frame_pack": (C.c_int, [_V, _PP, _PS, _PY, C.c_int32, _V]),
     "jdb200_slab_message_bytes": (_SZ, [_PD]),
     "jdb200_slab_kept_bytes": (_SZ, [_PD]),
     "jdb200_slab_scratch_bytes": (_SZ, [_PD]),
@@ -116,6 +122,9 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if a declared symbol is missing
             fn.restype, fn.argtypes = res, args
+        if handle.jdb200_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {handle.jdb200_abi_version()}, this package expects "
+                               f"{ABI_VERSION}: rebuild it (make -C jaxdem_b200/csrc)")
         _lib = handle
     return _lib
 

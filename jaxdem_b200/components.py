@@ -414,17 +414,52 @@ class ForceManager:
         batch = state_shape[0] if len(state_shape) == 3 else None
         g = torch.zeros(dim) if gravity is None else gravity
         z = lambda *s: torch.zeros(s, dtype=dtype, device=device)
-        return ForceManager(_leaf(g, dtype, device, batch, (dim,)), z(*state_shape), z(*state_shape),
-                            z(*state_shape[:-1], A))
+        fm = ForceManager(_leaf(g, dtype, device, batch, (dim,)), z(*state_shape), z(*state_shape),
+                          z(*state_shape[:-1], A))
+        fm.mark_clean()
+        return fm
+
+    # -- host-side knowledge "the three external buffers are all zero" (jdb200_params.promises) ----------
+    def _versions(self):
+        return tuple((t.data_ptr(), t._version) for t in (self.external_force, self.external_force_com,
+                                                           self.external_torque))
+
+    def buffers_clean(self) -> bool:
+        """True when nothing was added since the buffers were created as zeros or last cleared by ``apply``
+        (any torch-side in-place edit bumps the tensors' version counters)."""
+        return getattr(self, "_clean_at", None) == self._versions()
+
+    def mark_clean(self) -> None:
+        """Called after an entry point that runs ForceManager.apply (which zeroes the buffers on the device)."""
+        self._clean_at = self._versions()
+
+    @staticmethod
+    def _member_count(state):
+        """count = bincount(clump_id)[clump_id] (force_manager.py:227-228)."""
+        cid = state.clump_id.long()
+        cnt = torch.zeros_like(cid).scatter_add_(-1, cid, torch.ones_like(cid))
+        return torch.gather(cnt, -1, cid).to(state.dtype)
 
     @staticmethod
     def add_force(state, system, force, *, is_com=False):
+        """ForceManager.add_force (force_manager.py:196-232): a COM force is shared out over the members of the
+        clump, because ``apply`` segment-sums the buffer over each clump without dividing."""
         fm = system.force_manager
-        (fm.external_force_com if is_com else fm.external_force).add_(force)
+        force = torch.as_tensor(force, dtype=state.dtype, device=state.device)
+        if is_com:
+            if state.has_clumps:
+                force = force / ForceManager._member_count(state)[..., None]
+            fm.external_force_com.add_(force)
+        else:
+            fm.external_force.add_(force)
         return system
 
     @staticmethod
     def add_torque(state, system, torque):
+        """ForceManager.add_torque (force_manager.py:270-303): divided by the member count like a COM force."""
+        torque = torch.as_tensor(torque, dtype=state.dtype, device=state.device)
+        if state.has_clumps:
+            torque = torque / ForceManager._member_count(state)[..., None]
         system.force_manager.external_torque.add_(torque)
         return system
 
@@ -432,4 +467,5 @@ class ForceManager:
     def apply(state, system):
         """-> jdb200_force_manager_apply (force_manager.py:338-425)."""
         _call.call("jdb200_force_manager_apply", state, system)
+        system.force_manager.mark_clean()
         return state, system

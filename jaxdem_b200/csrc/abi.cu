@@ -49,6 +49,7 @@ template <typename F> int linear_before(cudaStream_t, Ctx<F>&);
 template <typename F> int linear_after(cudaStream_t, Ctx<F>&);
 template <typename F> int rotation_before(cudaStream_t, Ctx<F>&);
 template <typename F> int rotation_after(cudaStream_t, Ctx<F>&);
+template <typename F> int frame_pack(cudaStream_t, Ctx<F>&, int, void*);
 
 // ---- partition outputs for parity checks -------------------------------------
 template <typename F>
@@ -367,6 +368,16 @@ JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_param
     c.fused = 1;
     return celllist_force<F>(s, c, 4, false, true);
   }
+}
+
+JDB200_API int jdb200_frame_pack(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                 const jdb200_system* sys, int32_t fields, void* out) {
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  JDB_ENTER(false)
+  (void)ws_bytes;
+  if (!out || fields < 0 || fields > 255) return fields < 0 || fields > 255 ? JDB200_EINVAL : JDB200_ENULL;
+  JDB_DISPATCH(frame_pack<F>(s, c, fields, out))
 }
 
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,

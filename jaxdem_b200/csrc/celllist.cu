@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     for (int d = 0; d < D; ++d) {
       pc[d] = __ldcs(&c.pos_c[gidx * D + d]);  // State leaves are streamed once: evict-first, so the
       // shadow records written below stay in L2 for k_scatter / k_finalize / the pair kernel
-      pr[d] = __ldcs(&c.pos_p_rot[gidx * D + d]);
+      if (!(c.promises & JDB200_PROMISE_NO_POS_P)) pr[d] = __ldcs(&c.pos_p_rot[gidx * D + d]);
       if (MODE != 0) {
         f[d] = __ldcs(&c.force[gidx * D + d]);
         v[d] = __ldcs(&c.vel[gidx * D + d]);
@@ -193,16 +193,20 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     if (MODE != 0) {
       dt = c.dt[b];
       mass = __ldcs(&c.mass[gidx]);
-      fixed = __ldcs(&c.fixed[gidx]) != 0;
+      if (!(c.promises & JDB200_PROMISE_NO_FIXED)) fixed = __ldcs(&c.fixed[gidx]) != 0;
     }
-    for (int w = 0; w < c.W; ++w) bond |= __ldcs(&c.bond_id[gidx * c.W + w]) >= 0;
+    // streams the caller vouches for (jdb200_params.promises) are not read at all
+    if (!(c.promises & JDB200_PROMISE_NO_BONDS))
+      for (int w = 0; w < c.W; ++w) bond |= __ldcs(&c.bond_id[gidx * c.W + w]) >= 0;
     if (MODE == 3 || MODE == 4) {
       fixed_any = fixed;
+      if (!(c.promises & JDB200_PROMISE_NO_EXT)) {
 #pragma unroll
-      for (int d = 0; d < D; ++d)
-        ext_nz |= (__ldcs(&c.ext_force[gidx * D + d]) != F(0)) | (__ldcs(&c.ext_force_com[gidx * D + d]) != F(0));
+        for (int d = 0; d < D; ++d)
+          ext_nz |= (__ldcs(&c.ext_force[gidx * D + d]) != F(0)) | (__ldcs(&c.ext_force_com[gidx * D + d]) != F(0));
 #pragma unroll
-      for (int a = 0; a < A; ++a) ext_nz |= __ldcs(&c.ext_torque[gidx * A + a]) != F(0);
+        for (int a = 0; a < A; ++a) ext_nz |= __ldcs(&c.ext_torque[gidx * A + a]) != F(0);
+      }
     }
     const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
     F anchor[3] = {0, 0, 0}, box[3] = {1, 1, 1};
@@ -296,8 +300,29 @@ __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
   if (too_many) g.dense_fail = 1;
 }
 
-// K2b  dense: place particle i at cell_start[h] + arrival rank (order inside a
-// cell is fixed up by k_finalize).
+// K2b  dense: place particle i at cell_start[h] + arrival rank (order inside a cell is fixed
+// up by k_finalize).  The particle's (x, y, z, rad) record travels with it: ONE 256-bit store
+// per particle (f32: the record, the index and the key share a 32-byte sector) — a random
+// access costs the L1TEX pipe the same 32 wavefronts per warp whatever its width, so the
+// record is moved here, once, instead of being gathered again by k_finalize.
+__device__ __forceinline__ void st256(void* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                      float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(a4), "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
+__device__ __forceinline__ void st256(void* p, double a0, double a1, double a2, double a3) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a0), "d"(a1), "d"(a2), "d"(a3) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, float* a) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld256(const void* p, double* a) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a[0]), "=d"(a[1]), "=d"(a[2]), "=d"(a[3]) : "l"(p));
+}
+
 template <typename F>
 __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   pdl_prologue();
@@ -309,8 +334,15 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   if (!use_dense(g)) return;
   const size_t gidx = (size_t)b * c.n + i;
   const int key = (int)c.key[gidx];
+  const Vec4<F> p = c.urec[(c.fused ? 2 : 1) * gidx];
   const size_t slot = (size_t)b * c.n + c.cell_start[(size_t)b * c.cell_stride + key] + c.rank[gidx];
-  c.slot_rec[slot] = make_int2((int)i, key);  // one 8-byte store: half the partial sectors of two 4-byte stores
+  if (sizeof(F) == 4) {
+    st256(c.arec + 32 * slot, (float)p.x, (float)p.y, (float)p.z, (float)p.w, __int_as_float((int)i),
+          __int_as_float(key), 0.f, 0.f);
+  } else {
+    st256(c.arec + 32 * slot, (double)p.x, (double)p.y, (double)p.z, (double)p.w);
+    c.slot_rec[slot] = make_int2((int)i, key);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -498,17 +530,38 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   int i;
   long long dest;
   bool dense = use_dense(g);
+  Vec4<F> mine = Vec4<F>{0, 0, 0, 0};
   if (dense) {
     const int* cs = c.cell_start + (size_t)b * c.cell_stride;
-    const int2* __restrict__ tmp = c.slot_rec + off;
-    const int2 me = tmp[k];
-    i = me.x;
-    const int key = me.y;
+    int key;
+    if (sizeof(F) == 4) {
+      float a[8];
+      ld256(c.arec + 32 * (off + k), a);
+      mine = Vec4<F>{(F)a[0], (F)a[1], (F)a[2], (F)a[3]};
+      i = __float_as_int(a[4]);
+      key = __float_as_int(a[5]);
+    } else {
+      double a[4];
+      ld256(c.arec + 32 * (off + k), a);
+      mine = Vec4<F>{(F)a[0], (F)a[1], (F)a[2], (F)a[3]};
+      const int2 me = c.slot_rec[off + k];
+      i = me.x;
+      key = me.y;
+    }
     c.tmp_key[off + k] = key;  // cells stay in place: the key of arrival slot k is the key of final slot k
     const int s = cs[key], e = cs[key + 1];
     int r = 0;
-    for (int kk = s; kk < e; ++kk) r += tmp[kk].x < i;
+    if (e - s > 1) {  // rank = members of the cell with a smaller original index
+      if (sizeof(F) == 4) {
+        const int* ids = reinterpret_cast<const int*>(c.arec + 32 * off) + 4;
+        for (int kk = s; kk < e; ++kk) r += ids[8 * (size_t)kk] < i;
+      } else {
+        const int2* __restrict__ tmp = c.slot_rec + off;
+        for (int kk = s; kk < e; ++kk) r += tmp[kk].x < i;
+      }
+    }
     dest = s + r;
+    c.inv[off + i] = (int)dest;  // original index -> sorted slot (k_after un-permutes the row kernel's sums)
   } else if (sorted_perm) {
     i = sorted_perm[off + k];
     dest = k;
@@ -523,7 +576,7 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   c.perm[gd] = i;
   if (!dense || c.want_skey) c.skey[gd] = c.key[gi];
   const size_t us = c.fused ? 2 : 1;
-  c.spos[gd] = c.urec[us * gi];
+  c.spos[gd] = dense ? mine : c.urec[us * gi];
   if (c.clumps || g.any_bond) {
     bool has_bond = false;
     if (g.any_bond)
@@ -531,10 +584,11 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
     c.sclump[gd] = (int)c.clump_id[gi] | (has_bond ? 0x80000000 : 0);
   }
   if (c.nmat > 1) c.smat[gd] = (int)c.mat_id[gi];
-  if (c.fused) c.svel[gd] = c.urec[2 * gi + 1];
+  // (the fused flows keep the kicked velocity in the original-order record urec[2 i + 1]: k_after reads it there)
   if (c.law == JDB200_LAW_CUNDALLSTRACK) {
     const F* v = c.vel + gi * c.dim;
-    if (!c.fused) c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};
+    if (c.fused) c.svel[gd] = c.urec[2 * gi + 1];
+    else c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};
     const F* w = c.ang_vel + gi * c.A;
     c.sang[gd] = c.dim == 3 ? Vec4<F>{w[0], w[1], w[2], F(0)} : Vec4<F>{F(0), F(0), w[0], F(0)};
   }

@@ -13,6 +13,7 @@ struct Ctx {
   long long cell_stride;  // ints per system in the dense cell tables (max_cells + 1 rounded up to 64)
   int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
   long long win_lo[2], win_len[2];  // dense cell-table windows in use (jdb200_params.key_window_*; len 0: whole table)
+  int promises;  // jdb200_params.promises (JDB200_PROMISE_*)
   int fused;  // fused sphere step driver (abi.cu system_step): hash kernel integrates, pair kernel finishes the step
   // state (in place)
   F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;
@@ -41,6 +42,12 @@ struct Ctx {
   // (vx, vy, vz, mass) after the before-force kick.  Fused: the two records of a particle are interleaved
   // (stride 2), so the gather of k_finalize touches ONE full 32-byte sector (f32); otherwise stride 1.
   Vec4<F>* urec;
+  // [B*N] 32-byte records in ARRIVAL order (slot = cell_start[key] + arrival rank), written by k_scatter with ONE
+  // 256-bit store per particle: f32 (x, y, z, rad, index, key, 0, 0); f64 (x, y, z, rad) with (index, key) in slot_rec
+  char* arec;
+  int* inv;                    // [B*N] sorted slot of original particle i (k_finalize, dense path; aliases perm_b)
+  Vec4<F>* sforce;             // [B*N] sorted-order contact force sums of the row kernel (aliases segf)
+  Vec4<F>* storque;            // [B*N] sorted-order contact torque sums (aliases segf2)
   unsigned* coop_bar;          // [4] software state of the cooperative sort fallback
   int want_skey;               // host flag: dense builds also fill skey (partition export)
   unsigned long long* tile_state;  // [B*scan_tiles] decoupled look-back descriptors
@@ -88,12 +95,13 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.tmp_key = b.take<int>(BN);
   c.slot_rec = b.take<int2>(BN);
   c.urec = b.take<Vec4<F>>(2 * BN);
+  c.arec = b.take<char>(32 * BN);
   c.coop_bar = b.take<unsigned>(4);
   c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);
   c.tile_counter = b.take<int>(B);
   c.radix_counts = b.take<int>(B * 256 * (size_t)c.radix_blocks);
   c.radix_skip = b.take<int>(B);
-  c.spos = b.take<Vec4<F>>(BN);
+  c.spos = b.take<Vec4<F>>(BN + 8);  // the row kernel loads up to kU records past the end of a run
   c.svel = b.take<Vec4<F>>(BN);
   c.sang = b.take<Vec4<F>>(BN);
   c.sclump = b.take<int>(BN);
@@ -105,6 +113,9 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start_clump = b.take<int>(B * (N + 1));
   c.tile_state_clump = b.take<unsigned long long>(B * (size_t)cdiv(c.n + 1, kScanTile));
   c.tile_counter_clump = b.take<int>(B);
+  c.inv = c.perm_b;
+  c.sforce = reinterpret_cast<Vec4<F>*>(c.segf);
+  c.storque = reinterpret_cast<Vec4<F>*>(c.segf2);
   return b.off + 256;
 }
 
@@ -127,6 +138,7 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
   c.K = p->max_neighbors;
   c.grid_mode = p->grid_mode;
   c.clumps = p->clumps;
+  c.promises = p->promises;
   c.lin = p->linear_integrator;
   for (int w = 0; w < 2; ++w) {
     c.win_lo[w] = p->key_window_lo[w];

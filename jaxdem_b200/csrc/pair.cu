@@ -393,41 +393,38 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.svel[off + k], vis.idx, vis.f, vis.t, with_torque != 0);
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.urec[2 * (off + vis.idx) + 1], vis.idx, vis.f, vis.t, with_torque != 0);
   else store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
 }
 
 
 // ---------------------------------------------------------------------------
-// K4 main path: flat candidate walk.  Serves the systems whose partition is a dense table
-// with the default 3^D stencil (flat_walk_ok).  One thread owns one particle (sorted slot k):
-//   A  the 3^(D-1) stencil rows become slot ranges (x-runs of up to three cells; where the
-//      run wraps around the periodic box the wrapped cells are a range of their own), kept
-//      as (start, length) in a shared-memory column private to the thread; the first line
-//      of every range is prefetched into L1;
-//   B  ONE loop over the concatenated ranges (trip count = number of candidates, so lanes of a
-//      warp stay busy across row boundaries) does nothing but the overlap test
-//      |rij|^2 < (Ri + Rj)^2 and pushes the ordinal of every hit onto a per-thread contact
-//      list in shared memory.  Neighbouring lanes read neighbouring records of the sorted
-//      (x, y, z, rad) array, so the loads of a warp coalesce and hit L1;
-//   C  the contact list is evaluated with the force law: most lanes have work in every
-//      iteration, instead of ~1 lane in 8 when the law sits inside the candidate loop.
-// The kernel keeps registers (<= 64) and shared memory (14.25 KB per 128 threads) low on
-// purpose: it is bound by dependent-issue latency, and 32 resident warps per SM hide it.
-// Candidates are visited rows z-major, slots ascending, wrapped cells after the main run of
-// their row; contacts are summed in that order: deterministic, no atomics, no barriers.
-// EPI 0: DynamicCellList.compute_force epilogue (force / torque stores);
-// EPI 1: fused sphere driver epilogue (fused_sphere_epilogue).
+// K4 main path: the row kernel.  Serves the systems whose partition is a dense table with
+// the default 3^D stencil (flat_walk_ok).  One thread owns one particle (sorted slot k).
+//
+// What bounds this path on B200 is (i) instruction issue and (ii) the SM's single L1TEX
+// pipe, which spends ~2 cycles per 128-byte line a warp-wide access touches: a fully
+// scattered 4-byte store costs a warp as much as 32 coalesced ones.  Hence:
+//   A  the 3^(D-1) stencil rows become slot ranges (x-runs of up to three cells);
+//   B  the first kU = 4 slots of every run are loaded and tested WITHOUT a loop — twelve
+//      independent 16-byte loads in flight per z-plane, ~12 instructions per candidate, hits
+//      recorded as bits of a 36-bit mask; the rare longer runs and the cells that wrap around
+//      the periodic box in x go through a small per-thread list in shared memory;
+//   C  the force law runs only on the hits (exact reference arithmetic, min-image included),
+//      in a fixed order: deterministic, no atomics, no barriers;
+//   D  the sums are stored in SORTED order (one coalesced 16-byte store per thread);
+//      k_after, one thread per ORIGINAL particle, fetches them through the inverse
+//      permutation with one 16-byte gather and finishes the hook (collider epilogue, or
+//      the fused force manager + step_after_force) with coalesced State stores.
 // ---------------------------------------------------------------------------
 template <int D>
-struct FlatCfg {
+struct RowsCfg {
   static constexpr int kThreads = 128;
   static constexpr int kRows = D == 3 ? 9 : 3;
-  static constexpr int kRanges = 2 * kRows;  // main + wrapped range per row
-  static constexpr int kCap = 12;            // contact-list rows; a full list is evaluated and reused
-  static constexpr int kOffLen = kRanges * kThreads * 4;            // u8  [kRanges][kThreads]
-  static constexpr int kOffCl = kOffLen + kRanges * kThreads;       // u32 [kCap][kThreads]: sorted slots of the hits
-  static constexpr int kBytes = kOffCl + kCap * kThreads * 4;       // starts: u32 [kRanges][kThreads] at 0
+  static constexpr int kU = 4;       // slots per stencil row tested without a loop
+  static constexpr int kExtra = 12;  // per-thread list: run tails beyond kU and wrapped cells
+  static constexpr int kOffExtra = kRows * kThreads * 4;           // u32 [kRows][kThreads] run starts at 0
+  static constexpr int kBytes = kOffExtra + kExtra * kThreads * 4;  // u32 [kExtra][kThreads]
 };
 
 // keeps the compiler from folding a base pointer back into per-access 64-bit index arithmetic
@@ -445,8 +442,6 @@ __device__ __forceinline__ Vec4<double> ldg_vec4(const Vec4<double>* p) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(p) + 1);
   return Vec4<double>{u.x, u.y, v.x, v.y};
 }
-// explicit shared-memory accesses (32-bit shared addresses): the hot loop is a handful of
-// instructions per candidate and must not re-derive generic addresses
 __device__ __forceinline__ unsigned lds_u32(unsigned a) {
   unsigned v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -454,41 +449,6 @@ __device__ __forceinline__ unsigned lds_u32(unsigned a) {
 }
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_u8(unsigned a) {
-  unsigned v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_u16(unsigned a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// the overlap test of phase B
-template <typename F, int D, bool PERIODIC>
-__device__ __forceinline__ bool flat_overlap(const LawCtx<F>& lc, const Body<F>& a, const Vec4<F>& q, F hbmin2) {
-  using T = RT<F>;
-  F rx = T::sub(a.x, q.x), ry = T::sub(a.y, q.y), rz = D == 3 ? T::sub(a.z, q.z) : F(0);
-  F d2 = rx * rx + ry * ry + rz * rz;
-  if (PERIODIC && !(d2 < hbmin2)) {  // across the periodic boundary (rare): Domain._displacement
-    rx = T::sub(rx, T::mul(lc.box[0], T::rint(T::mul(rx, lc.inv_box[0]))));
-    ry = T::sub(ry, T::mul(lc.box[1], T::rint(T::mul(ry, lc.inv_box[1]))));
-    if (D == 3) rz = T::sub(rz, T::mul(lc.box[2], T::rint(T::mul(rz, lc.inv_box[2]))));
-    d2 = rx * rx + ry * ry + rz * rz;
-  }
-  const F rs = a.r + q.w;
-  // no overlap => every law returns exactly zero force and torque (the margin keeps pairs
-  // within rounding of touching on the list)
-  return d2 < rs * rs * F(1.00001);
 }
 
 // n / d for 0 <= n < 2^31, d >= 1, with rcp = 1.0f / d: float estimate + exact fix-up
@@ -501,200 +461,230 @@ __device__ __forceinline__ int div_fix(int n, int d, float rcp, int& rem) {
   return q;
 }
 
-template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE, int EPI>
-__device__ __forceinline__ void pair_flat_body(const Ctx<F>& c, int b, int k,
-                                               const GridInfo<typename RT<F>::I>& g, int with_torque,
-                                               unsigned sbase) {
+// candidate test of phase B: a hit is anything the exact law could turn into a non-zero force
+// (|rij|^2 < (Ri + Rj)^2 with a margin for rounding) or whose minimum image is not the plain
+// difference (pairs across the periodic seam: rare, decided exactly in phase C)
+template <typename F, int D, bool PERIODIC>
+__device__ __forceinline__ unsigned rows_hit(const Body<F>& a, const Vec4<F>& q, F hbmin2) {
+  const F rx = a.x - q.x, ry = a.y - q.y, rz = D == 3 ? a.z - q.z : F(0);
+  const F d2 = rx * rx + ry * ry + rz * rz;
+  const F rs = a.r + q.w;
+  // branch-free: both comparisons are evaluated and combined as integers
+  unsigned hit = (unsigned)(d2 < rs * rs * F(1.00001));
+  if (PERIODIC) hit |= (unsigned)!(d2 < hbmin2);
+  return hit;
+}
+
+template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
+__device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
+                                               const GridInfo<typename RT<F>::I>& g, unsigned sbase, F* f,
+                                               F* t) {
   using T = RT<F>;
-  using Cfg = FlatCfg<D>;
+  using Cfg = RowsCfg<D>;
   constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
   constexpr int NZ = D == 3 ? 3 : 1;
+  constexpr int kU = Cfg::kU;
   constexpr unsigned kT = Cfg::kThreads;
   const unsigned tid = threadIdx.x;
-  const unsigned rg0 = sbase + tid * 4;                  // range starts, this thread's column
-  const unsigned ln0 = sbase + Cfg::kOffLen + tid;       // range lengths
-  const unsigned cl0 = sbase + Cfg::kOffCl + tid * 4;    // contact slots
+  const unsigned rs0 = sbase + tid * 4;                    // run starts, this thread's column
+  const unsigned el0 = sbase + Cfg::kOffExtra + tid * 4;   // extra list
   const size_t off = (size_t)b * c.n;
   const Vec4<F>* sp = opaque_ptr(c.spos + off);
   const int* cst = opaque_ptr(c.cell_start + (size_t)b * c.cell_stride);
-  // loads whose latency the range set-up hides: own record, key, index, fused-epilogue record
   const Body<F> a = load_sorted(c, off, k, CS);
-  const int key = c.tmp_key[off + k];  // hash of slot k (k_scatter; the in-cell fix-up keeps cells in place)
-  const int idx = c.perm[off + k];
-  Vec4<F> vm = Vec4<F>{0, 0, 0, 0};
-  if (EPI == 1) vm = c.svel[off + k];
-  const int clump = SIMPLE ? 0 : (c.sclump[off + k] & 0x7fffffff);
-  const bool interact = c.interact && c.interact[b];
-  const LawCtx<F> lc = make_law_ctx(c, b);
-
-  // ---- A: stencil rows -> slot ranges (wrapped / out-of-grid rules of cell_list.py:66-80).
-  // Cell coordinates are decoded from the hash: flat_walk_ok() guarantees that every
-  // coordinate of the system lies in [0, g), so hash <-> coordinates is one-to-one ----
-  unsigned rga = rg0, lna = ln0;
-  int total = 0;
-  {
-    const int gx = (int)g.gd[0], gy = (int)g.gd[1], gz = (int)g.gd[2];
-    const int sy = gx, sz = gx * gy;  // strides of the x-fastest hash (_partition.py:91-93)
-    int cx, cy, cz = 0;
-    const int tq = div_fix(key, gx, __frcp_rn(__int2float_rn(gx)), cx);
-    if (D == 3) cz = div_fix(tq, gy, __frcp_rn(__int2float_rn(gy)), cy);
-    else cy = tq;
-    // main x segment: the cells of [cx - 1, cx + 1] inside the grid; periodic: the cell
-    // outside wraps around to the second segment (the grid has >= 3 cells per axis here)
-    const int x1 = max(cx - 1, 0);
-    const int n1 = min(cx + 1, gx - 1) - x1 + 1;
-    int x2 = -1;
-    if (PERIODIC) x2 = cx == 0 ? gx - 1 : (cx == gx - 1 ? 0 : -1);
-    int yb[3], zb[3];  // ny * stride_y, nz * stride_z; -1: row outside a non-periodic grid
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int ny = cy + j - 1;
-      if (PERIODIC) yb[j] = wrap1(ny, gy) * sy;
-      else yb[j] = (ny >= 0 && ny < gy) ? ny * sy : -1;
-      const int nz = cz + j - 1;
-      if (D != 3) zb[j] = 0;
-      else if (PERIODIC) zb[j] = wrap1(nz, gz) * sz;
-      else zb[j] = (nz >= 0 && nz < gz) ? nz * sz : -1;
-    }
-    int s1[Cfg::kRows], e1[Cfg::kRows];
-#pragma unroll
-    for (int iz = 0; iz < NZ; ++iz) {
-#pragma unroll
-      for (int iy = 0; iy < 3; ++iy) {
-        const int r = iz * 3 + iy;
-        const int zrow = D == 3 ? zb[iz] : 0;
-        const bool ok = PERIODIC || (yb[iy] >= 0 && zrow >= 0);
-        const int h0 = yb[iy] + zrow + x1;
-        s1[r] = ok ? cst[h0] : 0;
-        e1[r] = ok ? cst[h0 + n1] : 0;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < Cfg::kRows; ++r) {
-      if (e1[r] > s1[r]) {
-        sts_u32(rga, (unsigned)s1[r]);
-        sts_u8(lna, (unsigned)(e1[r] - s1[r]));
-        rga += kT * 4;
-        lna += kT;
-        total += e1[r] - s1[r];
-      }
-    }
-    if (PERIODIC && x2 >= 0) {  // boundary lanes: the wrapped cell of every row
-#pragma unroll
-      for (int iz = 0; iz < NZ; ++iz) {
-#pragma unroll
-        for (int iy = 0; iy < 3; ++iy) {
-          const int h2 = yb[iy] + (D == 3 ? zb[iz] : 0) + x2;
-          const int s2 = cst[h2], e2 = cst[h2 + 1];
-          if (e2 > s2) {
-            sts_u32(rga, (unsigned)s2);
-            sts_u8(lna, (unsigned)(e2 - s2));
-            rga += kT * 4;
-            lna += kT;
-            total += e2 - s2;
-          }
-        }
-      }
-    }
-  }
+  const int key = c.tmp_key[off + k];  // hash of slot k (the in-cell fix-up keeps cells in place)
   // |rij|^2 below this => every |rij_d| < box_d / 2 => the minimum-image term is exactly zero
   F hbmin2 = F(0);
   if (PERIODIC) {
-    F m = lc.box[0];
+    F m = c.box[b * D];
 #pragma unroll
-    for (int d = 1; d < D; ++d) m = T::fmin(m, lc.box[d]);
+    for (int d = 1; d < D; ++d) m = T::fmin(m, c.box[b * D + d]);
     m *= F(0.499999);
     hbmin2 = m * m;
   }
-  F f[3] = {0, 0, 0}, t[3] = {0, 0, 0};
 
-  rga = rg0;
-  lna = ln0;
-  int it = 0, kj = 0, ke = 0;
-  while (it < total) {
-    // ---- B: overlap tests, two candidates per trip (both loads in flight together) ----
-    unsigned cla = cl0;
-    const unsigned cle = cl0 + (Cfg::kCap - 1) * kT * 4;  // room for two pushes
-    do {
-      if (kj == ke) {
-        kj = (int)lds_u32(rga);
-        ke = kj + (int)lds_u8(lna);
-        rga += kT * 4;
-        lna += kT;
-      }
-      const int ka = kj++;
-      const bool two = it + 1 < total;
-      if (two && kj == ke) {
-        kj = (int)lds_u32(rga);
-        ke = kj + (int)lds_u8(lna);
-        rga += kT * 4;
-        lna += kT;
-      }
-      const int kb = two ? kj : ka;
-      kj += two ? 1 : 0;
-      const Vec4<F> qa = ldg_vec4(sp + ka);
-      const Vec4<F> qb = ldg_vec4(sp + kb);
-      if (flat_overlap<F, D, PERIODIC>(lc, a, qa, hbmin2)) {
-        sts_u32(cla, (unsigned)ka);
-        cla += kT * 4;
-      }
-      if (flat_overlap<F, D, PERIODIC>(lc, a, qb, hbmin2) && two) {
-        sts_u32(cla, (unsigned)kb);
-        cla += kT * 4;
-      }
-      it += 2;
-    } while (it < total && cla < cle);
-    // ---- C: force law on the contacts (the next contact's record is loaded ahead) ----
-    if (cla != cl0) {
-      int kc = (int)lds_u32(cl0);
-      Vec4<F> q = ldg_vec4(sp + kc);
-      for (unsigned ca = cl0; ca != cla; ca += kT * 4) {
-        const int kcur = kc;
-        const Vec4<F> qc = q;
-        if (ca + kT * 4 != cla) {
-          kc = (int)lds_u32(ca + kT * 4);
-          q = ldg_vec4(sp + kc);
-        }
-        if (SIMPLE) {
-          if (kcur == k) continue;  // clump_id == arange(N): only the particle itself is excluded
-        } else {
-          const int sc = c.sclump[off + kcur];
-          if (!pair_valid(c, off, idx, clump, sc, kcur, interact)) continue;
-        }
-        F rij[3] = {T::sub(a.x, qc.x), T::sub(a.y, qc.y), D == 3 ? T::sub(a.z, qc.z) : F(0)};
-        if (PERIODIC) {
-          const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-          if (!(d2 < hbmin2)) {
+  // ---- A: cell coordinates decoded from the hash (flat_walk_ok(): every coordinate lies in
+  // [0, g), so hash <-> coordinates is one-to-one); wrapped / out-of-grid rules of cell_list.py:66-80 ----
+  const int gx = (int)g.gd[0], gy = (int)g.gd[1], gz = (int)g.gd[2];
+  const int sy = gx, sz = gx * gy;  // strides of the x-fastest hash (_partition.py:91-93)
+  int cx, cy, cz = 0;
+  {
+    const int tq = div_fix(key, gx, __frcp_rn(__int2float_rn(gx)), cx);
+    if (D == 3) cz = div_fix(tq, gy, __frcp_rn(__int2float_rn(gy)), cy);
+    else cy = tq;
+  }
+  // x segment: the cells of [cx - 1, cx + 1] inside the grid; periodic: the cell outside wraps
+  // around and is handled on its own (x2; the grid has >= 3 cells per axis here)
+  const int x1 = max(cx - 1, 0);
+  const int n1 = min(cx + 1, gx - 1) - x1 + 1;
+  int x2 = -1;
+  if (PERIODIC) x2 = cx == 0 ? gx - 1 : (cx == gx - 1 ? 0 : -1);
+  // hash of cell (0, cy + iy - 1, cz + iz - 1) for the kRows stencil rows, parked in this thread's column of
+  // shared memory (the slot is overwritten by the run start once the row is visited); negative: the row lies
+  // outside a non-periodic grid
+  {
+    auto axis_base = [&](int n, int gn, int stride) -> int {
+      if (PERIODIC) return wrap1(n, gn) * stride;
+      return (n >= 0 && n < gn) ? n * stride : (int)0x80000000;  // stays negative after adding the other axis
+    };
+    const int ybs[3] = {axis_base(cy - 1, gy, sy), cy * sy, axis_base(cy + 1, gy, sy)};
+    int zbs[3] = {0, 0, 0};
+    if (D == 3) { zbs[0] = axis_base(cz - 1, gz, sz); zbs[1] = cz * sz; zbs[2] = axis_base(cz + 1, gz, sz); }
 #pragma unroll
-            for (int d = 0; d < D; ++d)
-              rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
-          }
+    for (int r = 0; r < Cfg::kRows; ++r) {
+      const int yb = ybs[r % 3], zb = zbs[r / 3];
+      sts_u32(rs0 + (unsigned)r * (kT * 4), (unsigned)(PERIODIC ? yb + zb : ((yb | zb) < 0 ? -1 : yb + zb)));
+    }
+  }
+
+  // ---- B: candidate tests, one stencil row per trip (the next row's range is loaded ahead) ----
+  unsigned mlo = 0u, mhi = 0u;     // bit r * kU + j of (mhi : mlo): slot (run start of row r) + j is a hit
+  int ne = 0;                      // entries of the extra list
+  bool ovf = false;                // extra list full: the generic walk redoes this particle
+  int s_self = 0;
+  auto push_extra = [&](int kj) {
+    if (ne < Cfg::kExtra) {
+      sts_u32(el0 + (unsigned)ne * (kT * 4), (unsigned)kj);
+      ++ne;
+    } else {
+      ovf = true;
+    }
+  };
+  int hb = (int)lds_u32(rs0);
+  int s_n = hb >= 0 ? cst[hb + x1] : 0;
+  int e_n = hb >= 0 ? cst[hb + x1 + n1] : 0;
+#pragma unroll 1
+  for (int r = 0; r < Cfg::kRows; ++r) {
+    const int s0 = s_n, len = e_n - s_n, hb0 = hb;
+    Vec4<F> q[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) q[j] = ldg_vec4(sp + s0 + j);  // past the run: harmless, masked below
+    if (r + 1 < Cfg::kRows) {  // next row
+      hb = (int)lds_u32(rs0 + (unsigned)(r + 1) * (kT * 4));
+      s_n = hb >= 0 ? cst[hb + x1] : 0;
+      e_n = hb >= 0 ? cst[hb + x1 + n1] : 0;
+    }
+    sts_u32(rs0 + (unsigned)r * (kT * 4), (unsigned)s0);
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      bits |= (rows_hit<F, D, PERIODIC>(a, q[j], hbmin2) & (unsigned)(j < len)) << j;
+    }
+    if (r < 32 / kU) mlo |= bits << (r * kU);
+    else mhi |= bits << (r * kU - 32);
+    if (r == Cfg::kRows / 2) s_self = s0;
+    // run tail (more than kU particles in three cells: dense random packings)
+    if (len > kU) {
+      for (int kj = s0 + kU; kj < s0 + len; ++kj)
+        if (rows_hit<F, D, PERIODIC>(a, ldg_vec4(sp + kj), hbmin2)) push_extra(kj);
+    }
+    // the cell that wraps around the periodic box in x (lanes of the first / last cell of an x-row)
+    if (PERIODIC && x2 >= 0) {
+      const int s2 = cst[hb0 + x2], e2 = cst[hb0 + x2 + 1];
+      for (int kj = s2; kj < e2; ++kj) {
+        const Vec4<F> qq = ldg_vec4(sp + kj);
+        // Domain._displacement (periodic.py:75-79)
+        F rr[3] = {a.x - qq.x, a.y - qq.y, D == 3 ? a.z - qq.z : F(0)};
+        F d2 = F(0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          rr[d] = T::sub(rr[d], T::mul(c.box[b * D + d], T::rint(T::mul(rr[d], c.inv_box[b * D + d]))));
+          d2 += rr[d] * rr[d];
         }
-        Body<F> bj;
-        bj.x = qc.x; bj.y = qc.y; bj.z = qc.z; bj.r = qc.w;
-        bj.mat = (c.nmat > 1) ? c.smat[off + kcur] : 0;
-        if (CS) {
-          const Vec4<F> v = c.svel[off + kcur];
-          const Vec4<F> w = c.sang[off + kcur];
-          bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
-          bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
-        }
-        F ff[3], tt[3];
-        pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
-        f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
-        if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+        const F rs = a.r + qq.w;
+        if (d2 < rs * rs * F(1.00001)) push_extra(kj);
       }
     }
   }
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, vm, idx, f, t, with_torque != 0);
-  else store_force_torque<F, D>(c, off + idx, f, t, g.any_ppr != 0, with_torque != 0);
+  const int idx = SIMPLE ? 0 : c.perm[off + k];
+  const int clump = SIMPLE ? 0 : (c.sclump[off + k] & 0x7fffffff);
+  const bool interact = c.interact && c.interact[b];
+  const LawCtx<F> lc = make_law_ctx(c, b);
+  if (SIMPLE) {  // clump_id == arange(N): only the particle itself is excluded; drop its bit
+    const int js = k - s_self;
+    if (js < kU) mlo &= ~(1u << (Cfg::kRows / 2 * kU + js));
+  }
+
+  // ---- C: the force law on the hits ----
+  f[0] = f[1] = f[2] = F(0);
+  t[0] = t[1] = t[2] = F(0);
+  auto contact = [&](int kcur) {
+    const Vec4<F> qc = ldg_vec4(sp + kcur);
+    if (SIMPLE) {
+      if (kcur == k) return;
+    } else {
+      const int sc = c.sclump[off + kcur];
+      if (!pair_valid(c, off, idx, clump, sc, kcur, interact)) return;
+    }
+    F rij[3] = {T::sub(a.x, qc.x), T::sub(a.y, qc.y), D == 3 ? T::sub(a.z, qc.z) : F(0)};
+    if (PERIODIC) {
+      const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+      if (!(d2 < hbmin2)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          rij[d] = T::sub(rij[d], T::mul(lc.box[d], T::rint(T::mul(rij[d], lc.inv_box[d]))));
+      }
+    }
+    Body<F> bj;
+    bj.x = qc.x; bj.y = qc.y; bj.z = qc.z; bj.r = qc.w;
+    bj.mat = (c.nmat > 1) ? c.smat[off + kcur] : 0;
+    if (CS) {
+      const Vec4<F> v = c.svel[off + kcur];
+      const Vec4<F> w = c.sang[off + kcur];
+      bj.vx = v.x; bj.vy = v.y; bj.vz = v.z; bj.m = v.w;
+      bj.wx = w.x; bj.wy = w.y; bj.wz = w.z;
+    }
+    F ff[3], tt[3];
+    pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
+    f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
+    if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+  };
+  if (!ovf) {
+    int e = 0;
+    while (true) {  // one instance of the law: mask bits in row order, then the extra list
+      int kcur;
+      if (mlo | mhi) {
+        const unsigned m = mlo ? mlo : mhi;
+        const unsigned bit = 31u - (unsigned)__clz((int)(m & (0u - m)));
+        const unsigned row = (bit / kU) + (mlo ? 0u : 32u / kU);
+        if (mlo) mlo &= mlo - 1u;
+        else mhi &= mhi - 1u;
+        kcur = (int)(lds_u32(rs0 + row * (kT * 4)) + bit % kU);
+      } else if (e < ne) {
+        kcur = (int)lds_u32(el0 + (unsigned)e * (kT * 4));
+        ++e;
+      } else {
+        break;
+      }
+      contact(kcur);
+    }
+  } else {
+    // generic x-run walk (law inside the candidate loop): any occupancy
+    ForceVis<F, LAW, D, PERIODIC, SIMPLE> vis{c, lc, off, c.spos + off};
+    vis.a = a;
+    vis.k = k;
+    vis.idx = c.perm[off + k];
+    vis.clump = clump;
+    vis.interact = interact;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) vis.hb[d] = lc.box[d] * F(0.499999);
+    vis.f[0] = vis.f[1] = vis.f[2] = F(0);
+    vis.t[0] = vis.t[1] = vis.t[2] = F(0);
+    const F pp[3] = {a.x, a.y, a.z};
+    walk_runs<F, D, PERIODIC>(c, b, g, pp, vis);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      f[d] = vis.f[d];
+      t[d] = vis.t[d];
+    }
+  }
 }
 
-template <typename F, int LAW, int D, bool PERIODIC, int EPI>
-__global__ void __launch_bounds__(FlatCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_flat(Ctx<F> c, int with_torque) {
+template <typename F, int LAW, int D, bool PERIODIC>
+__global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_rows(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
-  __shared__ __align__(16) unsigned char smem[FlatCfg<D>::kBytes];
+  __shared__ __align__(16) unsigned char smem[RowsCfg<D>::kBytes];
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
   const bool mine = flat_walk_ok(g);
@@ -706,8 +696,39 @@ __global__ void __launch_bounds__(FlatCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) 
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= c.n) return;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-  if (!c.clumps && !g.any_bond) pair_flat_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, with_torque, sbase);
-  else pair_flat_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, with_torque, sbase);
+  F f[3], t[3];
+  if (!c.clumps && !g.any_bond) pair_rows_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, sbase, f, t);
+  else pair_rows_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, sbase, f, t);
+  const size_t off = (size_t)b * c.n;
+  c.sforce[off + k] = Vec4<F>{f[0], f[1], f[2], F(0)};
+  if (LAW == JDB200_LAW_CUNDALLSTRACK) c.storque[off + k] = Vec4<F>{t[0], t[1], t[2], F(0)};
+}
+
+// D of the row kernel: one thread per ORIGINAL particle i.  EPI 0: the epilogue of
+// DynamicCellList.compute_force (cell_list.py:461-462); EPI 1: the fused sphere driver
+// (fused_sphere_epilogue: collider epilogue + ForceManager.apply + step_after_force).
+template <typename F, int D, int EPI>
+__global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
+  pdl_prologue();
+  using I = typename RT<F>::I;
+  const int b = blockIdx.y;
+  const GridInfo<I> g = c.gi[b];
+  const bool served = flat_walk_ok(g);
+  // not served by the row kernel: the generic kernel stores by itself — unless JDB200_GRID_DENSE kept it from
+  // being launched; then Collider.overflow is up and the hook still completes, with zero contact forces
+  if (!served && c.grid_mode != JDB200_GRID_DENSE) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const size_t off = (size_t)b * c.n;
+  Vec4<F> fs = Vec4<F>{0, 0, 0, 0}, ts = Vec4<F>{0, 0, 0, 0};
+  if (served) {
+    const int slot = c.inv[off + i];
+    fs = ldg_vec4(c.sforce + off + slot);
+    if (c.law == JDB200_LAW_CUNDALLSTRACK) ts = ldg_vec4(c.storque + off + slot);
+  }
+  const F f[3] = {fs.x, fs.y, fs.z}, t[3] = {ts.x, ts.y, ts.z};
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.urec[2 * (off + i) + 1], (int)i, f, t, with_torque != 0);
+  else store_force_torque<F, D>(c, off + i, f, t, g.any_ppr != 0, with_torque != 0);
 }
 
 // FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
@@ -1063,14 +1084,15 @@ int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
   const dim3 grid(cdiv(c.n, 128), c.batch);
   const int wt = with_torque ? 1 : 0;
   if (c.max_cells > 0) {  // a dense table exists
-    if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the flat kernel owns the systems it can serve
-      constexpr int kT = FlatCfg<D>::kThreads;
+    if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the row kernel owns the systems it can serve
+      constexpr int kT = RowsCfg<D>::kThreads;
       const dim3 gf(cdiv(c.n, kT), c.batch);
       if (c.periodic) {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, true, EPI>), gf, kT, s, c, wt));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, true>), gf, kT, s, c));
       } else {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_flat<F, L, D, false, EPI>), gf, kT, s, c, wt));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, false>), gf, kT, s, c));
       }
+      JDB_LAUNCH((k_after<F, D, EPI>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
     } else if (c.periodic) {         // wider canonical stencils: x-run kernel
       JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true, EPI>), grid, 128, s, c, wt));
     } else {

@@ -916,7 +916,51 @@ int rotation_after(cudaStream_t s, Ctx<F>& c) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Trajectory output (System.trajectory_rollout's default save_fn, system.py:55-57,101-120): ONE
+// launch packs the selected State leaves of a frame into a contiguous record
+//   [pos_c | vel | force | ang_vel | torque | q_w | q_xyz | pos]   (fields not selected are absent)
+// per system, so a frame leaves the device as one DMA instead of one clone per leaf.
+// pos = pos_c + pos_p_rot (state.py:295-304).
+// ---------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_frame_pack(Ctx<F> c, int fields, long long frame_len, F* __restrict__ out) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const long long n = c.n, D = c.dim, A = c.A;
+  const long long len[8] = {n * D, n * D, n * D, n * A, n * A, n, n * 3, n * D};
+  const F* src[8] = {c.pos_c, c.vel, c.force, c.ang_vel, c.torque, c.q_w, c.q_xyz, c.pos_c};
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < frame_len;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    int f = 0;
+    for (; f < 8; ++f) {
+      if (!((fields >> f) & 1)) continue;
+      if (r < len[f]) break;
+      r -= len[f];
+    }
+    if (f == 8) continue;
+    F v = src[f][(size_t)b * len[f] + r];
+    if (f == 7) v = RT<F>::add(v, c.pos_p_rot[(size_t)b * len[f] + r]);
+    out[(size_t)b * frame_len + e] = v;
+  }
+}
+
+template <typename F>
+int frame_pack(cudaStream_t s, Ctx<F>& c, int fields, void* out) {
+  const long long n = c.n, D = c.dim, A = c.A;
+  const long long len[8] = {n * D, n * D, n * D, n * A, n * A, n, n * 3, n * D};
+  long long frame_len = 0;
+  for (int f = 0; f < 8; ++f)
+    if ((fields >> f) & 1) frame_len += len[f];
+  if (frame_len == 0) return 0;
+  const int blocks = (int)std::min<long long>(cdiv(frame_len, 256), 148 * 16);
+  JDB_LAUNCH(k_frame_pack<F>, dim3(blocks, c.batch), 256, s, c, fields, frame_len, (F*)out);
+  return 0;
+}
+
 #define JDB_INST(F)                                                   \
+  template int frame_pack<F>(cudaStream_t, Ctx<F>&, int, void*);      \
   template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
   template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
   template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \

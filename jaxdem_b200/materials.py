@@ -71,7 +71,9 @@ class MaterialTable:
     @staticmethod
     def from_materials(mats: Sequence[Material], *, matcher: MaterialMatchmaker | None = None,
                        fill: float = 0.0) -> "MaterialTable":
-        keys = {f.name for m in mats for f in fields(m)} | set(_ALL_PROPS)
+        # keys come from the materials' own fields only (material_table.py:112): a law that needs a property no
+        # material defines fails in System.create with the reference's KeyError instead of running on zeros
+        keys = {f.name for m in mats for f in fields(m)}
         props = {k: torch.tensor([float(getattr(m, k, fill)) for m in mats], dtype=torch.float64)
                  for k in sorted(keys)}
         if matcher is None:

@@ -66,20 +66,25 @@ def _hypersphere_volume(rad: torch.Tensor, dim: int) -> torch.Tensor:
 
 
 def _symmetrize(conn: np.ndarray, N: int) -> np.ndarray:
-    """Bond lists are stored symmetrically (state.py:728-757)."""
-    w = max(conn.shape[-1], 1)
-    rows_idx = np.repeat(np.arange(N), conn.shape[-1])
-    cols = conn.reshape(-1)
-    valid = (cols >= 0) & (cols < N)
-    i_idx, j_idx = rows_idx[valid], cols[valid]
-    if i_idx.size == 0:
-        return np.full((N, w), -1, dtype=np.int64)
-    pairs = np.unique(np.stack((np.concatenate((i_idx, j_idx)), np.concatenate((j_idx, i_idx))), axis=1), axis=0)
-    counts = np.bincount(pairs[:, 0], minlength=N)
-    out = np.full((N, max(int(counts.max()), w)), -1, dtype=np.int64)
-    starts = np.cumsum(counts) - counts
-    out[pairs[:, 0], np.arange(pairs.shape[0]) - starts[pairs[:, 0]]] = pairs[:, 1]
-    return out
+    """Symmetric bond table: if j is listed for i then i is listed for j (what state.py:728-757 guarantees);
+    rows hold ascending partner ids, -1 padded, width = the widest row (at least the input width).
+    Every directed edge (i -> j) and its mirror become one 64-bit key i * N + j; sorting the unique keys
+    groups them by row with partners ascending."""
+    width = max(conn.shape[-1], 1)
+    src = np.broadcast_to(np.arange(N, dtype=np.int64)[:, None], conn.shape)
+    keep = (conn >= 0) & (conn < N)
+    a, b = src[keep], conn[keep].astype(np.int64)
+    table = np.full((N, width), -1, dtype=np.int64)
+    if a.size == 0:
+        return table
+    edge = np.unique(np.concatenate((a * N + b, b * N + a)))
+    row, partner = edge // N, edge % N
+    first = np.searchsorted(row, np.arange(N))            # where each row's block of keys begins
+    col = np.arange(edge.size) - first[row]
+    if col.max() >= width:
+        table = np.full((N, int(col.max()) + 1), -1, dtype=np.int64)
+    table[row, col] = partner
+    return table
 
 
 _FIELDS = ("pos_c", "pos_p", "vel", "force", "q", "ang_vel", "torque", "rad", "_rad", "volume", "mass",
@@ -97,6 +102,25 @@ class State:
         object.__setattr__(self, "has_clumps", bool(kw.get("has_clumps", True)))
         if self._pos_p_rot is None:
             self.refresh_cache()
+
+    def promise_bits(self) -> int:
+        """jdb200_params.promises this State can vouch for: no bonds / nothing fixed / pos_p == 0.  The three
+        reductions run once (one host synchronisation at first use) and are cached against the tensors' identity
+        and torch version counters, so an in-place edit or a re-assigned leaf re-evaluates them."""
+        from . import _lib
+        key = tuple((t.data_ptr(), t._version) for t in (self.bond_id, self.fixed, self.pos_p))
+        cached = self.__dict__.get("_promise_cache")
+        if cached is None or cached[0] != key:
+            bits = 0
+            if self.bond_id.numel() == 0 or bool((self.bond_id < 0).all()):
+                bits |= _lib.PROMISE_NO_BONDS
+            if not bool(self.fixed.any()):
+                bits |= _lib.PROMISE_NO_FIXED
+            if not bool((self.pos_p != 0).any()) and not bool((self._pos_p_rot != 0).any()):
+                bits |= _lib.PROMISE_NO_POS_P
+            cached = (key, bits)
+            object.__setattr__(self, "_promise_cache", cached)
+        return cached[1]
 
     def refresh_cache(self) -> None:
         object.__setattr__(self, "_pos_p_rot", Quaternion.rotate(self.q, self.pos_p).contiguous())

@@ -83,10 +83,23 @@ class System:
 
     # -- stepping -------------------------------------------------------------------
     def _is_native(self) -> bool:
+        """True when the single-call driver may replace the hook-by-hook loop: identity user hooks and every
+        hook of every component is this package's own implementation (a registered plugin that overrides a
+        hook in Python must run that override, reference plugin contract factory.py:240-320)."""
+        def own(obj, root, hooks):
+            impls = [root] + list(root._registry.values())
+            return all(any(getattr(type(obj), h, None) is getattr(k, h, None) for k in impls
+                           if k.__module__.startswith(__package__)) for h in hooks)
+
+        from .components import ForceManager as _FM
         return (self.user_pre_step_actions is _identity and self.user_post_step_actions is _identity
-                and type(self.collider).compute_force in (Collider.compute_force,)
-                + tuple(c.compute_force for c in Collider._registry.values())
-                and getattr(self.collider, "native_kind", None) in _lib.COLLIDER)
+                and own(self.collider, Collider, ("compute_force",))
+                and getattr(self.collider, "native_kind", None) in _lib.COLLIDER
+                and own(self.linear_integrator, LinearIntegrator, ("step_before_force", "step_after_force"))
+                and own(self.rotation_integrator, RotationIntegrator, ("step_before_force", "step_after_force"))
+                and own(self.domain, Domain, ("apply",))
+                and type(self.force_manager).apply is _FM.apply
+                and type(self.force_model).__module__.startswith(__package__))
 
     @staticmethod
     def _step_once(state: State, system: "System"):
@@ -115,6 +128,8 @@ class System:
         if fused:
             # time and step_count advance on the device, once per step, inside the same call
             _call.call("jdb200_system_step", state, system, C.c_int64(n), clock=True)
+            if n > 0:
+                system.force_manager.mark_clean()  # every step ends with the external buffers cleared
         else:
             for _ in range(n):
                 state, system = System._step_once(state, system)
@@ -128,25 +143,140 @@ class System:
         return CompiledStep(state, system, int(n))
 
     @staticmethod
-    def trajectory_rollout(state: State, system: "System", *, n: int, stride: int = 1, strides=None,
-                           save_fn: Callable | None = None):
-        """System.trajectory_rollout (system.py:606-699): n frames, each saved AFTER
-        ``stride`` steps; returns (state, system, stacked frames).  The default save_fn
-        keeps pos_c, vel, force, ang_vel, q (device tensors, stacked on a new leading axis)."""
-        if save_fn is None:
-            save_fn = lambda st, sy: {"pos_c": st.pos_c.clone(), "vel": st.vel.clone(), "force": st.force.clone(),
-                                      "ang_vel": st.ang_vel.clone(), "q_w": st.q.w.clone(),
-                                      "q_xyz": st.q.xyz.clone(), "time": sy.time.clone()}
-        frames = []
-        for f in range(n):
-            k = int(strides[f]) if strides is not None else stride
-            state, system = System.step(state, system, n=k)
-            frames.append(save_fn(state, system))
-        if frames and isinstance(frames[0], dict):
-            traj = {k: torch.stack([fr[k] for fr in frames]) for k in frames[0]}
+    def trajectory_rollout(state: State, system: "System", *, n: int | None = None, stride: int = 1, strides=None,
+                           save_fn: Callable | None = None, fields=("pos_c", "vel", "force", "ang_vel", "q_w",
+                                                                     "q_xyz", "pos"),
+                           to_host: bool = False, ring: int = 4):
+        """System.trajectory_rollout (system.py:606-699): one saved frame per entry of ``strides`` (or ``n``
+        frames ``stride`` steps apart), each saved AFTER its steps; a leading 0 stride records the initial state.
+        Returns ``(state, system, trajectory)``.
+
+        ``save_fn=None`` (default) is the reference's "save the state" in this package's form: the selected
+        State ``fields`` of a frame are packed by ONE kernel (jdb200_frame_pack) and the trajectory is a
+        :class:`Frames` object whose attributes (``traj.pos``, ``traj.vel`` ... , ``traj.time``,
+        ``traj.step_count``) carry a new leading frame axis.  ``to_host=False`` keeps it on the device;
+        ``to_host=True`` streams it out while the simulation continues: frames are packed into a small device
+        ring, a second stream copies each slot to pinned host memory, events keep the two streams honest
+        (``ring`` slots in flight).  A user ``save_fn(state, system)`` is called per frame instead and its
+        results are stacked (dict / tuple / tensor), exactly like the reference's scan."""
+        if strides is not None:
+            strides = [int(k) for k in (strides.tolist() if hasattr(strides, "tolist") else strides)]
         else:
-            traj = frames
-        return state, system, traj
+            if n is None:
+                raise ValueError("`n` must be provided when `strides` is None.")
+            strides = [int(stride)] * int(n)
+        if save_fn is not None:
+            frames = []
+            for k in strides:
+                state, system = System.step(state, system, n=k)
+                frames.append(save_fn(state, system))
+            return state, system, _stack_frames(frames)
+        rec = FrameRing(state, system, len(strides), fields, to_host=to_host, ring=ring)
+        for f, k in enumerate(strides):
+            state, system = System.step(state, system, n=k)
+            rec.save(f, state, system)
+        return state, system, rec.finish()
+
+
+def _stack_frames(frames):
+    if not frames:
+        return frames
+    f0 = frames[0]
+    if isinstance(f0, dict):
+        return {k: torch.stack([fr[k] for fr in frames]) for k in f0}
+    if isinstance(f0, (tuple, list)):
+        return type(f0)(_stack_frames([fr[i] for fr in frames]) for i in range(len(f0)))
+    if isinstance(f0, torch.Tensor):
+        return torch.stack(frames)
+    return frames
+
+
+class Frames:
+    """Stacked frames of a rollout: one tensor per saved field, leading axis = frame."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __getitem__(self, k):
+        return self.__dict__[k]
+
+    def keys(self):
+        return self.__dict__.keys()
+
+
+class FrameRing:
+    """Trajectory output path (reference system.py:101-120 stacks a copy of the whole pytree per frame).
+    Device side: jdb200_frame_pack writes the selected leaves of a frame as ONE contiguous record.
+    ``to_host``: the record goes to a slot of a device ring; a copy stream moves it to its row of one pinned
+    host array (cudaMemcpyAsync D2H) while the step kernels of the next frame already run; per-slot events
+    order "packed -> copied -> slot free again".  Otherwise the record is a row of a device-resident array."""
+
+    def __init__(self, state: State, system: "System", n_frames: int, fields, *, to_host: bool, ring: int = 4):
+        _call.require_cuda(state)
+        self.fields = tuple(fields)
+        unknown = [f for f in self.fields if f not in _lib.FRAME_FIELDS]
+        if unknown:
+            raise KeyError(f"unknown frame fields {unknown}; known: {_lib.FRAME_FIELDS}")
+        self.mask = sum(1 << _lib.FRAME_FIELDS.index(f) for f in set(self.fields))
+        lead = tuple(state.pos_c.shape[:-2])
+        N, D, A = state.N, state.dim, (1 if state.dim == 2 else 3)
+        widths = {"pos_c": (N, D), "vel": (N, D), "force": (N, D), "ang_vel": (N, A), "torque": (N, A),
+                  "q_w": (N, 1), "q_xyz": (N, 3), "pos": (N, D)}
+        self.layout, off = [], 0
+        for f in _lib.FRAME_FIELDS:  # the kernel's order
+            if (self.mask >> _lib.FRAME_FIELDS.index(f)) & 1:
+                ln = widths[f][0] * widths[f][1]
+                self.layout.append((f, off, widths[f]))
+                off += ln
+        self.frame_len, self.lead, self.n_frames, self.to_host = off, lead, n_frames, to_host
+        B = 1
+        for x in lead:
+            B *= x
+        dev, F = state.device, state.dtype
+        self.times = torch.empty((n_frames, *lead), dtype=F, device=dev)
+        self.counts = torch.empty((n_frames, *lead), dtype=torch.int64, device=dev)
+        if to_host:
+            self.ring = max(1, min(int(ring), max(n_frames, 1)))
+            self.slots = torch.empty((self.ring, B, self.frame_len), dtype=F, device=dev)
+            self.host = torch.empty((n_frames, B, self.frame_len), dtype=F).pin_memory()
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.packed = [torch.cuda.Event() for _ in range(self.ring)]
+            self.copied = [None] * self.ring
+        else:
+            self.dev_frames = torch.empty((n_frames, B, self.frame_len), dtype=F, device=dev)
+
+    def save(self, f: int, state: State, system: "System") -> None:
+        import ctypes as C
+        self.times[f].copy_(system.time)
+        self.counts[f].copy_(system.step_count)
+        if not self.to_host:
+            _call.call("jdb200_frame_pack", state, system, C.c_int32(self.mask), self.dev_frames[f], needs_ws=False)
+            return
+        slot = f % self.ring
+        cur = torch.cuda.current_stream(state.device)
+        if self.copied[slot] is not None:
+            cur.wait_event(self.copied[slot])  # the slot's previous frame has left the device
+        _call.call("jdb200_frame_pack", state, system, C.c_int32(self.mask), self.slots[slot], needs_ws=False)
+        self.packed[slot].record(cur)
+        self.copy_stream.wait_event(self.packed[slot])
+        with torch.cuda.stream(self.copy_stream):
+            self.host[f].copy_(self.slots[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.copied[slot] = ev
+
+    def finish(self) -> Frames:
+        if self.to_host:
+            self.copy_stream.synchronize()
+            base = self.host
+            times, counts = self.times.cpu(), self.counts.cpu()
+        else:
+            base, times, counts = self.dev_frames, self.times, self.counts
+        out = {}
+        for name, off, (n, w) in self.layout:
+            t = base[:, :, off:off + n * w].reshape(self.n_frames, *self.lead, n, w)
+            out[name] = t
+        return Frames(time=times, step_count=counts, **out)
 
 
 class CompiledStep:
@@ -158,7 +288,8 @@ class CompiledStep:
             raise RuntimeError("compile_step needs native components and identity user hooks")
         self.state, self.system, self.n = state, system, n
         _call.require_cuda(state)
-        _call.workspace(_call.params_for(state, system), state.device)  # allocate before capture
+        # allocate before capture; the graph bakes this pointer in, so keep the tensor alive with it
+        self._ws = _call.workspace(_call.params_for(state, system), state.device, system)
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=state.device)
         side.wait_stream(torch.cuda.current_stream(state.device))

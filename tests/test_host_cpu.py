@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.jdb200_abi_version() == 1
+    assert lib.jdb200_abi_version() == _lib.ABI_VERSION
 
 
 def test_params_struct_layout_matches_header():
