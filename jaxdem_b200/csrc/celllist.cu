@@ -5,13 +5,9 @@
 // Replaces _get_spatial_partition (jaxdem/colliders/cell_list.py:35-87) and
 // _grid_params (jaxdem/colliders/_partition.py:54-99).  Outputs are bit-identical
 // to a stable sort of (hash, iota) on the reference's linear x-fastest hash.
-#include <cooperative_groups.h>
-
 #include "ctx.cuh"
 #include "launch.cuh"
 #include "scan.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace jdb {
 
@@ -139,6 +135,7 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
     g.edge = 0;
     c.tile_counter[b] = 0;
     c.radix_skip[b] = 0;
+    if (b == 0) c.coop_bar[0] = 0u;  // arrival counter of the sort fallback's grid barrier
   }
 }
 
@@ -244,10 +241,9 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
         c.pos_c[gidx * D + d] = pc[d];
       }
     }
-    const size_t us = (MODE == 3 || MODE == 4) ? 2 : 1;  // fused flows interleave (pos, rad) and (vel, mass)
-    if (MODE == 3 || MODE == 4) c.urec[2 * gidx + 1] = Vec4<F>{v[0], v[1], v[2], mass};
+    if (MODE == 3 || MODE == 4) c.uvm[gidx] = Vec4<F>{v[0], v[1], v[2], mass};
     c.key[gidx] = key;
-    c.urec[us * gidx] = Vec4<F>{p[0], p[1], p[2], rad};
+    c.urec[gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
       bool in_table = key >= 0 && (long long)key < g.bound;
       if (in_table && c.win_len[0] > 0) {
@@ -263,6 +259,157 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     }
   }
   // flags consumed by the pair kernels (one store per warp at most)
+  if (__any_sync(0xffffffffu, bond) && (threadIdx.x & 31) == 0) c.gi[b].any_bond = 1;
+  if (__any_sync(0xffffffffu, ppr_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ppr = 1;
+  if (__any_sync(0xffffffffu, edge) && (threadIdx.x & 31) == 0) c.gi[b].edge = 1;
+  if (MODE == 3 || MODE == 4) {
+    if (__any_sync(0xffffffffu, ext_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ext = 1;
+    if (__any_sync(0xffffffffu, fixed_any) && (threadIdx.x & 31) == 0) c.gi[b].any_fixed = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1 (vectorised): the same hook arithmetic, FOUR particles per thread, every State stream moved
+// as 128-bit accesses — the (N, 3) row-major leaves as 3 float4 per 4 particles (SURVEY §7
+// "layout").  f32, n % 4 == 0 (so each system's rows start 16-byte aligned); otherwise k_hash.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(128) k_hash4(Ctx<float> c, const float* __restrict__ cell_size_override) {
+  pdl_prologue();
+  using F = float;
+  using T = RT<F>;
+  using I = int32_t;
+  using U = uint32_t;
+  constexpr int A = D == 3 ? 3 : 1;
+  constexpr int P = 4;  // particles per thread
+  const int b = blockIdx.y;
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * P;
+  const bool live = i0 < c.n;
+  const size_t g0 = (size_t)b * c.n + (live ? i0 : 0);
+  bool bond = false, ppr_nz = false, ext_nz = false, fixed_any = false, edge = false;
+  if (live) {
+    const GridInfo<I> g = c.gi[b];
+    // ---- loads: P * D floats of every (N, D) leaf = D float4 ----
+    F pc[P * D], pr[P * D], f[P * D], v[P * D], rad[P], mass[P];
+    bool fixed[P];
+    auto load_rows = [&](const F* base, F* out) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        const float4 t = ldcs4(base + g0 * D + 4 * q);
+        out[4 * q] = t.x; out[4 * q + 1] = t.y; out[4 * q + 2] = t.z; out[4 * q + 3] = t.w;
+      }
+    };
+    load_rows(c.pos_c, pc);
+#pragma unroll
+    for (int e = 0; e < P * D; ++e) pr[e] = f[e] = v[e] = F(0);
+    if (!(c.promises & JDB200_PROMISE_NO_POS_P)) load_rows(c.pos_p_rot, pr);
+    if (MODE != 0) {
+      load_rows(c.force, f);
+      load_rows(c.vel, v);
+    }
+    {
+      const float4 t = ldcs4(c.rad + g0);
+      rad[0] = t.x; rad[1] = t.y; rad[2] = t.z; rad[3] = t.w;
+    }
+    F dt = F(0);
+#pragma unroll
+    for (int p = 0; p < P; ++p) { mass[p] = F(1); fixed[p] = false; }
+    if (MODE != 0) {
+      dt = c.dt[b];
+      const float4 t = ldcs4(c.mass + g0);
+      mass[0] = t.x; mass[1] = t.y; mass[2] = t.z; mass[3] = t.w;
+      if (!(c.promises & JDB200_PROMISE_NO_FIXED)) {
+        const unsigned fx = __ldcs(reinterpret_cast<const unsigned*>(c.fixed + g0));
+#pragma unroll
+        for (int p = 0; p < P; ++p) fixed[p] = ((fx >> (8 * p)) & 0xffu) != 0u;
+      }
+    }
+    if (!(c.promises & JDB200_PROMISE_NO_BONDS))
+      for (int w = 0; w < P * c.W; ++w) bond |= __ldcs(&c.bond_id[g0 * c.W + w]) >= 0;
+    if (MODE == 3 || MODE == 4) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) fixed_any |= fixed[p];
+      if (!(c.promises & JDB200_PROMISE_NO_EXT)) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+          const float4 s1 = ldcs4(c.ext_force + g0 * D + 4 * q), s2 = ldcs4(c.ext_force_com + g0 * D + 4 * q);
+          ext_nz |= s1.x != 0.f || s1.y != 0.f || s1.z != 0.f || s1.w != 0.f || s2.x != 0.f || s2.y != 0.f ||
+                    s2.z != 0.f || s2.w != 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < A; ++q) {
+          const float4 s3 = ldcs4(c.ext_torque + g0 * A + 4 * q);
+          ext_nz |= s3.x != 0.f || s3.y != 0.f || s3.z != 0.f || s3.w != 0.f;
+        }
+      }
+    }
+    const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
+    F anchor[3] = {0, 0, 0}, box[3] = {1, 1, 1};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      anchor[d] = c.anchor[b * D + d];
+      box[d] = c.box[b * D + d];
+    }
+    // ---- arithmetic (identical, op for op, to k_hash) ----
+    I key[P];
+    F pos[P * D];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      if (MODE != 0 && MODE != 4) {
+        const F sc = T::div(T::mul(dt, F(0.5)), mass[p]);
+        const F free = fixed[p] ? F(0) : F(1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          v[p * D + d] = T::add(v[p * D + d], T::mul(T::mul(f[p * D + d], sc), free));
+          pc[p * D + d] = T::add(pc[p * D + d], T::mul(dt, v[p * D + d]));
+        }
+      }
+      U h = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        ppr_nz |= pr[p * D + d] != F(0);
+        pos[p * D + d] = T::add(pc[p * D + d], pr[p * D + d]);
+        const I cd = cell_coord<F, I>(pos[p * D + d], anchor[d], box[d], cs, g.gd[d], c.periodic);
+        edge |= cd < 0 || cd >= g.gd[d];
+        h += (U)cd * (U)g.stride[d];
+      }
+      key[p] = (I)h;
+    }
+    // ---- stores ----
+    auto store_rows = [&](F* base, const F* in) {
+#pragma unroll
+      for (int q = 0; q < D; ++q)
+        *reinterpret_cast<float4*>(base + g0 * D + 4 * q) = make_float4(in[4 * q], in[4 * q + 1], in[4 * q + 2], in[4 * q + 3]);
+    };
+    if (MODE != 0 && MODE != 4) {
+      if (MODE != 3) store_rows(c.vel, v);
+      store_rows(c.pos_c, pc);
+    }
+    int rk[P] = {0, 0, 0, 0};
+    if (g.dense) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        bool in_table = key[p] >= 0 && (long long)key[p] < g.bound;
+        if (in_table && c.win_len[0] > 0) {
+          const long long k = (long long)key[p];
+          in_table = (k >= c.win_lo[0] && k < c.win_lo[0] + c.win_len[0]) ||
+                     (k >= c.win_lo[1] && k < c.win_lo[1] + c.win_len[1]);
+        }
+        if (in_table) rk[p] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + key[p], 1);
+        else c.gi[b].dense_fail = 1;
+      }
+      *reinterpret_cast<int4*>(c.rank + g0) = make_int4(rk[0], rk[1], rk[2], rk[3]);
+    }
+    *reinterpret_cast<int4*>(c.key + g0) = make_int4(key[0], key[1], key[2], key[3]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const F z = D == 3 ? pos[p * D + D - 1] : F(0), vz = D == 3 ? v[p * D + D - 1] : F(0);
+      c.urec[g0 + p] = Vec4<F>{pos[p * D], pos[p * D + 1], z, rad[p]};
+      if (MODE == 3 || MODE == 4) c.uvm[g0 + p] = Vec4<F>{v[p * D], v[p * D + 1], vz, mass[p]};
+    }
+  }
   if (__any_sync(0xffffffffu, bond) && (threadIdx.x & 31) == 0) c.gi[b].any_bond = 1;
   if (__any_sync(0xffffffffu, ppr_nz) && (threadIdx.x & 31) == 0) c.gi[b].any_ppr = 1;
   if (__any_sync(0xffffffffu, edge) && (threadIdx.x & 31) == 0) c.gi[b].edge = 1;
@@ -334,7 +481,7 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   if (!use_dense(g)) return;
   const size_t gidx = (size_t)b * c.n + i;
   const int key = (int)c.key[gidx];
-  const Vec4<F> p = c.urec[(c.fused ? 2 : 1) * gidx];
+  const Vec4<F> p = c.urec[gidx];
   const size_t slot = (size_t)b * c.n + c.cell_start[(size_t)b * c.cell_stride + key] + c.rank[gidx];
   if (sizeof(F) == 4) {
     st256(c.arec + 32 * slot, (float)p.x, (float)p.y, (float)p.z, (float)p.w, __int_as_float((int)i),
@@ -479,14 +626,31 @@ __device__ __forceinline__ void radix_scatter_tile(const Ctx<F>& c, int b, int t
 // LSD passes: key -> key_b -> key_c -> key_b ...; values: (iota) -> perm_c -> rank -> perm_c ...
 // (rank[] is free in the sorted path).  The final permutation lands in perm_c or rank,
 // see sorted_perm_buffer().
+// Grid-wide barrier on a monotonic arrival counter (zeroed by k_setup): instance `phase` (1, 2, ...) is
+// passed once phase * gridDim.x blocks have arrived.  The launch keeps every block resident (grid <= one
+// wave, see build_partition), so the spin cannot starve a block that has not started.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& phase) {
+  __syncthreads();
+  ++phase;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = phase * gridDim.x;
+    while (*((volatile unsigned*)counter) < target) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <typename F>
 __global__ void __launch_bounds__(256) k_radix_sort(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
-  cg::grid_group grid = cg::this_grid();
   __shared__ int whist[8][256];
   __shared__ int s_warp[8];
   constexpr int passes = (int)sizeof(I);
+  unsigned phase = 0;
+  struct { unsigned* ctr; unsigned* ph; __device__ void sync() { grid_barrier(ctr, *ph); } } grid{c.coop_bar, &phase};
   for (int b = 0; b < c.batch; ++b) {
     if (use_dense(c.gi[b])) continue;  // grid-uniform
     const I* kin = c.key;
@@ -575,8 +739,7 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   const size_t gi = off + i, gd = off + dest;
   c.perm[gd] = i;
   if (!dense || c.want_skey) c.skey[gd] = c.key[gi];
-  const size_t us = c.fused ? 2 : 1;
-  c.spos[gd] = dense ? mine : c.urec[us * gi];
+  c.spos[gd] = dense ? mine : c.urec[gi];
   if (c.clumps || g.any_bond) {
     bool has_bond = false;
     if (g.any_bond)
@@ -584,10 +747,10 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
     c.sclump[gd] = (int)c.clump_id[gi] | (has_bond ? 0x80000000 : 0);
   }
   if (c.nmat > 1) c.smat[gd] = (int)c.mat_id[gi];
-  // (the fused flows keep the kicked velocity in the original-order record urec[2 i + 1]: k_after reads it there)
+  // (the fused flows keep the kicked velocity in the original-order record uvm[i]: k_after reads it there)
   if (c.law == JDB200_LAW_CUNDALLSTRACK) {
     const F* v = c.vel + gi * c.dim;
-    if (c.fused) c.svel[gd] = c.urec[2 * gi + 1];
+    if (c.fused) c.svel[gd] = c.uvm[gi];
     else c.svel[gd] = Vec4<F>{v[0], v[1], c.dim == 3 ? v[2] : F(0), c.mass[gi]};
     const F* w = c.ang_vel + gi * c.A;
     c.sang[gd] = c.dim == 3 ? Vec4<F>{w[0], w[1], w[2], F(0)} : Vec4<F>{F(0), F(0), w[0], F(0)};
@@ -607,8 +770,28 @@ static int coop_grid_limit(const void* fn, int block) {
   return sms * per_sm;
 }
 
+template <int D>
+static bool launch_hash4(cudaStream_t s, Ctx<double>&, const double*, int) { return false; }
+template <int D>
+static bool launch_hash4(cudaStream_t s, Ctx<float>& c, const float* cso, int mode) {
+  if (c.n % 4 != 0) return false;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!(al(c.pos_c) && al(c.pos_p_rot) && al(c.force) && al(c.vel) && al(c.rad) && al(c.mass) && al(c.ext_force) &&
+        al(c.ext_force_com) && al(c.ext_torque) && (reinterpret_cast<uintptr_t>(c.fixed) & 3) == 0))
+    return false;
+  const dim3 grid(cdiv(c.n, 4 * 128), c.batch);
+  auto go = [&]() -> int {
+    if (mode == 0) JDB_LAUNCH((k_hash4<D, 0>), grid, 128, s, c, cso);
+    else if (mode == 3) JDB_LAUNCH((k_hash4<D, 3>), grid, 128, s, c, cso);
+    else JDB_LAUNCH((k_hash4<D, 4>), grid, 128, s, c, cso);
+    return 0;
+  };
+  return go() == 0;
+}
+
 template <typename F, int D>
 static int launch_hash(cudaStream_t s, Ctx<F>& c, const F* cso, int mode, bool ext) {
+  if ((mode == 0 || mode == 3 || mode == 4) && launch_hash4<D>(s, c, cso, mode)) return 0;
   const dim3 grid(cdiv(c.n, 256), c.batch);
   if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0>), grid, 256, s, c, cso);
   else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3>), grid, 256, s, c, cso);
@@ -636,34 +819,13 @@ int build_partition(cudaStream_t s, Ctx<F>& c, const F* cell_size_override, int 
     JDB_LAUNCH(k_scatter<F>, dim3(pb, B), 256, s, c);
   }
   if (c.max_cells == 0 || c.grid_mode == JDB200_GRID_AUTO) {
+    // ONE ordinary launch (programmatic stream serialization like every other kernel of the library; legal in
+    // graph capture) with a software grid barrier between the count / scan / scatter phases; at most one
+    // resident wave of blocks.  When every system is dense the blocks exit at once.
     const int limit = coop_grid_limit((const void*)k_radix_sort<F>, 256);
     if (limit <= 0) return JDB200_ECUDA;
-    const int blocks = std::max(1, std::min(limit, c.radix_blocks));
-    const bool timed = g_timing.load(std::memory_order_relaxed) != 0;
-    if (timed) timing_begin("k_radix_sort", s);
-    // cooperative (grid syncs inside) AND programmatic stream serialization, like every other launch of
-    // the library: the kernel begins with pdl_prologue(), so the launch chain is not broken around it
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = s;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_radix_sort<F>, c);
-    if (e != cudaSuccess) {  // the combination is refused: plain cooperative launch
-      (void)cudaGetLastError();
-      void* args[] = {(void*)&c};
-      e = cudaLaunchCooperativeKernel((const void*)k_radix_sort<F>, dim3(blocks), dim3(256), args, 0, s);
-    }
-    if (timed) timing_end(s);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (e != cudaSuccess) return JDB200_ECUDA;
+    const int blocks = std::max(1, std::min(limit / 2, c.radix_blocks));
+    JDB_LAUNCH(k_radix_sort<F>, dim3(blocks), 256, s, c);
     sorted_perm = sorted_perm_buffer(c);
   }
   JDB_LAUNCH(k_finalize<F>, dim3(pb, B), 256, s, c, sorted_perm);

@@ -38,10 +38,11 @@ struct Ctx {
   int* cell_start;             // [B*(max_cells+1)] exclusive starts (dense)
   int* tmp_key;                // [B*N] dense key of the particle in arrival slot k
   int2* slot_rec;              // [B*N] (particle index, key) of arrival slot k: ONE 8-byte random store per particle
-  // [2*B*N] shadow records in ORIGINAL order: (x, y, z, rad) with pos = pos_c + pos_p_rot, and — fused driver —
-  // (vx, vy, vz, mass) after the before-force kick.  Fused: the two records of a particle are interleaved
-  // (stride 2), so the gather of k_finalize touches ONE full 32-byte sector (f32); otherwise stride 1.
+  // shadow records in ORIGINAL order, written by k_hash: urec[i] = (x, y, z, rad) with pos = pos_c + pos_p_rot
+  // (read back, coalesced, by k_scatter) and — fused flows — uvm[i] = (vx, vy, vz, mass) after the before-force
+  // kick (read back, coalesced, by k_after).  Two separate arrays: each reader streams exactly what it needs.
   Vec4<F>* urec;
+  Vec4<F>* uvm;
   // [B*N] 32-byte records in ARRIVAL order (slot = cell_start[key] + arrival rank), written by k_scatter with ONE
   // 256-bit store per particle: f32 (x, y, z, rad, index, key, 0, 0); f64 (x, y, z, rad) with (index, key) in slot_rec
   char* arec;
@@ -94,7 +95,8 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start = b.take<int>(B * (size_t)c.cell_stride);
   c.tmp_key = b.take<int>(BN);
   c.slot_rec = b.take<int2>(BN);
-  c.urec = b.take<Vec4<F>>(2 * BN);
+  c.urec = b.take<Vec4<F>>(BN);
+  c.uvm = b.take<Vec4<F>>(BN);
   c.arec = b.take<char>(32 * BN);
   c.coop_bar = b.take<unsigned>(4);
   c.tile_state = b.take<unsigned long long>(B * (size_t)c.scan_tiles);

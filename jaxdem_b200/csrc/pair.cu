@@ -147,6 +147,12 @@ __device__ __forceinline__ bool flat_walk_ok(const GridInfo<I>& g) {
   return fast_walk_ok(g) && g.range == 1 && !g.edge;
 }
 
+// the row kernel (k_pair_rows) packs a run start and its length into one word: starts below 2^27
+template <typename F>
+__device__ __forceinline__ bool rows_ok(const Ctx<F>& c, const GridInfo<typename RT<F>::I>& g) {
+  return flat_walk_ok(g) && c.n < (1ll << 27);
+}
+
 // wrap n into [0, g) for |n| < 2g: identical to n - g*floor(n/g) (cell_list.py:70-72)
 __device__ __forceinline__ int wrap1(int n, int g) { return n < 0 ? n + g : (n >= g ? n - g : n); }
 
@@ -312,12 +318,11 @@ __device__ __forceinline__ void store_force_torque(const Ctx<F>& c, size_t gidx,
 // buffers and fixed flags are gathered only when that kernel saw a non-zero entry (they are
 // zero otherwise, and stay zero).
 template <typename F, int D>
-__device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
-                                                      const GridInfo<typename RT<F>::I>& g, const Vec4<F>& vm,
-                                                      int idx, const F* f, const F* t, bool with_torque) {
+__device__ __forceinline__ void fused_sphere_compute(const Ctx<F>& c, int b, const GridInfo<typename RT<F>::I>& g,
+                                                     const Vec4<F>& vm, size_t gi, const F* f, const F* t,
+                                                     bool with_torque, F* o_force, F* o_vel, F* o_torque) {
   using T = RT<F>;
   constexpr int A = D == 3 ? 3 : 1;
-  const size_t off = (size_t)b * c.n, gi = off + idx;
   const F v[3] = {vm.x, vm.y, vm.z}, mass = vm.w;
   const F dt = c.dt[b];
   F fp[3] = {0, 0, 0}, fc[3] = {0, 0, 0}, r[3] = {0, 0, 0}, et[3] = {0, 0, 0}, grav[3] = {0, 0, 0};
@@ -343,8 +348,8 @@ __device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
   for (int d = 0; d < D; ++d) {
     const F fcom = T::add(fc[d], T::mul(grav[d], T::div(mass, F(1))));
     const F ft = T::add(T::add(f[d], fp[d]), fcom);
-    c.force[gi * D + d] = ft;
-    c.vel[gi * D + d] = T::add(v[d], T::mul(T::mul(ft, sc), free));
+    o_force[d] = ft;
+    o_vel[d] = T::add(v[d], T::mul(T::mul(ft, sc), free));
   }
   if (g.any_ext) {
 #pragma unroll
@@ -363,11 +368,48 @@ __device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
     const F cr[3] = {T::sub(T::mul(r[1], fp[2]), T::mul(r[2], fp[1])), T::sub(T::mul(r[2], fp[0]), T::mul(r[0], fp[2])),
                      T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]))};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) c.torque[gi * 3 + a] = T::add(tc[a], T::add(et[a], cr[a]));
+    for (int a = 0; a < 3; ++a) o_torque[a] = T::add(tc[a], T::add(et[a], cr[a]));
   } else {
     const F tc = t[2] + (r[0] * f[1] - r[1] * f[0]);
     const F cr = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
-    c.torque[gi] = T::add(tc, T::add(et[0], cr));
+    o_torque[0] = T::add(tc, T::add(et[0], cr));
+  }
+}
+
+template <typename F, int D>
+__device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
+                                                      const GridInfo<typename RT<F>::I>& g, const Vec4<F>& vm,
+                                                      int idx, const F* f, const F* t, bool with_torque) {
+  constexpr int A = D == 3 ? 3 : 1;
+  const size_t gi = (size_t)b * c.n + idx;
+  F of[3], ov[3], ot[3];
+  fused_sphere_compute<F, D>(c, b, g, vm, gi, f, t, with_torque, of, ov, ot);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    c.force[gi * D + d] = of[d];
+    c.vel[gi * D + d] = ov[d];
+  }
+  if (with_torque) {
+#pragma unroll
+    for (int a = 0; a < A; ++a) c.torque[gi * A + a] = ot[a];
+  }
+}
+
+// collider epilogue values (cell_list.py:461-462)
+template <typename F, int D>
+__device__ __forceinline__ void collider_epilogue_compute(const Ctx<F>& c, size_t gidx, const F* f, const F* t,
+                                                          bool any_ppr, F* o_torque) {
+  F pr[3] = {0, 0, 0};
+  if (any_ppr) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) pr[d] = c.pos_p_rot[gidx * D + d];
+  }
+  if (D == 3) {
+    o_torque[0] = t[0] + (pr[1] * f[2] - pr[2] * f[1]);
+    o_torque[1] = t[1] + (pr[2] * f[0] - pr[0] * f[2]);
+    o_torque[2] = t[2] + (pr[0] * f[1] - pr[1] * f[0]);
+  } else {
+    o_torque[0] = t[2] + (pr[0] * f[1] - pr[1] * f[0]);
   }
 }
 
@@ -393,7 +435,7 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.urec[2 * (off + vis.idx) + 1], vis.idx, vis.f, vis.t, with_torque != 0);
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.uvm[off + vis.idx], vis.idx, vis.f, vis.t, with_torque != 0);
   else store_force_torque<F, D>(c, off + vis.idx, vis.f, vis.t, g.any_ppr != 0, with_torque != 0);
 }
 
@@ -475,6 +517,70 @@ __device__ __forceinline__ unsigned rows_hit(const Body<F>& a, const Vec4<F>& q,
   return hit;
 }
 
+// packed f32x2 arithmetic (sm_100: FADD2 / FMUL2 work on 64-bit register pairs)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// The kU candidate tests of one stencil row -> kU hit bits.  f32: the record (x, y | z, rad) is two register
+// pairs; (ax, ay) - (x, y) and (az, -ar) - (z, rad) = (dz, -(ar + rad)) are two FADD2, their squares two FMUL2:
+// 4 packed + 2 adds + 1 multiply + 2 compares per candidate.
+template <typename F, int D, bool PERIODIC, int kU>
+struct RowTest {
+  Body<F> a;
+  F hbmin2;
+  __device__ __forceinline__ RowTest(const Body<F>& a_, F hb) : a(a_), hbmin2(hb) {}
+  __device__ __forceinline__ unsigned run(const Vec4<F>* p) const {
+    Vec4<F> q[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) q[j] = ldg_vec4(p + j);  // past the run: harmless, masked by the caller
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < kU; ++j) bits |= rows_hit<F, D, PERIODIC>(a, q[j], hbmin2) << j;
+    return bits;
+  }
+};
+template <int D, bool PERIODIC, int kU>
+struct RowTest<float, D, PERIODIC, kU> {
+  unsigned long long axy, azr;
+  float hbmin2;
+  __device__ __forceinline__ RowTest(const Body<float>& a, float hb)
+      : axy(pack2(a.x, a.y)), azr(pack2(a.z, -a.r)), hbmin2(hb) {}
+  __device__ __forceinline__ unsigned run(const Vec4<float>* p) const {
+    ulonglong2 q[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) q[j] = __ldg(reinterpret_cast<const ulonglong2*>(p + j));
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const unsigned long long u = sub2(axy, q[j].x), v = sub2(azr, q[j].y);
+      float dx2, dy2, dz2, rs2;
+      unpack2(mul2(u, u), dx2, dy2);
+      unpack2(mul2(v, v), dz2, rs2);
+      const float d2 = dx2 + dy2 + dz2;
+      unsigned hit = (unsigned)(d2 < rs2 * 1.00001f);
+      if (PERIODIC) hit |= (unsigned)!(d2 < hbmin2);
+      bits |= hit << j;
+    }
+    return bits;
+  }
+};
+
 template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
 __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
                                                const GridInfo<typename RT<F>::I>& g, unsigned sbase, F* f,
@@ -482,11 +588,12 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
   using T = RT<F>;
   using Cfg = RowsCfg<D>;
   constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
-  constexpr int NZ = D == 3 ? 3 : 1;
   constexpr int kU = Cfg::kU;
+  constexpr int kR = Cfg::kRows;
   constexpr unsigned kT = Cfg::kThreads;
-  const unsigned tid = threadIdx.x;
-  const unsigned rs0 = sbase + tid * 4;                    // run starts, this thread's column
+  constexpr unsigned kSlotMask = (1u << 27) - 1u;  // run word = start | min(len, 31) << 27 (rows_ok: n < 2^27)
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const unsigned rs0 = sbase + tid * 4;                    // run words, this thread's column
   const unsigned el0 = sbase + Cfg::kOffExtra + tid * 4;   // extra list
   const size_t off = (size_t)b * c.n;
   const Vec4<F>* sp = opaque_ptr(c.spos + off);
@@ -519,28 +626,34 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
   const int n1 = min(cx + 1, gx - 1) - x1 + 1;
   int x2 = -1;
   if (PERIODIC) x2 = cx == 0 ? gx - 1 : (cx == gx - 1 ? 0 : -1);
-  // hash of cell (0, cy + iy - 1, cz + iz - 1) for the kRows stencil rows, parked in this thread's column of
-  // shared memory (the slot is overwritten by the run start once the row is visited); negative: the row lies
-  // outside a non-periodic grid
+  // hash of cell (0, ny, nz), negative outside a non-periodic grid
+  auto axis_base = [&](int n, int gn, int stride) -> int {
+    if (PERIODIC) return wrap1(n, gn) * stride;
+    return (n >= 0 && n < gn) ? n * stride : (int)0x80000000;  // stays negative after adding the other axis
+  };
+  // all kRows run ranges at once (2 kRows independent loads), parked as run words in this thread's column
   {
-    auto axis_base = [&](int n, int gn, int stride) -> int {
-      if (PERIODIC) return wrap1(n, gn) * stride;
-      return (n >= 0 && n < gn) ? n * stride : (int)0x80000000;  // stays negative after adding the other axis
-    };
     const int ybs[3] = {axis_base(cy - 1, gy, sy), cy * sy, axis_base(cy + 1, gy, sy)};
     int zbs[3] = {0, 0, 0};
     if (D == 3) { zbs[0] = axis_base(cz - 1, gz, sz); zbs[1] = cz * sz; zbs[2] = axis_base(cz + 1, gz, sz); }
+    int s[kR], e[kR];
 #pragma unroll
-    for (int r = 0; r < Cfg::kRows; ++r) {
+    for (int r = 0; r < kR; ++r) {
       const int yb = ybs[r % 3], zb = zbs[r / 3];
-      sts_u32(rs0 + (unsigned)r * (kT * 4), (unsigned)(PERIODIC ? yb + zb : ((yb | zb) < 0 ? -1 : yb + zb)));
+      const bool ok = PERIODIC || (yb | zb) >= 0;
+      const int h0 = yb + zb + x1;
+      s[r] = ok ? cst[h0] : 0;
+      e[r] = ok ? cst[h0 + n1] : 0;
     }
+#pragma unroll
+    for (int r = 0; r < kR; ++r)
+      sts_u32(rs0 + (unsigned)r * (kT * 4), (unsigned)s[r] | ((unsigned)min(e[r] - s[r], 31) << 27));
   }
 
-  // ---- B: candidate tests, one stencil row per trip (the next row's range is loaded ahead) ----
+  // ---- B: candidate tests, one stencil row per trip ----
   unsigned mlo = 0u, mhi = 0u;     // bit r * kU + j of (mhi : mlo): slot (run start of row r) + j is a hit
   int ne = 0;                      // entries of the extra list
-  bool ovf = false;                // extra list full: the generic walk redoes this particle
+  bool ovf = false;                // extra list full (or a run of >= 31): the generic walk redoes this particle
   int s_self = 0;
   auto push_extra = [&](int kj) {
     if (ne < Cfg::kExtra) {
@@ -550,49 +663,71 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
       ovf = true;
     }
   };
-  int hb = (int)lds_u32(rs0);
-  int s_n = hb >= 0 ? cst[hb + x1] : 0;
-  int e_n = hb >= 0 ? cst[hb + x1 + n1] : 0;
+  const RowTest<F, D, PERIODIC, kU> rt(a, hbmin2);
 #pragma unroll 1
-  for (int r = 0; r < Cfg::kRows; ++r) {
-    const int s0 = s_n, len = e_n - s_n, hb0 = hb;
-    Vec4<F> q[kU];
-#pragma unroll
-    for (int j = 0; j < kU; ++j) q[j] = ldg_vec4(sp + s0 + j);  // past the run: harmless, masked below
-    if (r + 1 < Cfg::kRows) {  // next row
-      hb = (int)lds_u32(rs0 + (unsigned)(r + 1) * (kT * 4));
-      s_n = hb >= 0 ? cst[hb + x1] : 0;
-      e_n = hb >= 0 ? cst[hb + x1 + n1] : 0;
-    }
-    sts_u32(rs0 + (unsigned)r * (kT * 4), (unsigned)s0);
-    unsigned bits = 0;
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      bits |= (rows_hit<F, D, PERIODIC>(a, q[j], hbmin2) & (unsigned)(j < len)) << j;
-    }
+  for (int r = 0; r < kR; ++r) {
+    const unsigned w = lds_u32(rs0 + (unsigned)r * (kT * 4));
+    const int s0 = (int)(w & kSlotMask), len = (int)(w >> 27);
+    const unsigned bits = rt.run(sp + s0) & ((1u << min(len, kU)) - 1u);
     if (r < 32 / kU) mlo |= bits << (r * kU);
     else mhi |= bits << (r * kU - 32);
-    if (r == Cfg::kRows / 2) s_self = s0;
-    // run tail (more than kU particles in three cells: dense random packings)
-    if (len > kU) {
+    if (r == kR / 2) s_self = s0;
+    if (len > kU) {  // run tail (more than kU particles in three cells: dense random packings)
+      if (len == 31) ovf = true;
       for (int kj = s0 + kU; kj < s0 + len; ++kj)
         if (rows_hit<F, D, PERIODIC>(a, ldg_vec4(sp + kj), hbmin2)) push_extra(kj);
     }
-    // the cell that wraps around the periodic box in x (lanes of the first / last cell of an x-row)
-    if (PERIODIC && x2 >= 0) {
-      const int s2 = cst[hb0 + x2], e2 = cst[hb0 + x2 + 1];
-      for (int kj = s2; kj < e2; ++kj) {
-        const Vec4<F> qq = ldg_vec4(sp + kj);
-        // Domain._displacement (periodic.py:75-79)
-        F rr[3] = {a.x - qq.x, a.y - qq.y, D == 3 ? a.z - qq.z : F(0)};
-        F d2 = F(0);
+  }
+  // the cells that wrap around the periodic box in x (owners in the first / last cell of an x-row, at most a
+  // few lanes of a warp): the warp serves them one owner at a time, lane r taking stencil row r
+  if (PERIODIC) {
+    unsigned todo = __ballot_sync(0xffffffffu, x2 >= 0);
+    while (todo) {
+      const int L = __ffs((int)todo) - 1;
+      todo &= todo - 1u;
+      const int cyL = __shfl_sync(0xffffffffu, cy, L), czL = __shfl_sync(0xffffffffu, cz, L);
+      const int x2L = __shfl_sync(0xffffffffu, x2, L);
+      Body<F> o;
+      o.x = __shfl_sync(0xffffffffu, a.x, L); o.y = __shfl_sync(0xffffffffu, a.y, L);
+      o.z = __shfl_sync(0xffffffffu, a.z, L); o.r = __shfl_sync(0xffffffffu, a.r, L);
+      int neL = __shfl_sync(0xffffffffu, ne, L);
+      bool ovfL = false;
+      int s2 = 0, e2 = 0;
+      if ((int)lane < kR) {
+        const int h2 = wrap1(cyL + (int)lane % 3 - 1, gy) * sy + (D == 3 ? wrap1(czL + (int)lane / 3 - 1, gz) * sz : 0) + x2L;
+        s2 = cst[h2];
+        e2 = cst[h2 + 1];
+      }
+      const unsigned elL = sbase + Cfg::kOffExtra + (tid - lane + (unsigned)L) * 4;  // owner's extra list
+      for (int it = 0; __any_sync(0xffffffffu, s2 + it < e2); ++it) {
+        const int kj = s2 + it;
+        bool hit = false;
+        if (kj < e2) {
+          const Vec4<F> qq = ldg_vec4(sp + kj);
+          // Domain._displacement (periodic.py:75-79)
+          F rr[3] = {o.x - qq.x, o.y - qq.y, D == 3 ? o.z - qq.z : F(0)};
+          F d2 = F(0);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          rr[d] = T::sub(rr[d], T::mul(c.box[b * D + d], T::rint(T::mul(rr[d], c.inv_box[b * D + d]))));
-          d2 += rr[d] * rr[d];
+          for (int d = 0; d < D; ++d) {
+            rr[d] = T::sub(rr[d], T::mul(c.box[b * D + d], T::rint(T::mul(rr[d], c.inv_box[b * D + d]))));
+            d2 += rr[d] * rr[d];
+          }
+          const F rs = o.r + qq.w;
+          hit = d2 < rs * rs * F(1.00001);
         }
-        const F rs = a.r + qq.w;
-        if (d2 < rs * rs * F(1.00001)) push_extra(kj);
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        const int pos = neL + __popc(hm & ((1u << lane) - 1u));
+        if (hit) {
+          if (pos < Cfg::kExtra) sts_u32(elL + (unsigned)pos * (kT * 4), (unsigned)kj);
+          else ovfL = true;
+        }
+        neL += __popc(hm);
+      }
+      ovfL = __any_sync(0xffffffffu, ovfL);
+      __syncwarp();
+      if ((int)lane == L) {
+        ne = min(neL, Cfg::kExtra);
+        ovf |= ovfL;
       }
     }
   }
@@ -649,7 +784,7 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
         const unsigned row = (bit / kU) + (mlo ? 0u : 32u / kU);
         if (mlo) mlo &= mlo - 1u;
         else mhi &= mhi - 1u;
-        kcur = (int)(lds_u32(rs0 + row * (kT * 4)) + bit % kU);
+        kcur = (int)((lds_u32(rs0 + row * (kT * 4)) & kSlotMask) + bit % kU);
       } else if (e < ne) {
         kcur = (int)lds_u32(el0 + (unsigned)e * (kT * 4));
         ++e;
@@ -680,25 +815,48 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
   }
 }
 
+// The systems the row kernel cannot serve (sorted fallback, periodic de-dup, particles outside the grid)
+// take the generic walk INSIDE the same launch (no idle fallback kernel behind every step); kept out of
+// line so that its registers do not weigh on the main path.
 template <typename F, int LAW, int D, bool PERIODIC>
-__global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4) k_pair_rows(Ctx<F> c) {
+__device__ __noinline__ void pair_generic(const Ctx<F>& c, int b, int k, int with_torque) {
+  const GridInfo<typename RT<F>::I> g = c.gi[b];
+  const bool fast = fast_walk_ok(g), simple = !c.clumps && !g.any_bond;
+  if (c.fused) {
+    if (simple) pair_force_body<F, LAW, D, PERIODIC, true, 1>(c, b, k, g, fast, with_torque);
+    else pair_force_body<F, LAW, D, PERIODIC, false, 1>(c, b, k, g, fast, with_torque);
+  } else {
+    if (simple) pair_force_body<F, LAW, D, PERIODIC, true, 0>(c, b, k, g, fast, with_torque);
+    else pair_force_body<F, LAW, D, PERIODIC, false, 0>(c, b, k, g, fast, with_torque);
+  }
+}
+
+template <typename F, int LAW, int D, bool PERIODIC>
+__global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4)
+    k_pair_rows(const __grid_constant__ Ctx<F> c, int with_torque) {  // grid constant: pair_generic takes its address
   pdl_prologue();
   using I = typename RT<F>::I;
   __shared__ __align__(16) unsigned char smem[RowsCfg<D>::kBytes];
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
-  const bool mine = flat_walk_ok(g);
+  const bool mine = rows_ok(c, g);
   if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
-    if (mine) c.overflow[b] = (uint8_t)g.hash_overflow;
-    else if (c.grid_mode == JDB200_GRID_DENSE) c.overflow[b] = 1;  // nobody else serves this system
+    if (mine || c.grid_mode != JDB200_GRID_DENSE) c.overflow[b] = (uint8_t)g.hash_overflow;
+    else c.overflow[b] = 1;  // JDB200_GRID_DENSE and the dense table cannot hold this system
   }
-  if (!mine) return;
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= c.n) return;
+  const long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = k0 < c.n;
+  if (!mine) {
+    if (live && c.grid_mode != JDB200_GRID_DENSE) pair_generic<F, LAW, D, PERIODIC>(c, b, (int)k0, with_torque);
+    return;
+  }
+  // the body uses warp-wide votes: lanes past the end of the array redo the last particle and store nothing
+  const long long k = live ? k0 : c.n - 1;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   F f[3], t[3];
   if (!c.clumps && !g.any_bond) pair_rows_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, sbase, f, t);
   else pair_rows_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, sbase, f, t);
+  if (!live) return;
   const size_t off = (size_t)b * c.n;
   c.sforce[off + k] = Vec4<F>{f[0], f[1], f[2], F(0)};
   if (LAW == JDB200_LAW_CUNDALLSTRACK) c.storque[off + k] = Vec4<F>{t[0], t[1], t[2], F(0)};
@@ -713,7 +871,7 @@ __global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
-  const bool served = flat_walk_ok(g);
+  const bool served = rows_ok(c, g);
   // not served by the row kernel: the generic kernel stores by itself — unless JDB200_GRID_DENSE kept it from
   // being launched; then Collider.overflow is up and the hook still completes, with zero contact forces
   if (!served && c.grid_mode != JDB200_GRID_DENSE) return;
@@ -727,8 +885,82 @@ __global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
     if (c.law == JDB200_LAW_CUNDALLSTRACK) ts = ldg_vec4(c.storque + off + slot);
   }
   const F f[3] = {fs.x, fs.y, fs.z}, t[3] = {ts.x, ts.y, ts.z};
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.urec[2 * (off + i) + 1], (int)i, f, t, with_torque != 0);
+  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.uvm[off + i], (int)i, f, t, with_torque != 0);
   else store_force_torque<F, D>(c, off + i, f, t, g.any_ppr != 0, with_torque != 0);
+}
+
+// k_after, four particles per thread, 128-bit State stores (f32, n % 4 == 0): same values, same order
+template <int D, int EPI>
+__global__ void __launch_bounds__(128) k_after4(Ctx<float> c, int with_torque) {
+  pdl_prologue();
+  using F = float;
+  constexpr int A = D == 3 ? 3 : 1;
+  constexpr int P = 4;
+  const int b = blockIdx.y;
+  const GridInfo<int32_t> g = c.gi[b];
+  const bool served = rows_ok(c, g);
+  if (!served && c.grid_mode != JDB200_GRID_DENSE) return;
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * P;
+  if (i0 >= c.n) return;
+  const size_t off = (size_t)b * c.n, g0 = off + i0;
+  Vec4<F> fs[P], ts[P], vm[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) fs[p] = ts[p] = vm[p] = Vec4<F>{0, 0, 0, 0};
+  if (served) {
+    const int4 sl = *reinterpret_cast<const int4*>(c.inv + g0);
+    const int slot[P] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+    for (int p = 0; p < P; ++p) fs[p] = ldg_vec4(c.sforce + off + slot[p]);
+    if (c.law == JDB200_LAW_CUNDALLSTRACK) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) ts[p] = ldg_vec4(c.storque + off + slot[p]);
+    }
+  }
+  if (EPI == 1) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) vm[p] = c.uvm[g0 + p];
+  }
+  F of[P * D], ov[P * D], ot[P * A];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const F f[3] = {fs[p].x, fs[p].y, fs[p].z}, t[3] = {ts[p].x, ts[p].y, ts[p].z};
+    F o1[3] = {0, 0, 0}, o2[3] = {0, 0, 0}, o3[3] = {0, 0, 0};
+    if (EPI == 1) {
+      fused_sphere_compute<F, D>(c, b, g, vm[p], g0 + p, f, t, with_torque != 0, o1, o2, o3);
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) o1[d] = f[d];
+      if (with_torque) collider_epilogue_compute<F, D>(c, g0 + p, f, t, g.any_ppr != 0, o3);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) { of[p * D + d] = o1[d]; ov[p * D + d] = o2[d]; }
+#pragma unroll
+    for (int a = 0; a < A; ++a) ot[p * A + a] = o3[a];
+  }
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    *reinterpret_cast<float4*>(c.force + g0 * D + 4 * q) = make_float4(of[4 * q], of[4 * q + 1], of[4 * q + 2], of[4 * q + 3]);
+    if (EPI == 1)
+      *reinterpret_cast<float4*>(c.vel + g0 * D + 4 * q) = make_float4(ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]);
+  }
+  if (with_torque) {
+#pragma unroll
+    for (int q = 0; q < A; ++q)
+      *reinterpret_cast<float4*>(c.torque + g0 * A + 4 * q) = make_float4(ot[4 * q], ot[4 * q + 1], ot[4 * q + 2], ot[4 * q + 3]);
+  }
+}
+
+template <int D, int EPI>
+static bool launch_after4(cudaStream_t, Ctx<double>&, int) { return false; }
+template <int D, int EPI>
+static bool launch_after4(cudaStream_t s, Ctx<float>& c, int wt) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (c.n % 4 != 0 || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
+  auto go = [&]() -> int {
+    JDB_LAUNCH((k_after4<D, EPI>), dim3(cdiv(c.n, 4 * 128), c.batch), 128, s, c, wt);
+    return 0;
+  };
+  return go() == 0;
 }
 
 // FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
@@ -1088,11 +1320,13 @@ int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
       constexpr int kT = RowsCfg<D>::kThreads;
       const dim3 gf(cdiv(c.n, kT), c.batch);
       if (c.periodic) {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, true>), gf, kT, s, c));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, true>), gf, kT, s, c, wt));
       } else {
-        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, false>), gf, kT, s, c));
+        JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_rows<F, L, D, false>), gf, kT, s, c, wt));
       }
-      JDB_LAUNCH((k_after<F, D, EPI>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
+      if (!launch_after4<D, EPI>(s, c, wt))
+        JDB_LAUNCH((k_after<F, D, EPI>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
+      return 0;  // the systems it cannot serve took the generic walk inside the same launch
     } else if (c.periodic) {         // wider canonical stencils: x-run kernel
       JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true, EPI>), grid, 128, s, c, wt));
     } else {
