@@ -459,6 +459,9 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
 //      permutation with one 16-byte gather and finishes the hook (collider epilogue, or
 //      the fused force manager + step_after_force) with coalesced State stores.
 // ---------------------------------------------------------------------------
+#ifndef JDB_ROWS_MINB
+#define JDB_ROWS_MINB 10  // resident CTAs per SM the f32 row kernel is compiled for (spring / hertz: 48 registers, no spills)
+#endif
 template <int D>
 struct RowsCfg {
   static constexpr int kThreads = 128;
@@ -832,7 +835,7 @@ __device__ __noinline__ void pair_generic(const Ctx<F>& c, int b, int k, int wit
 }
 
 template <typename F, int LAW, int D, bool PERIODIC>
-__global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? 8 : 4)
+__global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW == JDB200_LAW_CUNDALLSTRACK ? 8 : JDB_ROWS_MINB) : 4)
     k_pair_rows(const __grid_constant__ Ctx<F> c, int with_torque) {  // grid constant: pair_generic takes its address
   pdl_prologue();
   using I = typename RT<F>::I;
