@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define JDB200_ABI_VERSION 2
+#define JDB200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define JDB200_API __attribute__((visibility("default")))
@@ -62,7 +62,8 @@ enum { JDB200_DOMAIN_FREE = 0, JDB200_DOMAIN_PERIODIC = 1, JDB200_DOMAIN_REFLECT
 enum { JDB200_LAW_SPRING = 0, JDB200_LAW_HERTZ = 1, JDB200_LAW_CUNDALLSTRACK = 2 };
 enum { JDB200_LIN_NONE = 0, JDB200_LIN_VERLET = 1, JDB200_LIN_EULER = 2 };
 enum { JDB200_ROT_NONE = 0, JDB200_ROT_VERLETSPIRAL = 1, JDB200_ROT_SPIRAL = 2 };
-enum { JDB200_COLLIDER_NONE = 0, JDB200_COLLIDER_CELLLIST = 1, JDB200_COLLIDER_NAIVE = 2 };
+enum { JDB200_COLLIDER_NONE = 0, JDB200_COLLIDER_CELLLIST = 1, JDB200_COLLIDER_NAIVE = 2,
+       JDB200_COLLIDER_NEIGHBORLIST = 3 /* Verlet list on top of the cell list; needs a jdb200_nlist */ };
 /* cell-table strategy.  AUTO picks, per system and per call, ON THE DEVICE:
  * DENSE (counting sort into a dense cell table) when every cell hash lies in
  * [0, max_cells) and no cell holds more than JDB200_DENSE_MAX_OCC particles,
@@ -211,6 +212,69 @@ JDB200_API int jdb200_naive_compute_force(void* stream, const jdb200_params* p, 
 JDB200_API int jdb200_naive_compute_potential_energy(void* stream, const jdb200_params* p,
                                           const jdb200_state* st, const jdb200_system* sys,
                                           void* ws, size_t ws_bytes, void* energy);
+
+/* ---- collider: NeighborList ("NeighborList", jaxdem/colliders/neighbor_list.py:133-776) ------------ */
+/* The collider's own leaves.  `sys` carries the SECONDARY collider's leaves (cell_size, neighbor_mask of the
+ * DynamicCellList that rebuilds the list, neighbor_list.py:436-440) and sys->collider_overflow is
+ * NeighborList.overflow.  p->max_neighbors = K (static), p->collider = JDB200_COLLIDER_NEIGHBORLIST. */
+typedef struct jdb200_nlist {
+  void* neighbor_list;  /* (B,N,K) I  NeighborList.neighbor_list, -1 padded, rows packed */
+  void* old_pos;        /* (B,N,D) F  NeighborList.old_pos: positions at the last build */
+  void* n_build_times;  /* (B,) I     NeighborList.n_build_times */
+  const void* cutoff;   /* (B,) F     NeighborList.cutoff */
+  const void* skin;     /* (B,) F     NeighborList.skin (absolute) */
+} jdb200_nlist;
+
+/* _check_and_rebuild (neighbor_list.py:57-131): max |pos - old_pos|^2 > skin^2/4 or n_build_times == 0 =>
+ * rebuild through DynamicCellList.create_neighbor_list with radius cutoff + skin (:443-480), old_pos <- pos,
+ * n_build_times += 1, overflow <- the builder's flag.  The decision is taken and acted upon ON THE DEVICE, per
+ * system of the batch; no host synchronisation.  This is NeighborList.create_neighbor_list (:404-441). */
+JDB200_API int jdb200_neighborlist_refresh(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                           const jdb200_system* sys, void* ws, size_t ws_bytes,
+                                           const jdb200_nlist* nl);
+/* NeighborList.compute_force (neighbor_list.py:542-632): refresh, then the list-driven force pass. */
+JDB200_API int jdb200_neighborlist_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                                 const jdb200_system* sys, void* ws, size_t ws_bytes,
+                                                 const jdb200_nlist* nl);
+/* NeighborList.compute_potential_energy (neighbor_list.py:634-727): energy (B,) F. */
+JDB200_API int jdb200_neighborlist_compute_potential_energy(void* stream, const jdb200_params* p,
+                                                            const jdb200_state* st, const jdb200_system* sys,
+                                                            void* ws, size_t ws_bytes, const jdb200_nlist* nl,
+                                                            void* energy);
+/* n x _step_once with the NeighborList collider (same contract as jdb200_system_step). */
+JDB200_API int jdb200_system_step_nl(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                     const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps,
+                                     const jdb200_nlist* nl);
+
+/* ---- minimiser inner loop: `minimize` with the FIRE optimiser ------------------------------------------
+ * jaxdem/minimizers/routines.py:151-383 (loop, carry, termination tests) and jaxdem/minimizers/optimizers.py:127-340
+ * (`fire`: FIREState and its update).  Every array below is a leaf of the reference's while_loop carry. */
+typedef struct jdb200_fire_state {
+  void* vel_pos;  /* (B,N,D) F  FIREState.vel["pos_c"]  */
+  void* vel_rot;  /* (B,N,A) F  FIREState.vel["rotvec"] */
+  void* dt;       /* (B,) F     FIREState.dt    */
+  void* alpha;    /* (B,) F     FIREState.alpha */
+  void* n_good;   /* (B,) int64 FIREState.N_good */
+  void* n_bad;    /* (B,) int64 FIREState.N_bad  */
+  void* pe;       /* (B,) F     carry: potential energy of the current state (total, not per particle) */
+  void* prev_pe;  /* (B,) F     carry: the one before (inf before the first iteration) */
+  void* steps;    /* (B,) int64 carry: iterations taken */
+  void* active;   /* (B,) int32 cond_fun of the while loop: 1 while the system keeps iterating */
+} jdb200_fire_state;
+typedef struct jdb200_fire_params { /* arguments of fire(...) and minimize(...); host scalars (static under jit) */
+  double dt, alpha_init, f_inc, f_dec, f_alpha, dt_max_scale, dt_min_scale;
+  double pe_tol, pe_diff_tol, force_tol;
+  int64_t n_min, n_bad_max, max_steps;
+} jdb200_fire_params;
+/* init != 0: opt_state = init(params), the initial evaluation (routines.py:239-258), steps = 0, active = cond.
+ * Then `n_iter` iterations of body_fun, each a no-op for the systems whose `active` is 0; pe / steps / active are
+ * updated on the device after every iteration, so the caller may poll `active` between calls (or not at all and
+ * run max_steps iterations).  p->collider selects the force / energy evaluation (cell list, naive, or neighbour
+ * list: then `nl` must be given, else NULL).  State is updated in place: pos_c, q, _pos_p_rot, force, torque. */
+JDB200_API int jdb200_minimize_fire(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                    const jdb200_system* sys, void* ws, size_t ws_bytes, const jdb200_nlist* nl,
+                                    const jdb200_fire_state* fs, const jdb200_fire_params* fp, int64_t n_iter,
+                                    int32_t init);
 
 /* ---- ForceManager.apply (jaxdem/forces/force_manager.py:338-425) --------- */
 JDB200_API int jdb200_force_manager_apply(void* stream, const jdb200_params* p, const jdb200_state* st,

@@ -8,19 +8,19 @@ All compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 """
 
 from .components import (Collider, CundallStrackForce, DirectEuler, Domain, DynamicCellList, ForceManager,
-                         ForceModel, FreeDomain, HertzianForce, Integrator, LinearIntegrator, NaiveSimulator,
+                         ForceModel, FreeDomain, HertzianForce, Integrator, LinearIntegrator, NaiveSimulator, NeighborList,
                          PeriodicDomain, ReflectDomain, RotationIntegrator, Spiral, SpringForce,
                          VelocityVerlet, VelocityVerletSpiral)
 from .factory import Factory
 from .materials import Material, MaterialMatchmaker, MaterialTable
 from .state import Quaternion, State, set_default_dtype
 from .system import System
-from . import utils
+from . import minimizers, utils
 
 __all__ = [
     "Collider", "CundallStrackForce", "DirectEuler", "Domain", "DynamicCellList", "Factory", "ForceManager",
     "ForceModel", "FreeDomain", "HertzianForce", "Integrator", "LinearIntegrator", "Material",
-    "MaterialMatchmaker", "MaterialTable", "NaiveSimulator", "PeriodicDomain", "Quaternion", "ReflectDomain",
+    "MaterialMatchmaker", "MaterialTable", "NaiveSimulator", "NeighborList", "PeriodicDomain", "Quaternion", "ReflectDomain",
     "RotationIntegrator", "Spiral", "SpringForce", "State", "System", "VelocityVerlet",
-    "VelocityVerletSpiral", "set_default_dtype", "utils",
+    "VelocityVerletSpiral", "set_default_dtype", "minimizers", "utils",
 ]

@@ -25,6 +25,7 @@ def require_cuda(state) -> None:
 
 def params_for(state, system, *, max_neighbors: int = 0) -> L.Params:
     col = system.collider
+    sec = getattr(col, "secondary_collider", None) or col  # NeighborList: the grid leaves are its cell list's
     batched = state.pos_c.ndim == 3
     p = L.Params()
     p.batch = state.pos_c.shape[0] if batched else 1
@@ -36,13 +37,13 @@ def params_for(state, system, *, max_neighbors: int = 0) -> L.Params:
     p.collider = L.COLLIDER.get(getattr(col, "native_kind", None), 0)
     p.linear_integrator = L.LIN[system.linear_integrator.native_kind]
     p.rotation_integrator = L.ROT[system.rotation_integrator.native_kind]
-    mask = getattr(col, "neighbor_mask", None)
+    mask = getattr(sec, "neighbor_mask", None)
     p.stencil_m = 0 if mask is None else mask.shape[-2]
     p.bond_width = state.bond_id.shape[-1]
     p.n_materials = len(system.mat_table)
-    p.max_neighbors = int(max_neighbors)
-    p.grid_mode = L.GRID[getattr(col, "grid_mode", "auto")]
-    p.max_cells = int(getattr(col, "max_cells", 0) or 0)
+    p.max_neighbors = int(max_neighbors or getattr(col, "max_neighbors", 0) or 0)
+    p.grid_mode = L.GRID[getattr(sec, "grid_mode", "auto")]
+    p.max_cells = int(getattr(sec, "max_cells", 0) or 0)
     kw = getattr(col, "key_windows", None)  # ((lo, len), (lo, len)): rows of the dense table in use (slab.py)
     if kw:
         for w, (lo, ln) in enumerate(kw):
@@ -96,9 +97,10 @@ def system_view(system) -> L.SystemView:
     v.anchor = dom.anchor.data_ptr()
     rc = getattr(dom, "restitution_coefficient", None)
     v.restitution = None if rc is None else rc.data_ptr()
-    cs = getattr(col, "cell_size", None)
+    sec = getattr(col, "secondary_collider", None) or col
+    cs = getattr(sec, "cell_size", None)
     v.cell_size = None if cs is None else cs.data_ptr()
-    nm = getattr(col, "neighbor_mask", None)
+    nm = getattr(sec, "neighbor_mask", None)
     v.neighbor_mask = None if nm is None else nm.data_ptr()
     v.collider_overflow = col.overflow.data_ptr()
     v.interact_same_bond_id = system.interact_same_bond_id.data_ptr()

@@ -18,11 +18,11 @@ DOMAIN = {"free": 0, "periodic": 1, "reflect": 2}
 LAW = {"spring": 0, "hertz": 1, "cundallstrack": 2}
 LIN = {"": 0, "verlet": 1, "euler": 2}
 ROT = {"": 0, "verletspiral": 1, "spiral": 2}
-COLLIDER = {"": 0, "celllist": 1, "naive": 2}
+COLLIDER = {"": 0, "celllist": 1, "naive": 2, "neighborlist": 3}
 GRID = {"auto": 0, "dense": 1, "sorted": 2}
 # jdb200_params.promises (include/jaxdem_b200.h)
 PROMISE_NO_EXT, PROMISE_NO_BONDS, PROMISE_NO_FIXED, PROMISE_NO_POS_P = 1, 2, 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 FRAME_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "q_w", "q_xyz", "pos")  # bit f of jdb200_frame_pack's `fields`
 ERRORS = {-1: "JDB200_EINVAL (bad params)", -2: "JDB200_ENULL (NULL pointer)",
           -3: "JDB200_EWORKSPACE (workspace too small)", -4: "JDB200_ECUDA (kernel launch failed)"}
@@ -56,6 +56,24 @@ class SystemView(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in SYSTEM_FIELDS]
 
 
+class NList(C.Structure):
+    """jdb200_nlist: the NeighborList collider's own leaves."""
+    _fields_ = [(k, C.c_void_p) for k in ("neighbor_list", "old_pos", "n_build_times", "cutoff", "skin")]
+
+
+class FireStateView(C.Structure):
+    """jdb200_fire_state"""
+    _fields_ = [(k, C.c_void_p) for k in ("vel_pos", "vel_rot", "dt", "alpha", "n_good", "n_bad", "pe", "prev_pe",
+                                          "steps", "active")]
+
+
+class FireParams(C.Structure):
+    """jdb200_fire_params"""
+    _fields_ = [(k, C.c_double) for k in ("dt", "alpha_init", "f_inc", "f_dec", "f_alpha", "dt_max_scale",
+                                          "dt_min_scale", "pe_tol", "pe_diff_tol", "force_tol")] + \
+               [(k, C.c_int64) for k in ("n_min", "n_bad_max", "max_steps")]
+
+
 class SlabDesc(C.Structure):
     _fields_ = [("n", C.c_int64), ("cap_mig", C.c_int64), ("cap_ghost", C.c_int64), ("dim", C.c_int32),
                 ("dtype", C.c_int32), ("n_layers", C.c_int32), ("lo_layer", C.c_int32), ("up_layer", C.c_int32),
@@ -72,7 +90,7 @@ class SlabRows(C.Structure):
 
 
 _PP, _PS, _PY = C.POINTER(Params), C.POINTER(StateView), C.POINTER(SystemView)
-_PD, _PR = C.POINTER(SlabDesc), C.POINTER(SlabRows)
+_PD, _PR, _PN = C.POINTER(SlabDesc), C.POINTER(SlabRows), C.POINTER(NList)
 _V, _SZ = C.c_void_p, C.c_size_t
 
 # symbol -> (restype, argtypes); every symbol include/jaxdem_b200.h declares
@@ -95,6 +113,12 @@ SYMBOLS = {
     "jdb200_domain_apply": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
     "jdb200_system_step": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64]),
     "jdb200_celllist_force_step_after": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ]),
+    "jdb200_neighborlist_refresh": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _PN]),
+    "jdb200_neighborlist_compute_force": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _PN]),
+    "jdb200_neighborlist_compute_potential_energy": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _PN, _V]),
+    "jdb200_system_step_nl": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, C.c_int64, _PN]),
+    "jdb200_minimize_fire": (C.c_int, [_V, _PP, _PS, _PY, _V, _SZ, _V, C.POINTER(FireStateView),
+                                       C.POINTER(FireParams), C.c_int64, C.c_int32]),
     "jdb200_frame_pack": (C.c_int, [_V, _PP, _PS, _PY, C.c_int32, _V]),
     "jdb200_slab_message_bytes": (_SZ, [_PD]),
     "jdb200_slab_kept_bytes": (_SZ, [_PD]),

@@ -312,6 +312,118 @@ class DynamicCellList(Collider):
 Collider.register("b200celllist")(DynamicCellList)
 
 
+@Collider.register("NeighborList")
+class NeighborList(Collider):
+    """Verlet neighbour-list collider (reference jaxdem/colliders/neighbor_list.py:133-776): a cached
+    ``(N, max_neighbors)`` list built by the secondary collider with radius ``cutoff + skin`` and rebuilt when a
+    particle has moved further than ``skin / 2`` since the last build.  The decision is taken on the device inside
+    the same call that walks the list (csrc/nlist.cu): no host round trip, legal in CUDA-graph capture, and under a
+    batch axis each system rebuilds only when IT must."""
+    native_kind = "neighborlist"
+
+    def __init__(self, secondary_collider, neighbor_list, old_pos, n_build_times, cutoff, skin, max_neighbors,
+                 overflow=None):
+        super().__init__(overflow)
+        self.secondary_collider = secondary_collider
+        self.neighbor_list, self.old_pos, self.n_build_times = neighbor_list, old_pos, n_build_times
+        self.cutoff, self.skin, self.max_neighbors = cutoff, skin, int(max_neighbors)
+
+    @classmethod
+    def Create(cls, state: State, cutoff, skin=None, skin_fraction=None, max_neighbors=None, number_density=1.0,
+               safety_factor=1.2, secondary_collider_type="CellList", secondary_collider_kw=None):
+        """NeighborList.Create (neighbor_list.py:286-402); host-side, once.  ``skin`` is the absolute buffer
+        distance, ``skin_fraction`` the same as a fraction of ``cutoff`` (default 0.05)."""
+        import warnings
+        from .factory import _normalize_key
+        if skin is not None and skin_fraction is not None:
+            raise ValueError("Pass either `skin` (absolute distance) or `skin_fraction` (fraction of the cutoff), "
+                             "not both.")
+        cutoff = float(cutoff)
+        skin_val = (0.05 if skin_fraction is None else float(skin_fraction)) * cutoff if skin is None else float(skin)
+        reach = cutoff + skin_val
+        dim, N = state.dim, state.N
+        rad = state._rad.detach().double().cpu()
+        pos = state.pos.detach().double().cpu().reshape(-1, N, dim)[0]  # batched: sized from the first system
+        # buffer size: density estimate vs typical packing, capped by the densest packing and by N (:346-392)
+        extent = torch.clamp(pos.amax(0) - pos.amin(0) + 2.0 * rad.max(), min=1.0)
+        density = max(float(number_density), float(pos.shape[0] / extent.prod()))
+        shell = lambda r: ((reach + 0.9 * r) / (0.9 * r)) ** dim
+        hard_cap = int(math.ceil((0.91 if dim == 2 else 0.74) * shell(float(rad.min()))))
+        typical = int(math.ceil(shell(float(rad.mean()))))
+        asked = max_neighbors
+        if max_neighbors is None:
+            ball = math.pi * reach ** dim * (1.0 if dim == 2 else 4.0 / 3.0)
+            max_neighbors = max(int(math.ceil(safety_factor * ball * density)), typical)
+        K = max(min(int(max_neighbors), hard_cap, N), 0)
+        if asked is not None and K < int(asked):
+            warnings.warn(f"NeighborList max_neighbors={asked} clamped to {K} (bounded by N={N} and the physical "
+                          f"packing limit of {hard_cap} neighbors within the search radius).", stacklevel=2)
+        key = _normalize_key(secondary_collider_type)
+        if key not in ("celllist", "b200celllist"):
+            raise NotImplementedError("jaxdem_b200's NeighborList rebuilds through the cell-list collider only "
+                                      f"(secondary_collider_type={secondary_collider_type!r})")
+        kw = dict(secondary_collider_kw or {})
+        kw["state"] = state
+        kw.setdefault("cell_size", reach)
+        sec = Collider.create(secondary_collider_type, **kw)
+        return cls(secondary_collider=sec, neighbor_list=None, old_pos=state.pos.detach().clone(),
+                   n_build_times=None, cutoff=cutoff, skin=skin_val, max_neighbors=K)
+
+    def _bind(self, dtype, device, batch):
+        super()._bind(dtype, device, batch)
+        self.secondary_collider._bind(dtype, device, batch)
+        I = int_dtype_for(dtype)
+        self.old_pos = self.old_pos.to(device=device, dtype=dtype).contiguous()
+        lead = self.old_pos.shape[:-1]
+        self.neighbor_list = torch.full((*lead, self.max_neighbors), -1, dtype=I, device=device)
+        self.n_build_times = torch.zeros((batch,) if batch is not None else (), dtype=I, device=device)
+        self.cutoff = _leaf(self.cutoff, dtype, device, batch, ())
+        self.skin = _leaf(self.skin, dtype, device, batch, ())
+        return self
+
+    def _nlist_view(self):
+        import ctypes as C
+        from . import _lib
+        v = _lib.NList()
+        v.neighbor_list = self.neighbor_list.data_ptr() if self.neighbor_list.numel() else None
+        v.old_pos, v.n_build_times = self.old_pos.data_ptr(), self.n_build_times.data_ptr()
+        v.cutoff, v.skin = self.cutoff.data_ptr(), self.skin.data_ptr()
+        self._nl_keep = v  # keep the struct alive across the asynchronous call
+        return C.byref(v)
+
+    @staticmethod
+    def compute_force(state, system):
+        """-> jdb200_neighborlist_compute_force (neighbor_list.py:542-632)."""
+        _call.call("jdb200_neighborlist_compute_force", state, system, system.collider._nlist_view())
+        return state, system
+
+    @staticmethod
+    def compute_potential_energy(state, system):
+        """-> jdb200_neighborlist_compute_potential_energy (neighbor_list.py:634-727)."""
+        e = torch.empty(state.pos_c.shape[:-2], dtype=state.dtype, device=state.device)
+        _call.call("jdb200_neighborlist_compute_potential_energy", state, system, system.collider._nlist_view(), e)
+        return state, system, e
+
+    @staticmethod
+    def create_neighbor_list(state, system, cutoff=None, max_neighbors=None):
+        """NeighborList.create_neighbor_list (neighbor_list.py:404-441): refresh the cached list if it is stale and
+        return it; ``cutoff`` and ``max_neighbors`` are ignored like in the reference."""
+        col = system.collider
+        _call.call("jdb200_neighborlist_refresh", state, system, col._nlist_view())
+        return state, system, col.neighbor_list, col.overflow
+
+    @staticmethod
+    def create_cross_neighbor_list(pos_a, pos_b, system, cutoff, max_neighbors: int):
+        """Delegates to the secondary collider (neighbor_list.py:729-776)."""
+        import copy
+        inner = copy.copy(system)
+        inner.collider = system.collider.secondary_collider
+        return inner.collider.create_cross_neighbor_list(pos_a, pos_b, inner, cutoff, max_neighbors)
+
+
+Collider.register("b200neighborlist")(NeighborList)
+
+
 # ---------------------------------------------------------------------------
 # Integrators (reference jaxdem/integrators/__init__.py:21-149)
 # ---------------------------------------------------------------------------

@@ -37,7 +37,7 @@ void timing_end(cudaStream_t s) {
 
 template <typename F> int build_partition(cudaStream_t, Ctx<F>&, const F*, int, bool);
 template <typename F> int celllist_force(cudaStream_t, Ctx<F>&, int, bool, bool);
-template <typename F> int celllist_energy(cudaStream_t, Ctx<F>&, F*);
+template <typename F> int celllist_energy(cudaStream_t, Ctx<F>&, F*, bool);
 template <typename F> int celllist_neighbor_list(cudaStream_t, Ctx<F>&, const F*, typename RT<F>::I*, uint8_t*);
 template <typename F> int celllist_cross_neighbor_list(cudaStream_t, Ctx<F>&, const F*, long long, const F*, typename RT<F>::I*, uint8_t*);
 template <typename F> int naive_force(cudaStream_t, Ctx<F>&);
@@ -50,6 +50,10 @@ template <typename F> int linear_after(cudaStream_t, Ctx<F>&);
 template <typename F> int rotation_before(cudaStream_t, Ctx<F>&);
 template <typename F> int rotation_after(cudaStream_t, Ctx<F>&);
 template <typename F> int frame_pack(cudaStream_t, Ctx<F>&, int, void*);
+template <typename F> int neighborlist_refresh(cudaStream_t, Ctx<F>&);
+template <typename F> int minimize_fire(cudaStream_t, Ctx<F>&, int, const jdb200_fire_state*, const jdb200_fire_params*, long long, int);
+template <typename F> int neighborlist_force(cudaStream_t, Ctx<F>&);
+template <typename F> int neighborlist_energy(cudaStream_t, Ctx<F>&, F*);
 
 // ---- partition outputs for parity checks -------------------------------------
 template <typename F>
@@ -105,6 +109,7 @@ template <typename F>
 int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
   if (collider == JDB200_COLLIDER_CELLLIST) return celllist_force<F>(s, c, 0, false, true);
   if (collider == JDB200_COLLIDER_NAIVE) return naive_force<F>(s, c);
+  if (collider == JDB200_COLLIDER_NEIGHBORLIST) return neighborlist_force<F>(s, c);
   // "" no-op collider zeroes force and torque (colliders/__init__.py:56-88)
   if (c.n == 0) return 0;
   if (cudaMemsetAsync(c.force, 0, sizeof(F) * c.batch * c.n * c.dim, s) != cudaSuccess) return JDB200_ECUDA;
@@ -196,6 +201,19 @@ using namespace jdb;
     return EXPR;                                   \
   }
 
+template <typename F>
+static int bind_nlist(Ctx<F>& c, const jdb200_nlist* nl) {
+  using I = typename RT<F>::I;
+  if (!nl || !nl->old_pos || !nl->n_build_times || !nl->cutoff || !nl->skin) return JDB200_ENULL;
+  if (!nl->neighbor_list && c.K > 0 && c.n > 0) return JDB200_ENULL;
+  c.nl_list = (I*)nl->neighbor_list;
+  c.nl_old_pos = (F*)nl->old_pos;
+  c.nl_builds = (I*)nl->n_build_times;
+  c.nl_cutoff = (const F*)nl->cutoff;
+  c.nl_skin = (const F*)nl->skin;
+  return 0;
+}
+
 extern "C" {
 
 JDB200_API int jdb200_abi_version(void) { return JDB200_ABI_VERSION; }
@@ -267,7 +285,7 @@ JDB200_API int jdb200_celllist_compute_potential_energy(void* stream, const jdb2
                                              void* ws, size_t ws_bytes, void* energy) {
   JDB_ENTER(true)
   if (!energy) return JDB200_ENULL;
-  JDB_DISPATCH(celllist_energy<F>(s, c, (F*)energy))
+  JDB_DISPATCH(celllist_energy<F>(s, c, (F*)energy, false))
 }
 
 JDB200_API int jdb200_celllist_create_neighbor_list(void* stream, const jdb200_params* p,
@@ -380,10 +398,73 @@ JDB200_API int jdb200_frame_pack(void* stream, const jdb200_params* p, const jdb
   JDB_DISPATCH(frame_pack<F>(s, c, fields, out))
 }
 
+#define JDB_DISPATCH_NL(EXPR)                      \
+  if (p->dtype == JDB200_F32) {                    \
+    using F = float;                               \
+    Ctx<F> c;                                      \
+    make_ctx<F>(c, p, st, sys, ws);                \
+    if (int e_ = bind_nlist<F>(c, nl)) return e_;  \
+    return EXPR;                                   \
+  } else {                                         \
+    using F = double;                              \
+    Ctx<F> c;                                      \
+    make_ctx<F>(c, p, st, sys, ws);                \
+    if (int e_ = bind_nlist<F>(c, nl)) return e_;  \
+    return EXPR;                                   \
+  }
+
+JDB200_API int jdb200_neighborlist_refresh(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                           const jdb200_system* sys, void* ws, size_t ws_bytes,
+                                           const jdb200_nlist* nl) {
+  JDB_ENTER(true)
+  JDB_DISPATCH_NL(neighborlist_refresh<F>(s, c))
+}
+
+JDB200_API int jdb200_neighborlist_compute_force(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                                 const jdb200_system* sys, void* ws, size_t ws_bytes,
+                                                 const jdb200_nlist* nl) {
+  JDB_ENTER(true)
+  JDB_DISPATCH_NL(neighborlist_force<F>(s, c))
+}
+
+JDB200_API int jdb200_neighborlist_compute_potential_energy(void* stream, const jdb200_params* p,
+                                                            const jdb200_state* st, const jdb200_system* sys,
+                                                            void* ws, size_t ws_bytes, const jdb200_nlist* nl,
+                                                            void* energy) {
+  JDB_ENTER(true)
+  if (!energy) return JDB200_ENULL;
+  JDB_DISPATCH_NL(neighborlist_energy<F>(s, c, (F*)energy))
+}
+
+JDB200_API int jdb200_system_step_nl(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                     const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps,
+                                     const jdb200_nlist* nl) {
+  JDB_ENTER(true)
+  if (n_steps < 0 || p->collider != JDB200_COLLIDER_NEIGHBORLIST) return JDB200_EINVAL;
+  JDB_DISPATCH_NL(system_step<F>(s, c, p->collider, (long long)n_steps))
+}
+
+JDB200_API int jdb200_minimize_fire(void* stream, const jdb200_params* p, const jdb200_state* st,
+                                    const jdb200_system* sys, void* ws, size_t ws_bytes, const jdb200_nlist* nl,
+                                    const jdb200_fire_state* fs, const jdb200_fire_params* fp, int64_t n_iter,
+                                    int32_t init) {
+  JDB_ENTER(true)
+  if (!fs || !fp) return JDB200_ENULL;
+  if (n_iter < 0 || fp->max_steps < 0) return JDB200_EINVAL;
+  if (!fs->vel_pos || !fs->vel_rot || !fs->dt || !fs->alpha || !fs->n_good || !fs->n_bad || !fs->pe || !fs->prev_pe ||
+      !fs->steps || !fs->active)
+    return JDB200_ENULL;
+  if (p->collider == JDB200_COLLIDER_NEIGHBORLIST) {
+    JDB_DISPATCH_NL(minimize_fire<F>(s, c, p->collider, fs, fp, (long long)n_iter, init))
+  }
+  if (p->collider != JDB200_COLLIDER_CELLLIST && p->collider != JDB200_COLLIDER_NAIVE) return JDB200_EINVAL;
+  JDB_DISPATCH(minimize_fire<F>(s, c, p->collider, fs, fp, (long long)n_iter, init))
+}
+
 JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jdb200_state* st,
                        const jdb200_system* sys, void* ws, size_t ws_bytes, int64_t n_steps) {
   JDB_ENTER(true)
-  if (n_steps < 0) return JDB200_EINVAL;
+  if (n_steps < 0 || p->collider == JDB200_COLLIDER_NEIGHBORLIST) return JDB200_EINVAL;  // -> jdb200_system_step_nl
   JDB_DISPATCH(system_step<F>(s, c, p->collider, (long long)n_steps))
 }
 

@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) {  // NeighborList: no rebuild for this system in this call
+    if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) c.coop_bar[0] = 0u;
+    return;
+  }
   __shared__ I s_gd[3], s_stride[3];
   __shared__ int s_ovf, s_dense;
   __shared__ long long s_bound;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
   using U = typename RT<F>::U;
   constexpr int A = D == 3 ? 3 : 1;
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < c.n;
   const size_t gidx = (size_t)b * c.n + (live ? i : 0);
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(128) k_hash4(Ctx<float> c, const float* __rest
   constexpr int A = D == 3 ? 3 : 1;
   constexpr int P = 4;  // particles per thread
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * P;
   const bool live = i0 < c.n;
   const size_t g0 = (size_t)b * c.n + (live ? i0 : 0);
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
   GridInfo<I>& g = c.gi[b];
   if (!g.dense) return;
   const size_t co = (size_t)b * c.cell_stride;
@@ -475,6 +482,7 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
   const GridInfo<I>& g = c.gi[b];
@@ -652,7 +660,7 @@ __global__ void __launch_bounds__(256) k_radix_sort(Ctx<F> c) {
   unsigned phase = 0;
   struct { unsigned* ctr; unsigned* ph; __device__ void sync() { grid_barrier(ctr, *ph); } } grid{c.coop_bar, &phase};
   for (int b = 0; b < c.batch; ++b) {
-    if (use_dense(c.gi[b])) continue;  // grid-uniform
+    if ((c.gate && !c.gate[b]) || use_dense(c.gi[b])) continue;  // grid-uniform
     const I* kin = c.key;
     const int* vin = nullptr;
     for (int p = 0; p < passes; ++p) {
@@ -687,6 +695,7 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= c.n) return;
   const GridInfo<I>& g = c.gi[b];

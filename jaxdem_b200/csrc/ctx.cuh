@@ -67,6 +67,19 @@ struct Ctx {
   unsigned long long* tile_state_clump;  // [B*tiles(N+1)]
   int* tile_counter_clump;     // [B]
   int scan_tiles, radix_blocks, reduce_blocks;
+  // ---- Verlet NeighborList collider (nlist.cu; NULL / unused for every other entry point) ----
+  const int* gate;             // [B] or NULL: the partition / list-build kernels of system b run only when gate[b] != 0
+  int* nl_gate;                // [B] rebuild decision of this call (workspace)
+  F* nl_part;                  // [B*reduce_blocks] per-block max squared displacement (workspace)
+  F* nl_cut;                   // [B] cutoff + skin (workspace)
+  I* nl_list;                  // (B,N,K) NeighborList.neighbor_list
+  F* nl_old_pos;               // (B,N,D) NeighborList.old_pos
+  I* nl_builds;                // (B,)    NeighborList.n_build_times
+  const F *nl_cutoff, *nl_skin;  // (B,)
+  // ---- minimiser (minimize.cu) ----
+  F* min_part;                 // [B*reduce_blocks*4] reduction partials (power lin / rot, max|grad|)
+  F* min_scal;                 // [B*8] per-iteration scalars (old dt, new dt, new alpha, reverse dt, velocity scale)
+  F* min_pe;                   // [B*2] potential energy of the evaluation (collider, force manager)
 };
 
 constexpr int kScanTile = 4096;    // cells per look-back tile (512 threads x 8)
@@ -115,6 +128,12 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start_clump = b.take<int>(B * (N + 1));
   c.tile_state_clump = b.take<unsigned long long>(B * (size_t)cdiv(c.n + 1, kScanTile));
   c.tile_counter_clump = b.take<int>(B);
+  c.nl_gate = b.take<int>(B);
+  c.nl_part = b.take<F>(B * (size_t)c.reduce_blocks);
+  c.nl_cut = b.take<F>(B);
+  c.min_part = b.take<F>(B * (size_t)c.reduce_blocks * 4);
+  c.min_scal = b.take<F>(B * 8);
+  c.min_pe = b.take<F>(B * 2);
   c.inv = c.perm_b;
   c.sforce = reinterpret_cast<Vec4<F>*>(c.segf);
   c.storque = reinterpret_cast<Vec4<F>*>(c.segf2);

@@ -1141,7 +1141,7 @@ __global__ void __launch_bounds__(128) k_neighbor_list(Ctx<F> c, const F* __rest
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= c.n) return;
+  if (k >= c.n || (c.gate && !c.gate[b])) return;
   const size_t off = (size_t)b * c.n;
   const LawCtx<F> lc = make_law_ctx(c, b);
   NlVis<F> vis{c, lc, off};
@@ -1177,7 +1177,7 @@ template <typename F>
 __global__ void k_nl_flag(Ctx<F> c, uint8_t* __restrict__ overflow) {
   pdl_prologue();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= c.batch) return;
+  if (b >= c.batch || (c.gate && !c.gate[b])) return;
   overflow[b] = (uint8_t)(c.gi[b].nl_overflow || c.gi[b].hash_overflow);
 }
 
@@ -1363,10 +1363,11 @@ int celllist_force(cudaStream_t s, Ctx<F>& c, int hash_mode, bool ext, bool with
   return c.dim == 3 ? launch_pair_force<F, 3>(s, c, with_torque) : launch_pair_force<F, 2>(s, c, with_torque);
 }
 
+// reuse: the partition in the workspace is the one a force call of the same State just built (minimiser loop)
 template <typename F>
-int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
+int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy, bool reuse) {
   if (c.n == 0) return cudaMemsetAsync(energy, 0, sizeof(F) * c.batch, s) == cudaSuccess ? 0 : JDB200_ECUDA;
-  int rc = build_partition<F>(s, c, nullptr, 0, false);
+  int rc = reuse ? 0 : build_partition<F>(s, c, nullptr, 0, false);
   if (rc) return rc;
   const dim3 grid(c.reduce_blocks, c.batch);
   JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
@@ -1423,7 +1424,7 @@ int naive_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
 
 #define JDB_INST(F)                                                                     \
   template int celllist_force<F>(cudaStream_t, Ctx<F>&, int, bool, bool);                          \
-  template int celllist_energy<F>(cudaStream_t, Ctx<F>&, F*);                           \
+  template int celllist_energy<F>(cudaStream_t, Ctx<F>&, F*, bool);                     \
   template int celllist_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, RT<F>::I*, uint8_t*); \
   template int celllist_cross_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, long long, const F*, RT<F>::I*, uint8_t*); \
   template int naive_force<F>(cudaStream_t, Ctx<F>&);                                   \

@@ -429,6 +429,69 @@ __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
   }
 }
 
+// ForceManager.compute_potential_energy (force_manager.py:427-479), gravity part: -sum(dot(g, pos_c) * mass / count)
+template <typename F>
+__global__ void __launch_bounds__(kReduceBlock) k_fm_energy(Ctx<F> c, ClumpCsr<F> csr, int have_csr) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  F e = F(0);
+  if (i < c.n) {
+    const size_t gi = (size_t)b * c.n + i;
+    F cnt = F(1);
+    if (have_csr) {
+      int s, en;
+      clump_range(c, csr, b, gi, s, en);
+      cnt = RT<F>::from_int((typename RT<F>::I)(en - s));
+    }
+    F d = F(0);
+    for (int k = 0; k < c.dim; ++k) d += c.gravity[b * c.dim + k] * c.pos_c[gi * c.dim + k];
+    e = d * c.mass[gi] / cnt;
+  }
+  __shared__ F sm[kReduceBlock];
+  sm[threadIdx.x] = e;
+  __syncthreads();
+  for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blockIdx.x] = sm[0];
+}
+template <typename F>
+__global__ void __launch_bounds__(kReduceBlock) k_fm_energy_final(Ctx<F> c, F* __restrict__ out) {
+  pdl_prologue();
+  const int b = blockIdx.x;
+  F acc = F(0);
+  for (int i = threadIdx.x; i < c.reduce_blocks; i += kReduceBlock) acc += c.partial[(size_t)b * c.reduce_blocks + i];
+  __shared__ F sm[kReduceBlock];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kReduceBlock / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[b] = -sm[0];
+}
+
+// ForceManager.apply followed by ForceManager.compute_potential_energy on the same clump CSR (minimiser loop)
+template <typename F>
+int force_manager_apply_pe(cudaStream_t s, Ctx<F>& c, F* pe_out) {
+  if (c.n == 0) return cudaMemsetAsync(pe_out, 0, sizeof(F) * c.batch, s) == cudaSuccess ? 0 : JDB200_ECUDA;
+  const dim3 gp(cdiv(c.n, 256), c.batch);
+  ClumpCsr<F> csr{nullptr, nullptr};
+  if (!c.clumps) {
+    JDB_LAUNCH(k_fm_spheres<F>, gp, 256, s, c);
+  } else {
+    int rc = build_clump_csr<F>(s, c, &csr);
+    if (rc) return rc;
+    JDB_LAUNCH(k_fm_totals<F>, gp, 256, s, c, csr);
+    JDB_LAUNCH(k_fm_reduce<F>, gp, 256, s, c, csr);
+  }
+  JDB_LAUNCH(k_fm_energy<F>, dim3(c.reduce_blocks, c.batch), kReduceBlock, s, c, csr, c.clumps ? 1 : 0);
+  JDB_LAUNCH(k_fm_energy_final<F>, dim3(c.batch), kReduceBlock, s, c, pe_out);
+  return 0;
+}
+
 template <typename F>
 int force_manager_apply(cudaStream_t s, Ctx<F>& c) {
   if (c.n == 0) return 0;
@@ -962,6 +1025,7 @@ int frame_pack(cudaStream_t s, Ctx<F>& c, int fields, void* out) {
 #define JDB_INST(F)                                                   \
   template int frame_pack<F>(cudaStream_t, Ctx<F>&, int, void*);      \
   template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
+  template int force_manager_apply_pe<F>(cudaStream_t, Ctx<F>&, F*);  \
   template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
   template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \
   template int linear_before<F>(cudaStream_t, Ctx<F>&);               \

@@ -20,6 +20,7 @@ from . import _call, _lib
 from .components import (Collider, Domain, ForceManager, ForceModel, LinearIntegrator, RotationIntegrator,
                          _leaf)
 from .materials import Material, MaterialMatchmaker, MaterialTable
+from .minimizers import make_minimizer
 from .state import State
 
 
@@ -40,7 +41,8 @@ class System:
                linear_integrator_kw=None, rotation_integrator_kw=None, collider_kw=None, domain_kw=None,
                force_model_kw=None, collider=None, domain=None, force_manager=None,
                interact_same_bond_id=False, user_pre_step_actions: Callable = _identity,
-               user_post_step_actions: Callable = _identity, dtype=None, device=None) -> "System":
+               user_post_step_actions: Callable = _identity, minimizer=None, minimizer_kw=None, dtype=None,
+               device=None) -> "System":
         from .state import default_device, default_float
         F = dtype or default_float()
         dev = torch.device(device) if device is not None else default_device()
@@ -79,6 +81,7 @@ class System:
             step_count=torch.zeros((batch,) if batch is not None else (), dtype=torch.int64, device=dev),
             dim=dim, interact_same_bond_id=_leaf(bool(interact_same_bond_id), torch.bool, dev, batch, ()),
             user_pre_step_actions=user_pre_step_actions, user_post_step_actions=user_post_step_actions,
+            minimizer=make_minimizer(minimizer, minimizer_kw, dt),
         )
 
     # -- stepping -------------------------------------------------------------------
@@ -127,13 +130,23 @@ class System:
             fused = system._is_native()
         if fused:
             # time and step_count advance on the device, once per step, inside the same call
-            _call.call("jdb200_system_step", state, system, C.c_int64(n), clock=True)
+            if system.collider.native_kind == "neighborlist":
+                _call.call("jdb200_system_step_nl", state, system, C.c_int64(n), system.collider._nlist_view(),
+                           clock=True)
+            else:
+                _call.call("jdb200_system_step", state, system, C.c_int64(n), clock=True)
             if n > 0:
                 system.force_manager.mark_clean()  # every step ends with the external buffers cleared
         else:
             for _ in range(n):
                 state, system = System._step_once(state, system)
         return state, system
+
+    @staticmethod
+    def minimize(state: State, system: "System", **kw):
+        """System.minimize (system.py:811-842) -> jaxdem_b200.minimizers.minimize."""
+        from .minimizers import minimize
+        return minimize(state, system, **kw)
 
     @staticmethod
     def compile_step(state: State, system: "System", *, n: int = 1) -> "CompiledStep":

@@ -1,4 +1,4 @@
-"""numpy restatement of the naive and cell-list colliders.  Oracle only.
+"""numpy restatement of the naive, cell-list and Verlet neighbour-list colliders.  Oracle only.
 
 jaxdem/colliders/__init__.py:225-243 (mask), naive.py:73-235,
 _partition.py:23-150, cell_list.py:35-96,99-174,187-261,374-595.
@@ -379,12 +379,132 @@ def celllist_create_cross_neighbor_list(pos_a, pos_b, system, cutoff, max_neighb
     count_ovf = bool(np.any(total > max_neighbors))
     return nl, bool(any_stencil_ovf or count_ovf or ovf_a or ovf_b)
 
+# --------------------------------------------------------------------------
+# Verlet NeighborList collider (jaxdem/colliders/neighbor_list.py:57-131, 286-480, 542-727)
+# --------------------------------------------------------------------------
+
+
+class ONeighborList:
+    """Fields of NeighborList (neighbor_list.py:262-284)."""
+
+    kind = "neighborlist"
+
+    def __init__(self, secondary, neighbor_list, old_pos, cutoff, skin, max_neighbors):
+        self.secondary_collider = secondary
+        self.neighbor_list = neighbor_list
+        self.old_pos = old_pos
+        self.n_build_times = 0
+        self.cutoff = cutoff
+        self.skin = skin
+        self.max_neighbors = int(max_neighbors)
+        self.overflow = False
+
+
+def neighborlist_max_neighbors(state, cutoff, skin_val, max_neighbors=None, number_density=1.0, safety_factor=1.2):
+    """The buffer-size heuristics of NeighborList.Create (neighbor_list.py:346-392)."""
+    list_cutoff = cutoff + skin_val
+    dim, N = state.dim, state.N
+    max_rad = float(np.max(state._rad))
+    pos = state.pos
+    box = np.maximum(pos.max(axis=0) - pos.min(axis=0) + 2.0 * max_rad, 1.0)
+    density_est = float(N / np.prod(box.astype(np.float64)))
+    eff_density = max(number_density, density_est)
+    r_eff = 0.9 * float(np.min(state._rad))
+    upper = ((list_cutoff + r_eff) / r_eff) ** dim
+    max_possible = int(np.ceil((0.91 if dim == 2 else 0.74) * upper))
+    r_eff_mean = 0.9 * float(np.mean(state._rad))
+    typical = int(np.ceil(((list_cutoff + r_eff_mean) / r_eff_mean) ** dim))
+    if max_neighbors is None:
+        vol = np.pi * list_cutoff**dim * (1.0 if dim == 2 else 4.0 / 3.0)
+        max_neighbors = max(int(np.ceil(safety_factor * vol * eff_density)), typical)
+    return max(min(max_neighbors, max_possible, N), 0)
+
+
+def neighborlist_create(state, cutoff, skin=None, skin_fraction=None, max_neighbors=None, number_density=1.0,
+                        safety_factor=1.2, secondary_collider_kw=None) -> ONeighborList:
+    """NeighborList.Create (neighbor_list.py:286-402), secondary collider = CellList with
+    cell_size = cutoff + skin unless given."""
+    if skin is not None and skin_fraction is not None:
+        raise ValueError("Pass either `skin` or `skin_fraction`, not both.")
+    if skin is None:
+        skin_val = float(0.05 if skin_fraction is None else skin_fraction) * cutoff
+    else:
+        skin_val = float(skin)
+    K = neighborlist_max_neighbors(state, cutoff, skin_val, max_neighbors, number_density, safety_factor)
+    kw = dict(secondary_collider_kw or {})
+    kw.pop("state", None)
+    kw.setdefault("cell_size", cutoff + skin_val)
+    sec = celllist_create(state, **kw)
+    F = state.fdtype
+    return ONeighborList(sec, np.full((state.N, K), -1, state.idtype), state.pos.copy(), F.type(cutoff),
+                         F.type(skin_val), K)
+
+
+def neighborlist_check_and_rebuild(state, system):
+    """_check_and_rebuild (neighbor_list.py:57-131), no history."""
+    col = system.collider
+    disp = state.pos - col.old_pos  # deliberately not a periodic displacement (:81-83)
+    max_disp_sq = np.max(la.norm2(disp)) if state.N else state.fdtype.type(0)
+    trigger = col.skin**2 / state.fdtype.type(4)
+    if (max_disp_sq > trigger) or col.n_build_times == 0:
+        list_cutoff = col.cutoff + col.skin  # _rebuild :463
+        system.collider = col.secondary_collider
+        try:
+            nl, ovf = celllist_create_neighbor_list(state, system, list_cutoff, col.max_neighbors)
+        finally:
+            system.collider = col
+        col.neighbor_list = nl
+        col.old_pos = state.pos.copy()
+        col.n_build_times += 1
+        col.overflow = ovf
+    return col.neighbor_list
+
+
+def _nl_pairs(state, system):
+    """(i, j) of every list entry that passes the -1 test and valid_interaction_mask as NeighborList calls it
+    (neighbor_list.py:588-598: clump of i, clump of j, bond row of i, index j), in list order."""
+    nl = neighborlist_check_and_rebuild(state, system)
+    N, K = nl.shape
+    ii = np.repeat(np.arange(N), K)
+    jj = nl.reshape(-1).astype(np.int64)
+    keep = jj != -1
+    ii, jj = ii[keep], jj[keep]
+    valid = valid_interaction_mask(state.clump_id[ii], state.clump_id[jj], state.bond_id[ii], jj,
+                                   system.interact_same_bond_id) > 0
+    return ii[valid], jj[valid]
+
+
+def neighborlist_compute_force(state, system):
+    """NeighborList.compute_force (neighbor_list.py:542-632)."""
+    force_fn = LAWS[system.force_model][0]
+    ii, jj = _nl_pairs(state, system)
+    F = np.zeros_like(state.force)
+    T = np.zeros_like(state.torque)
+    if len(ii):
+        f, t = force_fn(ii, jj, state.pos, state, system)
+        np.add.at(F, ii, f.astype(F.dtype))  # list order within a row
+        np.add.at(T, ii, t.astype(T.dtype))
+    state.force = F
+    state.torque = T + la.cross(state._pos_p_rot, F)
+
+
+def neighborlist_compute_potential_energy(state, system):
+    """NeighborList.compute_potential_energy (neighbor_list.py:634-727)."""
+    energy_fn = LAWS[system.force_model][1]
+    ii, jj = _nl_pairs(state, system)
+    E = np.zeros(state.N, state.fdtype)
+    if len(ii):
+        np.add.at(E, ii, energy_fn(ii, jj, state.pos, state, system).astype(E.dtype))
+    return (state.fdtype.type(0.5) * E).sum()
+
 
 def compute_force(state, system):
     if system.collider_type == "naive":
         naive_compute_force(state, system)
     elif system.collider_type == "celllist":
         celllist_compute_force(state, system)
+    elif system.collider_type == "neighborlist":
+        neighborlist_compute_force(state, system)
     else:  # "" no-op collider (colliders/__init__.py:56-88)
         state.force = state.force * 0
         state.torque = state.torque * 0
@@ -395,4 +515,6 @@ def compute_potential_energy(state, system):
         return naive_compute_potential_energy(state, system)
     if system.collider_type == "celllist":
         return celllist_compute_potential_energy(state, system)
+    if system.collider_type == "neighborlist":
+        return neighborlist_compute_potential_energy(state, system)
     return state.fdtype.type(0.0)

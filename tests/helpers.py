@@ -102,6 +102,8 @@ def build_gpu(inp, *, dtype, domain="periodic", law="spring", collider="CellList
         ckw.update(state=st, grid_mode=grid_mode)
         if max_cells is not None:
             ckw["max_cells"] = max_cells
+    elif collider.lower() == "neighborlist":
+        ckw.update(state=st)
     sy = jd.System.create(
         st.shape, dt=dt, linear_integrator_type=lin, rotation_integrator_type=rot, collider_type=collider,
         collider_kw=ckw, domain_type=domain, domain_kw=dkw, force_model_type=law, mat_table=mt,

@@ -229,3 +229,44 @@ def test_cross_neighbor_list_against_brute_force(dim, domain):
     assert ocol.celllist_create_cross_neighbor_list(pos_a[:0], ost.pos, osy, cutoff, 8)[0].shape == (0, 8)
     e = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos[:0], osy, cutoff, 8)
     assert (e[0] == -1).all() and not e[1]
+
+
+def test_neighborlist_oracle_pins():
+    # reference tests/test_clump_pair_friction.py:190-217: a fresh NeighborList is built before it is read
+    # (force [-0.2, 0] for overlap 0.2, n_build_times == 1); tests/test_excluded_pairs.py:11-61 through the
+    # NeighborList over a CellList; tests/test_colliders_invariance.py: same forces as the naive collider.
+    mt = oracle.make_material_table([dict(young=1.0, poisson=0.3, density=1.0)])
+    st = oracle.create_state([[0.0, 0.0], [0.8, 0.0]], rad=[0.5, 0.5], mass=[1, 1], clump_id=[0, 1])
+    sy = _sys(st, collider_type="neighborlist", collider_kw=dict(cutoff=1.5, skin=0.1, max_neighbors=10),
+              domain_type="periodic", domain_kw=dict(box_size=[10.0, 10.0]), mat_table=mt)
+    assert sy.collider.max_neighbors == 2 and (sy.collider.neighbor_list == -1).all()
+    colliders.compute_force(st, sy)
+    np.testing.assert_allclose(st.force[0], [-0.2, 0.0], atol=1e-14)
+    assert sy.collider.n_build_times == 1
+    colliders.compute_force(st, sy)
+    assert sy.collider.n_build_times == 1  # nothing moved
+    st.pos_c = st.pos_c + np.array([[0.051, 0.0], [0.0, 0.0]])  # further than skin / 2
+    colliders.compute_force(st, sy)
+    assert sy.collider.n_build_times == 2
+    mt = oracle.make_material_table([dict(young=1000.0, poisson=0.3, density=1.0)], "linear")
+    st = oracle.create_state([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]], rad=[1.1] * 3, bond_id=[[1], [0, 2], [1]])
+    sy = _sys(st, dt=1e-3, collider_type="neighborlist", collider_kw=dict(cutoff=3.0, skin=0.5), mat_table=mt)
+    colliders.compute_force(st, sy)
+    assert np.allclose(st.force[1], 0.0, atol=1e-5) and abs(st.force[0, 0]) > 0.1
+    assert np.allclose(st.force[0], -st.force[2], atol=1e-5)
+    rng = np.random.default_rng(3)
+    for dim in (2, 3):
+        n = 300
+        L = (n / 0.9) ** (1 / dim)
+        pos = rng.uniform(0, L, (n, dim))
+        a = oracle.create_state(pos, rad=rng.uniform(0.35, 0.5, n))
+        b = a.copy()
+        kw = dict(domain_type="periodic", domain_kw=dict(box_size=[L] * dim))
+        sa = _sys(a, collider_type="neighborlist", collider_kw=dict(cutoff=1.0, skin=0.2), **kw)
+        sb = _sys(b, collider_type="naive", **kw)
+        colliders.compute_force(a, sa)
+        colliders.compute_force(b, sb)
+        assert not sa.collider.overflow
+        np.testing.assert_allclose(a.force, b.force, atol=1e-9 * np.abs(b.force).max())
+        np.testing.assert_allclose(colliders.compute_potential_energy(a, sa),
+                                   colliders.compute_potential_energy(b, sb), rtol=1e-12)
