@@ -913,6 +913,17 @@ def run_cuda_slab(args, world, rank, local, dev):
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     e2e_value = n_total * e2e_steps / float(tm[0].item())
+    # per-kernel device time of rank 0's step (diagnostic events; separate pass, all ranks step together)
+    _lib.kernel_timing(rank == 0)
+    for _ in range(5):
+        flush_l2()
+        slab.step(1)
+    torch.cuda.synchronize()
+    kt = _lib.kernel_timing_collect() if rank == 0 else {}
+    _lib.kernel_timing(False)
+    kernels = {k: {"us_per_launch": 1e3 * v[0] / v[1], "launches_per_step": v[1] / 5.0, "us_per_step": 1e3 * v[0] / 5.0}
+               for k, v in kt.items()}
+    barrier()
     peak, peak_src = measured_peak()
     step_gbs = b_alg * n_total * args.steps / (ms_max * 1e-3) / 1e9
     own = torch.tensor([slab.n_own, slab.n_ghost], dtype=torch.int64, device=dev)
@@ -934,7 +945,8 @@ def run_cuda_slab(args, world, rank, local, dev):
             "gpu_launches": int(launches),
             "parity": parity,
             "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
-            "roofline": None,
+            "roofline": dominant_roofline(kernels, n, peak, peak_src, cfg),
+            "kernels_rank0": kernels,
             "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s",
                               "frac": step_gbs / (peak * world), "algorithmic_bytes_per_particle_step": b_alg,
                               "peak_source": peak_src + f" x {world} GPUs"},

@@ -63,7 +63,11 @@ enum { JDB200_LAW_SPRING = 0, JDB200_LAW_HERTZ = 1, JDB200_LAW_CUNDALLSTRACK = 2
 enum { JDB200_LIN_NONE = 0, JDB200_LIN_VERLET = 1, JDB200_LIN_EULER = 2 };
 enum { JDB200_ROT_NONE = 0, JDB200_ROT_VERLETSPIRAL = 1, JDB200_ROT_SPIRAL = 2 };
 enum { JDB200_COLLIDER_NONE = 0, JDB200_COLLIDER_CELLLIST = 1, JDB200_COLLIDER_NAIVE = 2,
-       JDB200_COLLIDER_NEIGHBORLIST = 3 /* Verlet list on top of the cell list; needs a jdb200_nlist */ };
+       JDB200_COLLIDER_NEIGHBORLIST = 3 /* Verlet list on top of the cell list; needs a jdb200_nlist */,
+       JDB200_COLLIDER_MULTICELLLIST = 4 /* DynamicMultiCellList (jaxdem/colliders/multi_cell_list.py:46-73,142-254):
+                                            the jdb200_celllist_* entry points with this value prune every stencil
+                                            cell by its expandable AABB (segmented min / max over the cell's sorted
+                                            run) before walking it; same results as the cell list */ };
 /* cell-table strategy.  AUTO picks, per system and per call, ON THE DEVICE:
  * DENSE (counting sort into a dense cell table) when every cell hash lies in
  * [0, max_cells) and no cell holds more than JDB200_DENSE_MAX_OCC particles,

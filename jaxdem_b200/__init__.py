@@ -7,7 +7,7 @@ All compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 ``include/jaxdem_b200.h``; there is no CPU fallback.
 """
 
-from .components import (Collider, CundallStrackForce, DirectEuler, Domain, DynamicCellList, ForceManager,
+from .components import (Collider, CundallStrackForce, DirectEuler, Domain, DynamicCellList, DynamicMultiCellList, ForceManager,
                          ForceModel, FreeDomain, HertzianForce, Integrator, LinearIntegrator, NaiveSimulator, NeighborList,
                          PeriodicDomain, ReflectDomain, RotationIntegrator, Spiral, SpringForce,
                          VelocityVerlet, VelocityVerletSpiral)
@@ -18,7 +18,7 @@ from .system import System
 from . import minimizers, utils
 
 __all__ = [
-    "Collider", "CundallStrackForce", "DirectEuler", "Domain", "DynamicCellList", "Factory", "ForceManager",
+    "Collider", "CundallStrackForce", "DirectEuler", "Domain", "DynamicCellList", "DynamicMultiCellList", "Factory", "ForceManager",
     "ForceModel", "FreeDomain", "HertzianForce", "Integrator", "LinearIntegrator", "Material",
     "MaterialMatchmaker", "MaterialTable", "NaiveSimulator", "NeighborList", "PeriodicDomain", "Quaternion", "ReflectDomain",
     "RotationIntegrator", "Spiral", "SpringForce", "State", "System", "VelocityVerlet",

@@ -18,7 +18,7 @@ DOMAIN = {"free": 0, "periodic": 1, "reflect": 2}
 LAW = {"spring": 0, "hertz": 1, "cundallstrack": 2}
 LIN = {"": 0, "verlet": 1, "euler": 2}
 ROT = {"": 0, "verletspiral": 1, "spiral": 2}
-COLLIDER = {"": 0, "celllist": 1, "naive": 2, "neighborlist": 3}
+COLLIDER = {"": 0, "celllist": 1, "naive": 2, "neighborlist": 3, "multicelllist": 4}
 GRID = {"auto": 0, "dense": 1, "sorted": 2}
 # jdb200_params.promises (include/jaxdem_b200.h)
 PROMISE_NO_EXT, PROMISE_NO_BONDS, PROMISE_NO_FIXED, PROMISE_NO_POS_P = 1, 2, 4, 8

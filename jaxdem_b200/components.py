@@ -312,6 +312,30 @@ class DynamicCellList(Collider):
 Collider.register("b200celllist")(DynamicCellList)
 
 
+@Collider.register("MultiCellList")
+class DynamicMultiCellList(DynamicCellList):
+    """Loose-grid collider (reference jaxdem/colliders/multi_cell_list.py:283-702): the cell list's partition plus
+    an expandable AABB per occupied cell (segmented min / max of the members' boxes over the cell's sorted run);
+    a stencil cell whose AABB does not reach the query box is skipped before its run is walked.  The prune only
+    drops cells without contacts, so forces, energies and neighbour lists equal DynamicCellList's.  Same C-ABI entry
+    points as the cell list with ``collider = JDB200_COLLIDER_MULTICELLLIST``."""
+    native_kind = "multicelllist"
+
+    @classmethod
+    def Create(cls, state: State, cell_size=None, search_range=None, box_size=None, max_hashes=None, max_cells=None,
+               grid_mode="auto"):
+        """DynamicMultiCellList.Create (multi_cell_list.py:330-392): the cell defaults to 2 r_max whatever the
+        polydispersity; ``max_hashes`` is the reference's deprecated no-op."""
+        del max_hashes
+        if cell_size is None:
+            cell_size = 2.0 * state._rad.detach().cpu().to(state.dtype).max()
+        return super().Create(state, cell_size=cell_size, search_range=search_range, box_size=box_size,
+                              max_cells=max_cells, grid_mode=grid_mode)
+
+
+Collider.register("b200multicelllist")(DynamicMultiCellList)
+
+
 @Collider.register("NeighborList")
 class NeighborList(Collider):
     """Verlet neighbour-list collider (reference jaxdem/colliders/neighbor_list.py:133-776): a cached

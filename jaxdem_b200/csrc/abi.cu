@@ -107,7 +107,8 @@ int partition_entry(cudaStream_t s, Ctx<F>& c, void* perm, void* sorted_hash, vo
 
 template <typename F>
 int collider_force(cudaStream_t s, Ctx<F>& c, int collider) {
-  if (collider == JDB200_COLLIDER_CELLLIST) return celllist_force<F>(s, c, 0, false, true);
+  if (collider == JDB200_COLLIDER_CELLLIST || collider == JDB200_COLLIDER_MULTICELLLIST)
+    return celllist_force<F>(s, c, 0, false, true);
   if (collider == JDB200_COLLIDER_NAIVE) return naive_force<F>(s, c);
   if (collider == JDB200_COLLIDER_NEIGHBORLIST) return neighborlist_force<F>(s, c);
   // "" no-op collider zeroes force and torque (colliders/__init__.py:56-88)
@@ -457,7 +458,9 @@ JDB200_API int jdb200_minimize_fire(void* stream, const jdb200_params* p, const 
   if (p->collider == JDB200_COLLIDER_NEIGHBORLIST) {
     JDB_DISPATCH_NL(minimize_fire<F>(s, c, p->collider, fs, fp, (long long)n_iter, init))
   }
-  if (p->collider != JDB200_COLLIDER_CELLLIST && p->collider != JDB200_COLLIDER_NAIVE) return JDB200_EINVAL;
+  if (p->collider != JDB200_COLLIDER_CELLLIST && p->collider != JDB200_COLLIDER_NAIVE &&
+      p->collider != JDB200_COLLIDER_MULTICELLLIST)
+    return JDB200_EINVAL;
   JDB_DISPATCH(minimize_fire<F>(s, c, p->collider, fs, fp, (long long)n_iter, init))
 }
 

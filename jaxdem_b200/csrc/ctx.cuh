@@ -76,6 +76,11 @@ struct Ctx {
   F* nl_old_pos;               // (B,N,D) NeighborList.old_pos
   I* nl_builds;                // (B,)    NeighborList.n_build_times
   const F *nl_cutoff, *nl_skin;  // (B,)
+  // ---- MultiCellList (loose-grid AABB pruning, pair.cu) ----
+  int prune;                   // 1: every stencil cell is tested against its expandable AABB before its run is walked
+  const F* prune_cut;          // [B] or NULL: neighbour-list builds prune with a query box of +-cutoff around the point
+  Vec4<F>* aabb_c;             // [B*N] cell AABB centre, stored at the FIRST sorted slot of the cell's run
+  Vec4<F>* aabb_h;             // [B*N] cell AABB half extent, same indexing
   // ---- minimiser (minimize.cu) ----
   F* min_part;                 // [B*reduce_blocks*4] reduction partials (power lin / rot, max|grad|)
   F* min_scal;                 // [B*8] per-iteration scalars (old dt, new dt, new alpha, reverse dt, velocity scale)
@@ -128,6 +133,8 @@ inline size_t carve(Ctx<F>& c, void* ws) {
   c.cell_start_clump = b.take<int>(B * (N + 1));
   c.tile_state_clump = b.take<unsigned long long>(B * (size_t)cdiv(c.n + 1, kScanTile));
   c.tile_counter_clump = b.take<int>(B);
+  c.aabb_c = b.take<Vec4<F>>(BN);
+  c.aabb_h = b.take<Vec4<F>>(BN);
   c.nl_gate = b.take<int>(B);
   c.nl_part = b.take<F>(B * (size_t)c.reduce_blocks);
   c.nl_cut = b.take<F>(B);
@@ -166,6 +173,8 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
     c.win_len[w] = p->key_window_len[w];
   }
   c.rot = p->rotation_integrator;
+  c.prune = p->collider == JDB200_COLLIDER_MULTICELLLIST;
+  if (c.prune) c.want_skey = 1;  // run boundaries of the sorted hashes, dense or sorted
   if (st) {
     c.pos_c = (F*)st->pos_c; c.pos_p = (F*)st->pos_p; c.vel = (F*)st->vel; c.force = (F*)st->force;
     c.q_w = (F*)st->q_w; c.q_xyz = (F*)st->q_xyz; c.ang_vel = (F*)st->ang_vel;

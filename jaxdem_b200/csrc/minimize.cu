@@ -288,7 +288,7 @@ __global__ void k_fire_init(Ctx<F> c, Fire<F> fs) {
 template <typename F>
 static int fire_eval(cudaStream_t s, Ctx<F>& c, int collider) {
   int rc = 0;
-  if (collider == JDB200_COLLIDER_CELLLIST) {
+  if (collider == JDB200_COLLIDER_CELLLIST || collider == JDB200_COLLIDER_MULTICELLLIST) {
     if ((rc = celllist_force<F>(s, c, 0, false, true))) return rc;
     if ((rc = celllist_energy<F>(s, c, c.min_pe, true))) return rc;  // same positions: the partition is reused
   } else if (collider == JDB200_COLLIDER_NAIVE) {

@@ -71,10 +71,46 @@ __device__ __forceinline__ bool pair_valid(const Ctx<F>& c, size_t off, int owne
 // Walk the stencil of sorted slot k: calls vis.cell(m, start, end) for every stencil
 // row whose target cell is looked up (rows removed by the periodic de-dup are skipped;
 // the reference turns them into hash -1, which no periodic cell carries).
+// MultiCellList (multi_cell_list.py:186-204, 475-481): does the query box overlap the expandable AABB of the cell
+// whose sorted run starts at slot s?  dr = Domain.displacement(query centre, cell centre) (division form).
+template <typename F>
+__device__ __forceinline__ bool aabb_overlap(const Ctx<F>& c, int b, size_t off, int s, const F* qc, const F* qh) {
+  using T = RT<F>;
+  const Vec4<F> cc = c.aabb_c[off + s], hh = c.aabb_h[off + s];
+  const F cv[3] = {cc.x, cc.y, cc.z}, hv[3] = {hh.x, hh.y, hh.z};
+  for (int d = 0; d < c.dim; ++d) {
+    F dr = T::sub(qc[d], cv[d]);
+    if (c.periodic) {
+      const F bx = c.box[b * c.dim + d];
+      dr = T::sub(dr, T::mul(bx, T::rint(T::div(dr, bx))));
+    }
+    if (!(T::abs(dr) <= T::add(qh[d], hv[d]))) return false;
+  }
+  return true;
+}
+
 template <typename F, typename Vis>
 __device__ __forceinline__ void walk_stencil_at(const Ctx<F>& c, int b, const F* pp, const F* cell_size_override,
-                                                Vis& vis) {
+                                                Vis& vis, F qrad = F(-1)) {
   using I = typename RT<F>::I;
+  using T = RT<F>;
+  // loose-grid pruning: query box = the particle's own box [pos - rad, pos + rad] (force / energy), or the point
+  // +- cutoff (neighbour-list builds)
+  F qc[3] = {0, 0, 0}, qh[3] = {0, 0, 0};
+  bool prune = false;
+  if (c.prune) {
+    if (c.prune_cut) {
+      prune = true;
+      for (int d = 0; d < c.dim; ++d) { qc[d] = pp[d]; qh[d] = c.prune_cut[b]; }
+    } else if (qrad >= F(0)) {
+      prune = true;
+      for (int d = 0; d < c.dim; ++d) {
+        const F lo = T::sub(pp[d], qrad), hi = T::add(pp[d], qrad);
+        qc[d] = T::mul(F(0.5), T::add(lo, hi));
+        qh[d] = T::mul(F(0.5), T::sub(hi, lo));
+      }
+    }
+  }
   const GridInfo<I> g = c.gi[b];
   const size_t off = (size_t)b * c.n;
   const bool dense = use_dense(g);
@@ -114,7 +150,7 @@ __device__ __forceinline__ void walk_stencil_at(const Ctx<F>& c, int b, const F*
       }
       e = lo;
     }
-    if (e > s) vis.cell(m, s, e);
+    if (e > s && (!prune || aabb_overlap(c, b, off, s, qc, qh))) vis.cell(m, s, e);
   }
 }
 
@@ -123,7 +159,7 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
                                              Vis& vis) {
   const Vec4<F> p = c.spos[(size_t)b * c.n + k];
   const F pp[3] = {p.x, p.y, p.z};
-  walk_stencil_at<F>(c, b, pp, cell_size_override, vis);
+  walk_stencil_at<F>(c, b, pp, cell_size_override, vis, p.w);
 }
 
 // ---------------------------------------------------------------------------
@@ -150,7 +186,7 @@ __device__ __forceinline__ bool flat_walk_ok(const GridInfo<I>& g) {
 // the row kernel (k_pair_rows) packs a run start and its length into one word: starts below 2^27
 template <typename F>
 __device__ __forceinline__ bool rows_ok(const Ctx<F>& c, const GridInfo<typename RT<F>::I>& g) {
-  return flat_walk_ok(g) && c.n < (1ll << 27);
+  return flat_walk_ok(g) && c.n < (1ll << 27) && !c.prune;  // MultiCellList: the generic walk prunes per cell
 }
 
 // wrap n into [0, g) for |n| < 2g: identical to n - g*floor(n/g) (cell_list.py:70-72)
@@ -824,7 +860,7 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
 template <typename F, int LAW, int D, bool PERIODIC>
 __device__ __noinline__ void pair_generic(const Ctx<F>& c, int b, int k, int with_torque) {
   const GridInfo<typename RT<F>::I> g = c.gi[b];
-  const bool fast = fast_walk_ok(g), simple = !c.clumps && !g.any_bond;
+  const bool fast = fast_walk_ok(g) && !c.prune, simple = !c.clumps && !g.any_bond;
   if (c.fused) {
     if (simple) pair_force_body<F, LAW, D, PERIODIC, true, 1>(c, b, k, g, fast, with_torque);
     else pair_force_body<F, LAW, D, PERIODIC, false, 1>(c, b, k, g, fast, with_torque);
@@ -977,7 +1013,8 @@ __global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
   const GridInfo<I> g = c.gi[b];
   // FAST = false also serves the systems the flat kernel (below) cannot: stencil range > 1
   // FAST: wider canonical stencils (range != 1; launched instead of the flat kernel when M != 3^D)
-  const bool mine = FAST ? (fast_walk_ok(g) && g.range != 1) : !(flat_walk_ok(g) || (fast_walk_ok(g) && g.range != 1));
+  const bool mine = c.prune ? !FAST
+                            : (FAST ? (fast_walk_ok(g) && g.range != 1) : !(flat_walk_ok(g) || (fast_walk_ok(g) && g.range != 1)));
   // Collider.overflow (cell_list.py:463).  JDB200_GRID_DENSE launches only the FAST kernel: a
   // system it cannot serve (table too small, custom stencil, periodic de-dup) raises the flag.
   if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) {
@@ -990,8 +1027,8 @@ __global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
   // small grid (an idle launch must cost nothing) and strides over the particles
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < c.n;
        k += (long long)gridDim.x * blockDim.x) {
-    if (simple) pair_force_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, FAST, with_torque);
-    else pair_force_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, FAST, with_torque);
+    if (simple) pair_force_body<F, LAW, D, PERIODIC, true, EPI>(c, b, (int)k, g, FAST && !c.prune, with_torque);
+    else pair_force_body<F, LAW, D, PERIODIC, false, EPI>(c, b, (int)k, g, FAST && !c.prune, with_torque);
   }
 }
 
@@ -1056,7 +1093,7 @@ __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
     vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
     vis.interact = c.interact && c.interact[b];
     vis.e = F(0);
-    if (fast_walk_ok(g)) {
+    if (fast_walk_ok(g) && !c.prune) {
       const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
       if (c.dim == 3) {
         if (c.periodic) walk_runs<F, 3, true>(c, b, g, pp, vis);
@@ -1302,6 +1339,45 @@ __global__ void __launch_bounds__(kReduceBlock) k_naive_energy(Ctx<F> c) {
 }
 
 // ---------------------------------------------------------------------------
+// MultiCellList: expandable AABB of every occupied cell (_loose_cell_aabbs, multi_cell_list.py:46-73): segmented
+// min / max of the members' boxes [pos - rad, pos + rad] (with_rad) or of the bare positions (neighbour-list
+// builds, :466-468) over the cell's sorted run; centre and half extent are stored at the run's first slot.
+// ---------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_cell_aabb(Ctx<F> c, int with_rad) {
+  pdl_prologue();
+  using T = RT<F>;
+  using I = typename RT<F>::I;
+  const int b = blockIdx.y;
+  if (c.gate && !c.gate[b]) return;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.n) return;
+  const size_t off = (size_t)b * c.n;
+  const I key = c.skey[off + k];
+  if (k > 0 && c.skey[off + k - 1] == key) return;  // not the first slot of a run
+  F lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (long long j = k; j < c.n && c.skey[off + j] == key; ++j) {
+    const Vec4<F> p = c.spos[off + j];
+    const F r = with_rad ? p.w : F(0);
+    const F x[3] = {p.x, p.y, p.z};
+    for (int d = 0; d < 3; ++d) {
+      const F a = T::sub(x[d], r), z = T::add(x[d], r);
+      lo[d] = j == k ? a : T::fmin(lo[d], a);
+      hi[d] = j == k ? z : T::fmax(hi[d], z);
+    }
+  }
+  c.aabb_c[off + k] = Vec4<F>{T::mul(F(0.5), T::add(lo[0], hi[0])), T::mul(F(0.5), T::add(lo[1], hi[1])),
+                              T::mul(F(0.5), T::add(lo[2], hi[2])), F(0)};
+  c.aabb_h[off + k] = Vec4<F>{T::mul(F(0.5), T::sub(hi[0], lo[0])), T::mul(F(0.5), T::sub(hi[1], lo[1])),
+                              T::mul(F(0.5), T::sub(hi[2], lo[2])), F(0)};
+}
+template <typename F>
+static int cell_aabbs(cudaStream_t s, Ctx<F>& c, int with_rad) {
+  JDB_LAUNCH(k_cell_aabb<F>, dim3(cdiv(c.n, 256), c.batch), 256, s, c, with_rad);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 template <typename F>
@@ -1318,6 +1394,14 @@ template <typename F, int D, int EPI>
 int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
   const dim3 grid(cdiv(c.n, 128), c.batch);
   const int wt = with_torque ? 1 : 0;
+  if (c.prune) {  // MultiCellList: one thread per particle, generic stencil walk with the per-cell AABB test
+    if (c.periodic) {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, false, EPI>), grid, 128, s, c, wt));
+    } else {
+      JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, false, false, EPI>), grid, 128, s, c, wt));
+    }
+    return 0;
+  }
   if (c.max_cells > 0) {  // a dense table exists
     if (c.M == (D == 3 ? 27 : 9)) {  // default stencil: the row kernel owns the systems it can serve
       constexpr int kT = RowsCfg<D>::kThreads;
@@ -1360,6 +1444,7 @@ int celllist_force(cudaStream_t s, Ctx<F>& c, int hash_mode, bool ext, bool with
   if (c.n == 0) return 0;
   int rc = build_partition<F>(s, c, nullptr, hash_mode, ext);
   if (rc) return rc;
+  if (c.prune && (rc = cell_aabbs<F>(s, c, 1))) return rc;
   return c.dim == 3 ? launch_pair_force<F, 3>(s, c, with_torque) : launch_pair_force<F, 2>(s, c, with_torque);
 }
 
@@ -1369,6 +1454,7 @@ int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy, bool reuse) {
   if (c.n == 0) return cudaMemsetAsync(energy, 0, sizeof(F) * c.batch, s) == cudaSuccess ? 0 : JDB200_ECUDA;
   int rc = reuse ? 0 : build_partition<F>(s, c, nullptr, 0, false);
   if (rc) return rc;
+  if (c.prune && !reuse && (rc = cell_aabbs<F>(s, c, 1))) return rc;
   const dim3 grid(c.reduce_blocks, c.batch);
   JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
   JDB_LAUNCH(k_final_sum<F>, dim3(c.batch), kReduceBlock, s, c.partial, c.reduce_blocks, energy);
@@ -1384,6 +1470,10 @@ int celllist_neighbor_list(cudaStream_t s, Ctx<F>& c, const F* cutoff, typename 
   JDB_LAUNCH(k_nl_cell_size<F>, dim3(cdiv(c.batch, 64)), 64, s, c, cutoff, cs_nl);
   int rc = build_partition<F>(s, c, cs_nl, 0, false);
   if (rc) return rc;
+  if (c.prune) {  // multi_cell_list.py:466-481: AABBs of the bare positions, query box = point +- cutoff
+    if ((rc = cell_aabbs<F>(s, c, 0))) return rc;
+    c.prune_cut = cutoff;
+  }
   JDB_LAUNCH(k_neighbor_list<F>, dim3(cdiv(c.n, 128), c.batch), 128, s, c, cs_nl, cutoff, nl);
   JDB_LAUNCH(k_nl_flag<F>, dim3(cdiv(c.batch, 64)), 64, s, c, overflow);
   return 0;
@@ -1400,6 +1490,10 @@ int celllist_cross_neighbor_list(cudaStream_t s, Ctx<F>& c, const F* pos_a, long
   JDB_LAUNCH(k_nl_cell_size<F>, dim3(cdiv(c.batch, 64)), 64, s, c, cutoff, cs_nl);
   int rc = build_partition<F>(s, c, cs_nl, 0, false);
   if (rc) return rc;
+  if (c.prune) {  // multi_cell_list.py:640-643, 676-682
+    if ((rc = cell_aabbs<F>(s, c, 0))) return rc;
+    c.prune_cut = cutoff;
+  }
   JDB_LAUNCH(k_cross_neighbor_list<F>, dim3(cdiv(n_a, 128), c.batch), 128, s, c, pos_a, n_a, cs_nl, cutoff, nl);
   JDB_LAUNCH(k_nl_flag<F>, dim3(cdiv(c.batch, 64)), 64, s, c, overflow);
   return 0;

@@ -84,7 +84,7 @@ def minimize(state, system, max_steps: int = 10000, pe_tol: float = 1e-16, pe_di
     if not isinstance(mz, FireMinimizer):
         raise NotImplementedError("jaxdem_b200.minimize runs the FIRE optimiser (jaxdem_b200.minimizers.fire)")
     kind = getattr(system.collider, "native_kind", "")
-    if kind not in ("celllist", "naive", "neighborlist"):
+    if kind not in ("celllist", "multicelllist", "naive", "neighborlist"):
         raise NotImplementedError(f"minimize needs a native collider, got {type(system.collider).__name__}")
     _call.require_cuda(state)
     fp = _lib.FireParams(dt=mz.dt, alpha_init=mz.alpha_init, f_inc=mz.f_inc, f_dec=mz.f_dec, f_alpha=mz.f_alpha,

@@ -82,6 +82,36 @@ class OCellList:
         self.overflow = False
 
 
+class OMultiCellList(OCellList):
+    """DynamicMultiCellList (multi_cell_list.py:283-328): the cell list's fields; traversal prunes by cell AABB."""
+
+    kind = "multicelllist"
+
+
+def multicelllist_create(state, cell_size=None, search_range=None, box_size=None, max_hashes=None) -> OMultiCellList:
+    """DynamicMultiCellList.Create (multi_cell_list.py:330-392): like the cell list's, with the default cell
+    2 r_max whatever the polydispersity."""
+    if cell_size is None:
+        cell_size = state.fdtype.type(2.0) * np.max(state._rad)
+    base = celllist_create(state, cell_size=cell_size, search_range=search_range, box_size=box_size)
+    return OMultiCellList(base.neighbor_mask, base.cell_size)
+
+
+def loose_cell_aabbs(member_min, member_max, sorted_hash):
+    """_loose_cell_aabbs (multi_cell_list.py:46-73): per-cell union of the member boxes, a segmented min / max over
+    the sorted runs, broadcast back to every member: (centre, half extent) indexed by sorted slot."""
+    n = member_min.shape[0]
+    if n == 0:
+        return member_min, member_min
+    seg_start = np.concatenate([[True], sorted_hash[1:] != sorted_hash[:-1]])
+    seg_id = np.cumsum(seg_start) - 1
+    starts = np.nonzero(seg_start)[0]
+    cmin = np.minimum.reduceat(member_min, starts, axis=0)[seg_id]
+    cmax = np.maximum.reduceat(member_max, starts, axis=0)[seg_id]
+    half = member_min.dtype.type(0.5)
+    return half * (cmin + cmax), half * (cmax - cmin)
+
+
 def float_to_int(x: np.ndarray, idtype) -> np.ndarray:
     """float -> int conversion with the saturating semantics XLA and CUDA share
     (NaN -> 0); numpy's own astype is undefined out of range."""
@@ -203,11 +233,22 @@ def _traverse(state, system, visit):
     pos, perm, sh, nh, ovf = _partition_for(state, system, col.cell_size)
     N = state.N
     iota = np.arange(N)
+    prune = getattr(col, "kind", "") == "multicelllist"
+    if prune:  # multi_cell_list.py:170-180: expandable AABB per loose cell, query box = the particle's own box
+        rad = state._rad[:, None]
+        xmin, xmax = pos - rad, pos + rad
+        cell_center, cell_half = loose_cell_aabbs(xmin[perm], xmax[perm], sh)
+        half = state.fdtype.type(0.5)
+        qc, qh = half * (xmin + xmax), half * (xmax - xmin)
     for m in range(nh.shape[1]):
         target = nh[:, m]
         start = np.searchsorted(sh, target, side="left")
         end = np.searchsorted(sh, target, side="right")
         cnt = end - start
+        if prune:  # :186-204: a cell whose box does not reach the query box is skipped wholesale
+            ss = np.minimum(start, max(N, 1) - 1)
+            dr = system.domain.displacement(qc, cell_center[ss])
+            cnt = np.where(np.all(np.abs(dr) <= qh + cell_half[ss], axis=-1), cnt, 0)
         for t in range(int(cnt.max()) if N else 0):
             sel = np.nonzero(cnt > t)[0]
             kj = start[sel] + t
@@ -280,9 +321,16 @@ def celllist_create_neighbor_list(state, system, cutoff, max_neighbors):
     any_stencil_ovf = False
     total = np.zeros(N, np.int64)
     iota = np.arange(N)
+    prune = getattr(col, "kind", "") == "multicelllist"
+    if prune:  # multi_cell_list.py:466-468: AABBs of the bare positions
+        cell_center, cell_half = loose_cell_aabbs(pos[perm], pos[perm], sh)
     for m in range(M):
         target = nh[:, m]
         k = np.searchsorted(sh, target, side="left").astype(np.int64)
+        if prune:  # :475-481: non-overlapping cells are looked up as hash -1, which no particle carries
+            ss = np.minimum(k, max(1, N) - 1)
+            dr = dom.displacement(pos, cell_center[ss])
+            target = np.where(np.all(np.abs(dr) <= cutoff + cell_half[ss], axis=-1), target, I.type(-1))
         c = np.zeros(N, np.int64)
         while True:
             safe_k = np.minimum(k, max(1, N) - 1)
@@ -501,8 +549,8 @@ def neighborlist_compute_potential_energy(state, system):
 def compute_force(state, system):
     if system.collider_type == "naive":
         naive_compute_force(state, system)
-    elif system.collider_type == "celllist":
-        celllist_compute_force(state, system)
+    elif system.collider_type in ("celllist", "multicelllist"):
+        celllist_compute_force(state, system)  # _traverse prunes when the collider is the loose grid
     elif system.collider_type == "neighborlist":
         neighborlist_compute_force(state, system)
     else:  # "" no-op collider (colliders/__init__.py:56-88)
@@ -513,7 +561,7 @@ def compute_force(state, system):
 def compute_potential_energy(state, system):
     if system.collider_type == "naive":
         return naive_compute_potential_energy(state, system)
-    if system.collider_type == "celllist":
+    if system.collider_type in ("celllist", "multicelllist"):
         return celllist_compute_potential_energy(state, system)
     if system.collider_type == "neighborlist":
         return neighborlist_compute_potential_energy(state, system)

@@ -39,6 +39,10 @@ def create_system(state, *, dt=0.005, linear_integrator_type="verlet",
         kw = dict(collider_kw or {})
         kw.pop("state", None)
         s.collider = colliders.celllist_create(state, **kw)
+    elif s.collider_type == "multicelllist":
+        kw = dict(collider_kw or {})
+        kw.pop("state", None)
+        s.collider = colliders.multicelllist_create(state, **kw)
     elif s.collider_type == "neighborlist":
         kw = dict(collider_kw or {})
         kw.pop("state", None)

@@ -98,7 +98,7 @@ def build_gpu(inp, *, dtype, domain="periodic", law="spring", collider="CellList
     if domain == "reflect":
         dkw["restitution_coefficient"] = restitution
     ckw = dict(collider_kw or {})
-    if collider.lower() == "celllist":
+    if collider.lower() in ("celllist", "multicelllist"):
         ckw.update(state=st, grid_mode=grid_mode)
         if max_cells is not None:
             ckw["max_cells"] = max_cells

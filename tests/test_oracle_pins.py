@@ -270,3 +270,33 @@ def test_neighborlist_oracle_pins():
         np.testing.assert_allclose(a.force, b.force, atol=1e-9 * np.abs(b.force).max())
         np.testing.assert_allclose(colliders.compute_potential_energy(a, sa),
                                    colliders.compute_potential_energy(b, sb), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dim,domain", [(2, "periodic"), (3, "periodic"), (3, "reflect")])
+def test_multicelllist_oracle_equals_celllist(dim, domain):
+    # reference multi_cell_list.py:283-289: "forces are bit-identical to DynamicCellList" (the prune only skips
+    # contact-free cells); neighbour lists likewise.  Polydisperse clumps, cells of 2 r_max.
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_oracle, make_inputs
+    inp = make_inputs(900, dim, seed=31, dtype=np.float64, phi=0.5, poly=3.0, clumps=True)
+    a, sa = build_oracle(inp, dtype=np.float64, collider="multicelllist", law="hertz", domain=domain)
+    b, sb = build_oracle(inp, dtype=np.float64, collider="celllist", law="hertz", domain=domain)
+    assert float(sa.collider.cell_size) != float(sb.collider.cell_size)  # the defaults differ (alpha = 3 > 2.5)
+    sb.collider.cell_size, sb.collider.neighbor_mask = sa.collider.cell_size, sa.collider.neighbor_mask
+    colliders.compute_force(a, sa)
+    colliders.compute_force(b, sb)
+    assert np.array_equal(a.force, b.force) and np.array_equal(a.torque, b.torque)
+    assert colliders.compute_potential_energy(a, sa) == colliders.compute_potential_energy(b, sb)
+    na, oa = colliders.celllist_create_neighbor_list(a, sa, 0.8, 30)
+    nb, ob = colliders.celllist_create_neighbor_list(b, sb, 0.8, 30)
+    assert np.array_equal(na, nb) and oa == ob
+    # and the prune really skips cells: some stencil cells of some particles hold members out of reach
+    pos, perm, sh, nh, _ = colliders._partition_for(a, sa, sa.collider.cell_size)
+    rad = a._rad[:, None]
+    cc, ch = colliders.loose_cell_aabbs((pos - rad)[perm], (pos + rad)[perm], sh)
+    start = np.minimum(np.searchsorted(sh, nh[:, 0], side="left"), a.N - 1)
+    hit = sh[start] == nh[:, 0]
+    dr = sa.domain.displacement(pos, cc[start])
+    skipped = hit & ~np.all(np.abs(dr) <= rad + ch[start], axis=-1)
+    assert skipped.any()
