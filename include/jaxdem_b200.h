@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define JDB200_ABI_VERSION 3
+#define JDB200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define JDB200_API __attribute__((visibility("default")))
@@ -133,6 +133,10 @@ typedef struct jdb200_state {
   void* bond_id;   /* (B,N,W) I, -1 padded */
   void* fixed;     /* (B,N) uint8 */
   void* pos_p_rot; /* (B,N,D) F  cache R(q)·pos_p (State._pos_p_rot) */
+  const void* n_rows; /* optional () int64 ON THE DEVICE, or NULL: the number of LIVE rows, <= params.n.  Non-NULL
+                         (batch == 1, dense cell table): params.n is only the launch bound; every kernel reads the
+                         live count itself and leaves rows [n_rows, n) alone.  Used by the slab decomposition, whose
+                         owned + ghost row count changes every step and is known on the device only. */
 } jdb200_state;
 
 /* System leaves (jaxdem/system.py:123-228 and the components it holds). */
@@ -349,7 +353,9 @@ JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_param
  * colliders/cell_list.py:55-60, on the device copies of anchor / box_size / cell_size —
  * and writes the rows that left as full records into the message of their direction (and as
  * ghost records into `kept`: they stay behind as ghosts; their row indices go to `holes`) and
- * the rows within `search_range` layers of a face as ghost records.  The caller exchanges the
+ * the rows within `search_range` layers of a face as ghost records.  Inside a message section the
+ * records are FIELD-MAJOR (word c of record r at base[c * capacity + r]): a warp's stores are
+ * contiguous, which is what peer-memory stores over NVLink need.  The caller exchanges the
  * two messages with its neighbours (NCCL), reads the counts from the 64-byte headers (int64:
  * [0] full records, [1] ghost records, [2] rows that moved further than the halo;
  * `header_local`: [0] rows that stay, [1] left downwards, [2] left upwards, [3] strays) and
@@ -395,6 +401,36 @@ JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const j
 JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
                                   const int64_t* counts, const void* from_lo, const void* from_up, const void* kept,
                                   void* holes);
+
+/* The same exchange WITHOUT the host (device protocol; peer-memory transport only).  The row
+ * counts live in `dev_state` (16 int64 words on the device: [0] owned rows, [1] owned + ghost rows —
+ * point jdb200_state.n_rows of the hooks at these words —, [2] exchanges completed, [3] sticky
+ * JDB200_SLAB_* status bits, [4..10] the counts of the last exchange as in jdb200_slab_unpack,
+ * [11] / [12] largest migrant / ghost counts seen, [13] internal ticket); desc.n is only the launch
+ * BOUND (rows the kernels may touch, <= the row capacity).  msg_lo / msg_up and from_lo / from_up
+ * hold one pointer per PARITY (exchange number & 1): the messages this rank writes — normally
+ * straight into the neighbours' receive buffers over NVLink — and the buffers the neighbours
+ * write into.  jdb200_slab_pack_dev stores the records, then the counts, then — from the block
+ * that finishes last, after a system-scope fence — header word 7 = exchange number + 1 with
+ * release semantics.  jdb200_slab_unpack_dev starts with one block that spins (acquire loads, at
+ * most timeout_ns nanoseconds) on word 7 of both of its receive buffers, derives the counts, checks
+ * them against the capacities and the bound, publishes the new row counts and repairs the rows as
+ * jdb200_slab_unpack does.  Two parities are enough: a neighbour can only write the message of
+ * exchange s + 2 after it has seen this rank's flag of exchange s + 1, which this rank stores after
+ * it has unpacked exchange s.  Errors never stop the stream: they set status bits (the rows are then
+ * left untouched) which the caller reads whenever it likes.  Capturable in a CUDA graph: no
+ * argument changes from step to step. */
+#define JDB200_SLAB_STRAY 1        /* a particle moved further than the halo in one step / the box changed */
+#define JDB200_SLAB_MESSAGE_FULL 2 /* more migrants / ghosts than the message capacities */
+#define JDB200_SLAB_ROWS_FULL 4    /* owned + ghost rows exceed the bound */
+#define JDB200_SLAB_TIMEOUT 8      /* a neighbour's message did not arrive in time */
+#define JDB200_SLAB_DEV_WORDS 16
+JDB200_API int jdb200_slab_pack_dev(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                    void* dev_state, void* const msg_lo[2], void* const msg_up[2], void* kept,
+                                    void* holes, void* header_local, void* scratch, size_t scratch_bytes);
+JDB200_API int jdb200_slab_unpack_dev(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                      void* dev_state, const void* const from_lo[2], const void* const from_up[2],
+                                      const void* header_local, const void* kept, void* holes, int64_t timeout_ns);
 
 /* Number of kernels the library has launched since load (diagnostic counter for
  * bench.py's `gpu_launches`; relaxed atomic, not part of the data path). */

@@ -22,7 +22,7 @@ COLLIDER = {"": 0, "celllist": 1, "naive": 2, "neighborlist": 3, "multicelllist"
 GRID = {"auto": 0, "dense": 1, "sorted": 2}
 # jdb200_params.promises (include/jaxdem_b200.h)
 PROMISE_NO_EXT, PROMISE_NO_BONDS, PROMISE_NO_FIXED, PROMISE_NO_POS_P = 1, 2, 4, 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 FRAME_FIELDS = ("pos_c", "vel", "force", "ang_vel", "torque", "q_w", "q_xyz", "pos")  # bit f of jdb200_frame_pack's `fields`
 ERRORS = {-1: "JDB200_EINVAL (bad params)", -2: "JDB200_ENULL (NULL pointer)",
           -3: "JDB200_EWORKSPACE (workspace too small)", -4: "JDB200_ECUDA (kernel launch failed)"}
@@ -41,7 +41,7 @@ class Params(C.Structure):
 
 
 STATE_FIELDS = ("pos_c", "pos_p", "vel", "force", "q_w", "q_xyz", "ang_vel", "torque", "inertia",
-                "rad", "mass", "clump_id", "mat_id", "bond_id", "fixed", "pos_p_rot")
+                "rad", "mass", "clump_id", "mat_id", "bond_id", "fixed", "pos_p_rot", "n_rows")
 SYSTEM_FIELDS = ("dt", "box_size", "inv_box_size", "anchor", "restitution", "cell_size",
                  "neighbor_mask", "collider_overflow", "interact_same_bond_id", "gravity",
                  "external_force", "external_force_com", "external_torque", "mat_young",
@@ -126,6 +126,8 @@ SYMBOLS = {
     "jdb200_slab_holes_bytes": (_SZ, [_PD]),
     "jdb200_slab_pack": (C.c_int, [_V, _PD, _PR, _V, _V, _V, _V, _V, _V, _SZ]),
     "jdb200_slab_unpack": (C.c_int, [_V, _PD, _PR, C.POINTER(C.c_int64), _V, _V, _V, _V]),
+    "jdb200_slab_pack_dev": (C.c_int, [_V, _PD, _PR, _V, C.POINTER(_V), C.POINTER(_V), _V, _V, _V, _V, _SZ]),
+    "jdb200_slab_unpack_dev": (C.c_int, [_V, _PD, _PR, _V, C.POINTER(_V), C.POINTER(_V), _V, _V, _V, C.c_int64]),
     "jdb200_timing_enable": (C.c_int, [C.c_int]),
     "jdb200_timing_collect": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

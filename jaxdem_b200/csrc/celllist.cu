@@ -19,6 +19,7 @@ namespace jdb {
 template <typename F>
 __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ cell_size_override) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   if (c.gate && !c.gate[b]) {  // NeighborList: no rebuild for this system in this call
@@ -165,6 +166,7 @@ __device__ __forceinline__ bool use_dense(const GridInfo<I>& g) {
 template <typename F, int D, int MODE>
 __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ cell_size_override) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using T = RT<F>;
   using I = typename RT<F>::I;
   using U = typename RT<F>::U;
@@ -283,6 +285,7 @@ __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterp
 template <int D, int MODE>
 __global__ void __launch_bounds__(128) k_hash4(Ctx<float> c, const float* __restrict__ cell_size_override) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using F = float;
   using T = RT<F>;
   using I = int32_t;
@@ -432,6 +435,7 @@ __global__ void __launch_bounds__(128) k_hash4(Ctx<float> c, const float* __rest
 template <typename F>
 __global__ void __launch_bounds__(512) k_scan(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
@@ -480,6 +484,7 @@ __device__ __forceinline__ void ld256(const void* p, double* a) {
 template <typename F>
 __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
@@ -653,6 +658,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& phase)
 template <typename F>
 __global__ void __launch_bounds__(256) k_radix_sort(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   __shared__ int whist[8][256];
   __shared__ int s_warp[8];
@@ -700,6 +706,7 @@ inline const int* sorted_perm_buffer(const Ctx<F>& c) {
 template <typename F>
 __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restrict__ sorted_perm) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   if (c.gate && !c.gate[b]) return;  // NeighborList: this system keeps its list in this call
@@ -790,7 +797,7 @@ template <int D>
 static bool launch_hash4(cudaStream_t s, Ctx<double>&, const double*, int) { return false; }
 template <int D>
 static bool launch_hash4(cudaStream_t s, Ctx<float>& c, const float* cso, int mode) {
-  if (c.n % 4 != 0) return false;
+  if (c.n % 4 != 0 || c.n_dev) return false;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!(al(c.pos_c) && al(c.pos_p_rot) && al(c.force) && al(c.vel) && al(c.rad) && al(c.mass) && al(c.ext_force) &&
         al(c.ext_force_com) && al(c.ext_torque) && (reinterpret_cast<uintptr_t>(c.fixed) & 3) == 0))

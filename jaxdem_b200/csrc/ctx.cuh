@@ -76,6 +76,9 @@ struct Ctx {
   F* nl_old_pos;               // (B,N,D) NeighborList.old_pos
   I* nl_builds;                // (B,)    NeighborList.n_build_times
   const F *nl_cutoff, *nl_skin;  // (B,)
+  // ---- ragged rows (slab decomposition without host synchronisation) ----
+  const long long* n_dev;      // jdb200_state.n_rows or NULL: the LIVE row count, read on the device by every kernel
+                               // (n above is then the launch bound: grids cover it, rows >= *n_dev are not touched)
   // ---- MultiCellList (loose-grid AABB pruning, pair.cu) ----
   int prune;                   // 1: every stencil cell is tested against its expandable AABB before its run is walked
   const F* prune_cut;          // [B] or NULL: neighbour-list builds prune with a query box of +-cutoff around the point
@@ -182,6 +185,7 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
     c.mass = (F*)st->mass; c.pos_p_rot = (F*)st->pos_p_rot;
     c.clump_id = (I*)st->clump_id; c.mat_id = (I*)st->mat_id; c.bond_id = (I*)st->bond_id;
     c.fixed = (uint8_t*)st->fixed;
+    c.n_dev = (const long long*)st->n_rows;
   }
   if (sys) {
     c.dt = (F*)sys->dt; c.box = (F*)sys->box_size; c.inv_box = (F*)sys->inv_box_size;

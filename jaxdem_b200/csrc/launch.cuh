@@ -45,6 +45,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 }
 }  // namespace jdb
 
+// ragged rows (Ctx.n_dev): a kernel that takes Ctx by value replaces its launch bound n by the live row count
+#define JDB_LIVE_ROWS(c)                    \
+  do {                                      \
+    if ((c).n_dev) (c).n = *(c).n_dev;      \
+  } while (0)
+
 #define JDB_LAUNCH(kernel, grid, block, stream, ...)                       \
   do {                                                                     \
     const bool jdb_t_ = jdb::g_timing.load(std::memory_order_relaxed) != 0; \

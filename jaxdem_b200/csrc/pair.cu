@@ -122,7 +122,7 @@ __device__ __forceinline__ void walk_stencil_at(const Ctx<F>& c, int b, const F*
   const I* mask = c.mask + (size_t)b * c.M * c.dim;
   const I* skey = c.skey + off;
   const int* cstart = c.cell_start + (size_t)b * c.cell_stride;
-  const int n = (int)c.n;
+  const int n = (int)(c.n_dev ? *c.n_dev : c.n);
   for (int m = 0; m < c.M; ++m) {
     const I h = neighbor_hash<F, I>(cc, mask + m * c.dim, g.gd, g.stride, c.dim, c.periodic);
     if (c.periodic && g.need_dedup) {
@@ -883,14 +883,15 @@ __global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW ==
     if (mine || c.grid_mode != JDB200_GRID_DENSE) c.overflow[b] = (uint8_t)g.hash_overflow;
     else c.overflow[b] = 1;  // JDB200_GRID_DENSE and the dense table cannot hold this system
   }
+  const long long n_live = c.n_dev ? *c.n_dev : c.n;  // ragged rows (batch == 1: offsets do not depend on n)
   const long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = k0 < c.n;
+  const bool live = k0 < n_live;
   if (!mine) {
     if (live && c.grid_mode != JDB200_GRID_DENSE) pair_generic<F, LAW, D, PERIODIC>(c, b, (int)k0, with_torque);
     return;
   }
   // the body uses warp-wide votes: lanes past the end of the array redo the last particle and store nothing
-  const long long k = live ? k0 : c.n - 1;
+  const long long k = live ? k0 : n_live - 1;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   F f[3], t[3];
   if (!c.clumps && !g.any_bond) pair_rows_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, sbase, f, t);
@@ -907,6 +908,7 @@ __global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW ==
 template <typename F, int D, int EPI>
 __global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];
@@ -994,7 +996,7 @@ static bool launch_after4(cudaStream_t, Ctx<double>&, int) { return false; }
 template <int D, int EPI>
 static bool launch_after4(cudaStream_t s, Ctx<float>& c, int wt) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (c.n % 4 != 0 || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
+  if (c.n % 4 != 0 || c.n_dev || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
   auto go = [&]() -> int {
     JDB_LAUNCH((k_after4<D, EPI>), dim3(cdiv(c.n, 4 * 128), c.batch), 128, s, c, wt);
     return 0;
@@ -1008,6 +1010,7 @@ static bool launch_after4(cudaStream_t s, Ctx<float>& c, int wt) {
 template <typename F, int LAW, int D, bool PERIODIC, bool FAST, int EPI>
 __global__ void __launch_bounds__(128) k_pair_force(Ctx<F> c, int with_torque) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   const GridInfo<I> g = c.gi[b];

@@ -74,86 +74,99 @@ struct SlabMsg {
   }
 };
 
+// records are FIELD-MAJOR inside a section: word c of record r lives at base[c * cap + r], so the
+// lanes of a warp (consecutive ranks r) store consecutive addresses — over NVLink that is one
+// 128-byte packet per warp store instead of 32 packets of 4 bytes
 template <typename F, int D>
-__device__ __forceinline__ void write_full(const SlabRows<F>& s, long long i, F* f, long long* iv) {
+__device__ __forceinline__ void write_full(const SlabRows<F>& s, long long i, F* f, long long* iv, size_t cap, size_t r) {
   constexpr int A = D == 3 ? 3 : 1;
   int c = 0;
+  f += r;
+  iv += r;
 #pragma unroll
-  for (int d = 0; d < D; ++d) f[c++] = s.pos_c[i * D + d];
+  for (int d = 0; d < D; ++d) f[cap * c++] = s.pos_c[i * D + d];
 #pragma unroll
-  for (int d = 0; d < D; ++d) f[c++] = s.vel[i * D + d];
+  for (int d = 0; d < D; ++d) f[cap * c++] = s.vel[i * D + d];
 #pragma unroll
-  for (int d = 0; d < D; ++d) f[c++] = s.force[i * D + d];
+  for (int d = 0; d < D; ++d) f[cap * c++] = s.force[i * D + d];
 #pragma unroll
-  for (int a = 0; a < A; ++a) f[c++] = s.ang_vel[i * A + a];
+  for (int a = 0; a < A; ++a) f[cap * c++] = s.ang_vel[i * A + a];
 #pragma unroll
-  for (int a = 0; a < A; ++a) f[c++] = s.torque[i * A + a];
+  for (int a = 0; a < A; ++a) f[cap * c++] = s.torque[i * A + a];
 #pragma unroll
-  for (int a = 0; a < A; ++a) f[c++] = s.inertia[i * A + a];
-  f[c++] = s.q_w[i];
+  for (int a = 0; a < A; ++a) f[cap * c++] = s.inertia[i * A + a];
+  f[cap * c++] = s.q_w[i];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) f[c++] = s.q_xyz[i * 3 + a];
-  f[c++] = s.rad[i];
-  f[c++] = s.mass[i];
+  for (int a = 0; a < 3; ++a) f[cap * c++] = s.q_xyz[i * 3 + a];
+  f[cap * c++] = s.rad[i];
+  f[cap * c++] = s.mass[i];
   iv[0] = s.gid[i];
-  iv[1] = (long long)s.mat_id[i];
-  iv[2] = (long long)s.fixed[i];
+  iv[cap] = (long long)s.mat_id[i];
+  iv[2 * cap] = (long long)s.fixed[i];
 }
 template <typename F, int D>
-__device__ __forceinline__ void read_full(const SlabRows<F>& s, long long i, const F* f, const long long* iv) {
+__device__ __forceinline__ void read_full(const SlabRows<F>& s, long long i, const F* f, const long long* iv, size_t cap,
+                                          size_t r) {
   constexpr int A = D == 3 ? 3 : 1;
   int c = 0;
+  f += r;
+  iv += r;
 #pragma unroll
-  for (int d = 0; d < D; ++d) s.pos_c[i * D + d] = f[c++];
+  for (int d = 0; d < D; ++d) s.pos_c[i * D + d] = f[cap * c++];
 #pragma unroll
-  for (int d = 0; d < D; ++d) s.vel[i * D + d] = f[c++];
+  for (int d = 0; d < D; ++d) s.vel[i * D + d] = f[cap * c++];
 #pragma unroll
-  for (int d = 0; d < D; ++d) s.force[i * D + d] = f[c++];
+  for (int d = 0; d < D; ++d) s.force[i * D + d] = f[cap * c++];
 #pragma unroll
-  for (int a = 0; a < A; ++a) s.ang_vel[i * A + a] = f[c++];
+  for (int a = 0; a < A; ++a) s.ang_vel[i * A + a] = f[cap * c++];
 #pragma unroll
-  for (int a = 0; a < A; ++a) s.torque[i * A + a] = f[c++];
+  for (int a = 0; a < A; ++a) s.torque[i * A + a] = f[cap * c++];
 #pragma unroll
-  for (int a = 0; a < A; ++a) s.inertia[i * A + a] = f[c++];
-  s.q_w[i] = f[c++];
+  for (int a = 0; a < A; ++a) s.inertia[i * A + a] = f[cap * c++];
+  s.q_w[i] = f[cap * c++];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) s.q_xyz[i * 3 + a] = f[c++];
-  s.rad[i] = f[c++];
-  s.mass[i] = f[c++];
+  for (int a = 0; a < 3; ++a) s.q_xyz[i * 3 + a] = f[cap * c++];
+  s.rad[i] = f[cap * c++];
+  s.mass[i] = f[cap * c++];
   s.gid[i] = iv[0];
-  s.mat_id[i] = (typename RT<F>::I)iv[1];
-  s.fixed[i] = (uint8_t)iv[2];
+  s.mat_id[i] = (typename RT<F>::I)iv[cap];
+  s.fixed[i] = (uint8_t)iv[2 * cap];
 }
 template <typename F, int D>
-__device__ __forceinline__ void write_ghost(const SlabRows<F>& s, long long i, F* f, long long* iv) {
+__device__ __forceinline__ void write_ghost(const SlabRows<F>& s, long long i, F* f, long long* iv, size_t cap, size_t r) {
   constexpr int A = D == 3 ? 3 : 1;
   int c = 0;
+  f += r;
+  iv += r;
 #pragma unroll
-  for (int d = 0; d < D; ++d) f[c++] = s.pos_c[i * D + d];
+  for (int d = 0; d < D; ++d) f[cap * c++] = s.pos_c[i * D + d];
 #pragma unroll
-  for (int d = 0; d < D; ++d) f[c++] = s.vel[i * D + d];
+  for (int d = 0; d < D; ++d) f[cap * c++] = s.vel[i * D + d];
 #pragma unroll
-  for (int a = 0; a < A; ++a) f[c++] = s.ang_vel[i * A + a];
-  f[c++] = s.rad[i];
-  f[c++] = s.mass[i];
+  for (int a = 0; a < A; ++a) f[cap * c++] = s.ang_vel[i * A + a];
+  f[cap * c++] = s.rad[i];
+  f[cap * c++] = s.mass[i];
   iv[0] = s.gid[i];
-  iv[1] = (long long)s.mat_id[i];
+  iv[cap] = (long long)s.mat_id[i];
 }
 // a ghost row: what the force laws read; the rest of the row is set to inert values
 template <typename F, int D>
-__device__ __forceinline__ void read_ghost(const SlabRows<F>& s, long long i, const F* f, const long long* iv) {
+__device__ __forceinline__ void read_ghost(const SlabRows<F>& s, long long i, const F* f, const long long* iv, size_t cap,
+                                           size_t r) {
   constexpr int A = D == 3 ? 3 : 1;
   int c = 0;
+  f += r;
+  iv += r;
 #pragma unroll
-  for (int d = 0; d < D; ++d) s.pos_c[i * D + d] = f[c++];
+  for (int d = 0; d < D; ++d) s.pos_c[i * D + d] = f[cap * c++];
 #pragma unroll
-  for (int d = 0; d < D; ++d) s.vel[i * D + d] = f[c++];
+  for (int d = 0; d < D; ++d) s.vel[i * D + d] = f[cap * c++];
 #pragma unroll
-  for (int a = 0; a < A; ++a) s.ang_vel[i * A + a] = f[c++];
-  s.rad[i] = f[c++];
-  s.mass[i] = f[c++];
+  for (int a = 0; a < A; ++a) s.ang_vel[i * A + a] = f[cap * c++];
+  s.rad[i] = f[cap * c++];
+  s.mass[i] = f[cap * c++];
   s.gid[i] = iv[0];
-  s.mat_id[i] = (typename RT<F>::I)iv[1];
+  s.mat_id[i] = (typename RT<F>::I)iv[cap];
   s.fixed[i] = 0;
 #pragma unroll
   for (int d = 0; d < D; ++d) s.force[i * D + d] = F(0);
@@ -167,11 +180,35 @@ __device__ __forceinline__ void read_ghost(const SlabRows<F>& s, long long i, co
   for (int a = 0; a < 3; ++a) s.q_xyz[i * 3 + a] = F(0);
 }
 
+// ---- device-side exchange state (jdb200_slab_pack_dev / _unpack_dev): int64 words -------------
+// The row counts of a slab change every step and are known on the device only.  With this block
+// the whole exchange runs without the host: kernels are launched over a BOUND (desc.n) and read the
+// live counts here; the two neighbours signal "message complete" through a flag word in the
+// message header (peer-memory store with release semantics), not through a host-visible barrier.
+enum : int {
+  kDevOwn = 0,     // owned rows
+  kDevLocal = 1,   // owned + ghost rows (jdb200_state.n_rows of the force evaluation points here)
+  kDevSeq = 2,     // exchanges completed; parity of the message buffers = seq & 1
+  kDevStatus = 3,  // sticky bits, JDB200_SLAB_* (include/jaxdem_b200.h)
+  kDevCounts = 4,  // SlabCounts of the current exchange (7 words)
+  kDevMaxMig = 11, // largest migrant / ghost counts seen (capacity tuning)
+  kDevMaxGhost = 12,
+  kDevTicket = 13, // block ticket of the pack kernel
+  kDevWords = 16
+};
+constexpr int kHdrFlag = 7;  // header word 7: seq + 1 of the exchange whose message is complete
+
 struct SlabGeom {
-  long long n;
+  long long n;  // owned rows — or, with n_dev, the launch bound
   int n_layers, lo, up, R;
   long long cap_m, cap_g;
+  long long* dev;  // device-side exchange state or NULL (counts come from the host)
 };
+__device__ __forceinline__ long long slab_rows_live(const SlabGeom& gm) {
+  if (!gm.dev) return gm.n;
+  const long long n = gm.dev[kDevOwn];
+  return n < gm.n ? n : gm.n;
+}
 
 // category bits: 1 halo-lo, 2 halo-up, 4 leave-lo, 8 leave-up, 16 stray
 // INTEGRATE: VelocityVerlet.step_before_force (velocity_verlet.py:57-61; the arithmetic of
@@ -184,9 +221,11 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, SlabR
   pdl_prologue();
   using I = typename RT<F>::I;
   using T = RT<F>;
+  const long long n = slab_rows_live(gm);
+  if ((long long)blockIdx.x * blockDim.x >= n && blockIdx.x > 0) return;  // past the live rows (block 0 always counts)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int c8 = 0;
-  bool live = i < gm.n;
+  bool live = i < n;
   if (live) {
     F* pos_c = rows.pos_c;
     if (INTEGRATE) {
@@ -240,20 +279,22 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, SlabR
 }
 
 // exclusive scan of the block counts (one block: thread t owns a contiguous chunk of blocks,
-// the 1024 chunk sums are scanned with shuffles), totals into the message headers and the
-// local header
-__global__ void __launch_bounds__(1024) k_slab_scan(int nblocks, int* __restrict__ bc, long long* __restrict__ hdr_lo,
-                                                    long long* __restrict__ hdr_up, long long* __restrict__ hdr_local) {
+// the 1024 chunk sums are scanned with shuffles); totals -> tot[6] (stay, leave-lo, leave-up,
+// halo-lo, halo-up, stray)
+__global__ void __launch_bounds__(1024) k_slab_scan(SlabGeom gm, int* __restrict__ bc, long long* __restrict__ tot) {
   pdl_prologue();
   __shared__ int s_warp[32][6];
   __shared__ int s_tot[6];
+  const long long n = slab_rows_live(gm);
+  const int nblocks = (int)max((n + kSlabBlock - 1) / kSlabBlock, 1LL);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = (nblocks + 1023) / 1024;
   const int b0 = min((int)threadIdx.x * per, nblocks), b1 = min(b0 + per, nblocks);
   int sum[6] = {0, 0, 0, 0, 0, 0};
   for (int b = b0; b < b1; ++b) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) sum[j] += bc[(size_t)b * 8 + j];
+    const int4 lo4 = *reinterpret_cast<const int4*>(bc + (size_t)b * 8);
+    const int2 hi2 = *reinterpret_cast<const int2*>(bc + (size_t)b * 8 + 4);
+    sum[0] += lo4.x; sum[1] += lo4.y; sum[2] += lo4.z; sum[3] += lo4.w; sum[4] += hi2.x; sum[5] += hi2.y;
   }
   int excl[6];
 #pragma unroll
@@ -287,121 +328,226 @@ __global__ void __launch_bounds__(1024) k_slab_scan(int nblocks, int* __restrict
 #pragma unroll
   for (int j = 0; j < 6; ++j) run[j] = excl[j] + s_warp[warp][j];
   for (int b = b0; b < b1; ++b) {
+    int4 lo4 = *reinterpret_cast<const int4*>(bc + (size_t)b * 8);
+    int2 hi2 = *reinterpret_cast<const int2*>(bc + (size_t)b * 8 + 4);
+    const int v[6] = {lo4.x, lo4.y, lo4.z, lo4.w, hi2.x, hi2.y};
+    lo4 = make_int4(run[0], run[1], run[2], run[3]);
+    hi2 = make_int2(run[4], run[5]);
+    *reinterpret_cast<int4*>(bc + (size_t)b * 8) = lo4;
+    *reinterpret_cast<int2*>(bc + (size_t)b * 8 + 4) = hi2;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int v = bc[(size_t)b * 8 + j];
-      bc[(size_t)b * 8 + j] = run[j];
-      run[j] += v;
-    }
+    for (int j = 0; j < 6; ++j) run[j] += v[j];
   }
-  if (threadIdx.x == 0) {
-    // header: [0] full records, [1] ghost records, [2] strays seen by the sender
-    hdr_lo[0] = s_tot[1]; hdr_lo[1] = s_tot[3]; hdr_lo[2] = s_tot[5];
-    hdr_up[0] = s_tot[2]; hdr_up[1] = s_tot[4]; hdr_up[2] = s_tot[5];
-    hdr_local[0] = s_tot[0]; hdr_local[1] = s_tot[1]; hdr_local[2] = s_tot[2]; hdr_local[3] = s_tot[5];
-  }
+  if (threadIdx.x < 6) tot[threadIdx.x] = s_tot[threadIdx.x];
+}
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 constexpr int kPackLists = 4;  // leave-lo, leave-up, halo-lo, halo-up (block-count columns 1..4)
 
+// the two messages of one exchange: [parity] — the host protocol passes the same pointer twice
+struct SlabPorts {
+  void* lo[2];
+  void* up[2];
+};
+
 template <typename F, int D>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, const uint8_t* __restrict__ cat,
-                                                           const int* __restrict__ bc, void* msg_lo, void* msg_up,
-                                                           void* kept, int* __restrict__ holes) {
+                                                           const int* __restrict__ bc, const long long* __restrict__ tot,
+                                                           SlabPorts out, void* kept, int* __restrict__ holes,
+                                                           long long* __restrict__ hdr_local) {
   pdl_prologue();
   using M = SlabMsg<F, D>;
   __shared__ int s_w[kSlabBlock / 32][kPackLists];
+  const long long n = slab_rows_live(gm);
+  const long long seq = gm.dev ? gm.dev[kDevSeq] : 0;
+  const int par = (int)(seq & 1);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < gm.n;
+  const bool live = i < n;
   const int c8 = live ? cat[i] : 0;
   const bool stay = live && !(c8 & 12);
   const bool fl[kPackLists] = {live && (c8 & 4) != 0, live && (c8 & 8) != 0, stay && (c8 & 1) != 0,
                                stay && (c8 & 2) != 0};
-  if (!__syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3])) return;  // interior block: nothing to pack
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int rank[kPackLists];
+  const M lo(out.lo[par], gm.cap_m, gm.cap_g), up(out.up[par], gm.cap_m, gm.cap_g);
+  if (__syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3])) {  // interior blocks have nothing to pack
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int rank[kPackLists];
 #pragma unroll
-  for (int j = 0; j < kPackLists; ++j) {
-    const unsigned m = __ballot_sync(0xffffffffu, fl[j]);
-    rank[j] = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) s_w[warp][j] = __popc(m);
-  }
-  __syncthreads();
-  const int* base = bc + (size_t)blockIdx.x * 8 + 1;
+    for (int j = 0; j < kPackLists; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, fl[j]);
+      rank[j] = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_w[warp][j] = __popc(m);
+    }
+    __syncthreads();
+    const int* base = bc + (size_t)blockIdx.x * 8 + 1;
 #pragma unroll
-  for (int j = 0; j < kPackLists; ++j) {
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += s_w[w][j];
-    rank[j] += woff + base[j];
+    for (int j = 0; j < kPackLists; ++j) {
+      int woff = 0;
+      for (int w = 0; w < warp; ++w) woff += s_w[w][j];
+      rank[j] += woff + base[j];
+    }
+    // kept: ghost records of the leavers, lower direction in records [0, cap_m), upper in [cap_m, 2 cap_m);
+    // holes: their row indices, same split
+    const M kp(kept, 0, 2 * gm.cap_m);
+    const size_t cm = (size_t)gm.cap_m, cg = (size_t)gm.cap_g;
+    if (fl[0] && rank[0] < gm.cap_m) {
+      write_full<F, D>(src, i, lo.mig_f, lo.mig_i, cm, rank[0]);
+      write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, rank[0]);
+      holes[rank[0]] = (int)i;
+    }
+    if (fl[1] && rank[1] < gm.cap_m) {
+      write_full<F, D>(src, i, up.mig_f, up.mig_i, cm, rank[1]);
+      write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, cm + rank[1]);
+      holes[gm.cap_m + rank[1]] = (int)i;
+    }
+    if (fl[2] && rank[2] < gm.cap_g) write_ghost<F, D>(src, i, lo.gh_f, lo.gh_i, cg, rank[2]);
+    if (fl[3] && rank[3] < gm.cap_g) write_ghost<F, D>(src, i, up.gh_f, up.gh_i, cg, rank[3]);
   }
-  if (!live) return;
-  const M lo(msg_lo, gm.cap_m, gm.cap_g), up(msg_up, gm.cap_m, gm.cap_g);
-  // kept: ghost records of the leavers, lower direction in rows [0, cap_m), upper in [cap_m, 2 cap_m);
-  // holes: their row indices, same split
-  const M kp(kept, 0, 2 * gm.cap_m);
-  if (fl[0] && rank[0] < gm.cap_m) {
-    write_full<F, D>(src, i, lo.mig_f + (size_t)rank[0] * M::WF, lo.mig_i + (size_t)rank[0] * 3);
-    write_ghost<F, D>(src, i, kp.gh_f + (size_t)rank[0] * M::WG, kp.gh_i + (size_t)rank[0] * 2);
-    holes[rank[0]] = (int)i;
+  // headers — [0] full records, [1] ghost records, [2] strays seen by the sender — and, device protocol,
+  // the "message complete" flag: written by the block that finishes last, after every block's stores
+  // were fenced at system scope (the messages may live in a neighbour's memory)
+  if (gm.dev) {
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(gm.dev + kDevTicket), 1ULL);
+      s_last = t == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+  } else if (blockIdx.x != 0) {
+    return;
   }
-  if (fl[1] && rank[1] < gm.cap_m) {
-    write_full<F, D>(src, i, up.mig_f + (size_t)rank[1] * M::WF, up.mig_i + (size_t)rank[1] * 3);
-    write_ghost<F, D>(src, i, kp.gh_f + (size_t)(gm.cap_m + rank[1]) * M::WG, kp.gh_i + (size_t)(gm.cap_m + rank[1]) * 2);
-    holes[gm.cap_m + rank[1]] = (int)i;
+  if (threadIdx.x == 0) {
+    lo.header[0] = tot[1]; lo.header[1] = tot[3]; lo.header[2] = tot[5];
+    up.header[0] = tot[2]; up.header[1] = tot[4]; up.header[2] = tot[5];
+    hdr_local[0] = tot[0]; hdr_local[1] = tot[1]; hdr_local[2] = tot[2]; hdr_local[3] = tot[5];
+    if (gm.dev) {
+      gm.dev[kDevTicket] = 0;
+      __threadfence_system();
+      st_release_sys(lo.header + kHdrFlag, seq + 1);
+      st_release_sys(up.header + kHdrFlag, seq + 1);
+    }
   }
-  if (fl[2] && rank[2] < gm.cap_g)
-    write_ghost<F, D>(src, i, lo.gh_f + (size_t)rank[2] * M::WG, lo.gh_i + (size_t)rank[2] * 2);
-  if (fl[3] && rank[3] < gm.cap_g)
-    write_ghost<F, D>(src, i, up.gh_f + (size_t)rank[3] * M::WG, up.gh_i + (size_t)rank[3] * 2);
 }
 
-// counts of one exchange, known on the host after it: owned rows before, arrivals from the
-// lower / upper neighbour, leavers to the lower / upper neighbour, halo of the lower / upper
+// counts of one exchange: owned rows before, arrivals from the lower / upper neighbour, leavers to
+// the lower / upper neighbour, halo of the lower / upper neighbour.  Host protocol: kernel
+// arguments; device protocol: dev[kDevCounts ...], written by k_slab_repair
 struct SlabCounts {
   long long n_old, a_lo, a_up, k_lo, k_up, g_lo, g_up;
 };
-
-// holes[0, k_lo) and holes[cap_m, cap_m + k_up) are sorted; merged (sorted) list -> holes[2 cap_m ...)
-__global__ void __launch_bounds__(kSlabBlock) k_slab_merge_holes(SlabGeom gm, SlabCounts cn, int* __restrict__ holes) {
-  pdl_prologue();
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long l = cn.k_lo + cn.k_up;
-  if (t >= l) return;
-  const bool first = t < cn.k_lo;
-  const int* mine = first ? holes : holes + gm.cap_m;
-  const int* other = first ? holes + gm.cap_m : holes;
-  const long long r = first ? t : t - cn.k_lo, no = first ? cn.k_up : cn.k_lo;
-  const int v = mine[r];
-  long long lo = 0, hi = no;  // number of entries of the other list below v (indices are distinct)
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (other[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  holes[2 * gm.cap_m + r + lo] = v;
+__device__ __forceinline__ SlabCounts slab_counts(const SlabGeom& gm, const SlabCounts& host) {
+  if (!gm.dev) return host;
+  const long long* c = gm.dev + kDevCounts;
+  return SlabCounts{c[0], c[1], c[2], c[3], c[4], c[5], c[6]};
 }
 
 template <typename F, int D>
 __device__ __forceinline__ void copy_row(const SlabRows<F>& s, long long from, long long to) {
   F f[SlabMsg<F, D>::WF];
   long long iv[3];
-  write_full<F, D>(s, from, f, iv);
-  read_full<F, D>(s, to, f, iv);
+  write_full<F, D>(s, from, f, iv, 1, 0);
+  read_full<F, D>(s, to, f, iv, 1, 0);
 }
 
-// more leavers than arrivals: the holes the arrivals do not fill are R = sorted_holes[a, l); the new
-// row count is n' = n_old - (l - a).  Rows of the tail [n', n_old) that are not holes move, in index
-// order, into the holes below n' (a prefix of R).  One block: the tail is l - a rows long.
+// One block repairs the owned rows after an exchange:
+//  (device protocol) wait for both neighbours' "message complete" flags, read the counts from the
+//  headers, check them against the capacities, publish the new row counts;
+//  merge the two sorted hole lists holes[0, k_lo) and holes[cap_m, cap_m + k_up) -> holes[2 cap_m ...);
+//  more leavers than arrivals: the holes the arrivals do not fill are R = sorted_holes[a, l), the new
+//  row count is n' = n_old - (l - a); rows of the tail [n', n_old) that are not holes move, in index
+//  order, into the holes below n' (a prefix of R).
 template <typename F, int D>
-__global__ void __launch_bounds__(1024) k_slab_tail_move(SlabGeom gm, SlabRows<F> rows, SlabCounts cn,
-                                                         const int* __restrict__ holes) {
+__global__ void __launch_bounds__(1024) k_slab_repair(SlabGeom gm, SlabRows<F> rows, SlabCounts host, SlabPorts in,
+                                                      const long long* __restrict__ hdr_local, int* __restrict__ holes,
+                                                      long long timeout_ns) {
   pdl_prologue();
   __shared__ int s_warp[32];
   __shared__ int s_base;
+  __shared__ SlabCounts s_cn;
+  if (threadIdx.x == 0) {
+    s_base = 0;
+    if (!gm.dev) {
+      s_cn = host;
+    } else {
+      long long* dev = gm.dev;
+      const long long seq = dev[kDevSeq];
+      const int par = (int)(seq & 1);
+      const long long* hlo = (const long long*)in.lo[par];
+      const long long* hup = (const long long*)in.up[par];
+      long long status = 0;
+      const unsigned long long t0 = global_timer_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys(hlo + kHdrFlag) != seq + 1 || ld_acquire_sys(hup + kHdrFlag) != seq + 1) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > (unsigned long long)timeout_ns) {
+          status |= JDB200_SLAB_TIMEOUT;
+          break;
+        }
+      }
+      SlabCounts cn;
+      cn.n_old = dev[kDevOwn];
+      cn.k_lo = hdr_local[1]; cn.k_up = hdr_local[2];
+      cn.a_lo = hlo[0]; cn.g_lo = hlo[1];
+      cn.a_up = hup[0]; cn.g_up = hup[1];
+      if (hdr_local[3] || hlo[2] || hup[2]) status |= JDB200_SLAB_STRAY;
+      const long long mig = max(max(cn.k_lo, cn.k_up), max(cn.a_lo, cn.a_up)), gh = max(cn.g_lo, cn.g_up);
+      if (mig > gm.cap_m || gh > gm.cap_g) status |= JDB200_SLAB_MESSAGE_FULL;
+      long long n_new = cn.n_old - cn.k_lo - cn.k_up + cn.a_lo + cn.a_up;
+      long long n_gh = cn.k_lo + cn.k_up + cn.g_lo + cn.g_up;
+      if (max(n_new, cn.n_old) + n_gh > gm.n) status |= JDB200_SLAB_ROWS_FULL;
+      if (status & (JDB200_SLAB_TIMEOUT | JDB200_SLAB_MESSAGE_FULL | JDB200_SLAB_ROWS_FULL)) {
+        // nothing can be placed safely: leave the rows as they are (the host raises at its next look)
+        cn.a_lo = cn.a_up = cn.k_lo = cn.k_up = cn.g_lo = cn.g_up = 0;
+        n_new = cn.n_old;
+        n_gh = 0;
+      }
+      dev[kDevMaxMig] = max(dev[kDevMaxMig], mig);
+      dev[kDevMaxGhost] = max(dev[kDevMaxGhost], gh);
+      dev[kDevStatus] |= status;
+      long long* c = dev + kDevCounts;
+      c[0] = cn.n_old; c[1] = cn.a_lo; c[2] = cn.a_up; c[3] = cn.k_lo; c[4] = cn.k_up; c[5] = cn.g_lo; c[6] = cn.g_up;
+      dev[kDevOwn] = n_new;
+      dev[kDevLocal] = n_new + n_gh;
+      dev[kDevSeq] = seq + 1;
+      s_cn = cn;
+    }
+  }
+  __syncthreads();
+  const SlabCounts cn = s_cn;
   const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
+  // ---- merge the hole lists (indices are distinct) ----
+  for (long long t = threadIdx.x; t < l; t += blockDim.x) {
+    const bool first = t < cn.k_lo;
+    const int* mine = first ? holes : holes + gm.cap_m;
+    const int* other = first ? holes + gm.cap_m : holes;
+    const long long r = first ? t : t - cn.k_lo, no = first ? cn.k_up : cn.k_lo;
+    const int v = mine[r];
+    long long lo = 0, hi = no;  // number of entries of the other list below v
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (other[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    holes[2 * gm.cap_m + r + lo] = v;
+  }
+  if (l <= a) return;
+  __syncthreads();
+  // ---- tail move ----
   const long long nr = l - a, n_new = cn.n_old - nr;
   const int* R = holes + 2 * gm.cap_m + a;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long t0 = 0; t0 < nr; t0 += 1024) {
     const long long row = n_new + t0 + threadIdx.x;
@@ -435,32 +581,32 @@ __global__ void __launch_bounds__(1024) k_slab_tail_move(SlabGeom gm, SlabRows<F
 // then the ghost rows behind the owned rows: leavers kept behind (lower, upper), halo of the
 // lower, halo of the upper neighbour
 template <typename F, int D>
-__global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(SlabGeom gm, SlabRows<F> dst, SlabCounts cn,
-                                                             const void* from_lo, const void* from_up, const void* kept,
-                                                             const int* __restrict__ holes) {
+__global__ void __launch_bounds__(kSlabBlock) k_slab_unpack(SlabGeom gm, SlabRows<F> dst, SlabCounts host, SlabPorts in,
+                                                             const void* kept, const int* __restrict__ holes) {
   pdl_prologue();
   using M = SlabMsg<F, D>;
+  const SlabCounts cn = slab_counts(gm, host);
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const M lo((void*)from_lo, gm.cap_m, gm.cap_g), up((void*)from_up, gm.cap_m, gm.cap_g), kp((void*)kept, 0, 2 * gm.cap_m);
   const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
+  if (t >= a + l + cn.g_lo + cn.g_up) return;
+  const int par = gm.dev ? (int)((gm.dev[kDevSeq] - 1) & 1) : 0;  // k_slab_repair has advanced seq already
+  const M lo(in.lo[par], gm.cap_m, gm.cap_g), up(in.up[par], gm.cap_m, gm.cap_g), kp((void*)kept, 0, 2 * gm.cap_m);
+  const size_t cm = (size_t)gm.cap_m, cg = (size_t)gm.cap_g;
   if (t < a) {
     const long long row = t < l ? (long long)holes[2 * gm.cap_m + t] : cn.n_old + (t - l);
-    if (t < cn.a_lo) read_full<F, D>(dst, row, lo.mig_f + (size_t)t * M::WF, lo.mig_i + (size_t)t * 3);
-    else read_full<F, D>(dst, row, up.mig_f + (size_t)(t - cn.a_lo) * M::WF, up.mig_i + (size_t)(t - cn.a_lo) * 3);
+    if (t < cn.a_lo) read_full<F, D>(dst, row, lo.mig_f, lo.mig_i, cm, t);
+    else read_full<F, D>(dst, row, up.mig_f, up.mig_i, cm, t - cn.a_lo);
     return;
   }
   t -= a;
   const long long row = cn.n_old - l + a + t;
-  if (t < cn.k_lo) { read_ghost<F, D>(dst, row, kp.gh_f + (size_t)t * M::WG, kp.gh_i + (size_t)t * 2); return; }
+  if (t < cn.k_lo) { read_ghost<F, D>(dst, row, kp.gh_f, kp.gh_i, 2 * cm, t); return; }
   t -= cn.k_lo;
-  if (t < cn.k_up) {
-    read_ghost<F, D>(dst, row, kp.gh_f + (size_t)(gm.cap_m + t) * M::WG, kp.gh_i + (size_t)(gm.cap_m + t) * 2);
-    return;
-  }
+  if (t < cn.k_up) { read_ghost<F, D>(dst, row, kp.gh_f, kp.gh_i, 2 * cm, cm + t); return; }
   t -= cn.k_up;
-  if (t < cn.g_lo) { read_ghost<F, D>(dst, row, lo.gh_f + (size_t)t * M::WG, lo.gh_i + (size_t)t * 2); return; }
+  if (t < cn.g_lo) { read_ghost<F, D>(dst, row, lo.gh_f, lo.gh_i, cg, t); return; }
   t -= cn.g_lo;
-  if (t < cn.g_up) read_ghost<F, D>(dst, row, up.gh_f + (size_t)t * M::WG, up.gh_i + (size_t)t * 2);
+  if (t < cn.g_up) read_ghost<F, D>(dst, row, up.gh_f, up.gh_i, cg, t);
 }
 
 static inline int slab_check(const jdb200_slab_desc* d) {
@@ -471,43 +617,45 @@ static inline int slab_check(const jdb200_slab_desc* d) {
   if (d->lo_layer < 0 || d->up_layer > d->n_layers || d->lo_layer >= d->up_layer) return JDB200_EINVAL;
   return 0;
 }
-static inline SlabGeom slab_geom(const jdb200_slab_desc* d) {
-  return SlabGeom{d->n, d->n_layers, d->lo_layer, d->up_layer, d->search_range, d->cap_mig, d->cap_ghost};
+static inline SlabGeom slab_geom(const jdb200_slab_desc* d, void* dev) {
+  return SlabGeom{d->n, d->n_layers, d->lo_layer, d->up_layer, d->search_range, d->cap_mig, d->cap_ghost, (long long*)dev};
 }
 
 template <typename F, int D>
-int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, void* msg_lo, void* msg_up,
-              void* kept, void* holes, void* header_local, void* scratch) {
-  using M = SlabMsg<F, D>;
-  const SlabGeom gm = slab_geom(d);
+int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, SlabPorts out, void* kept,
+              void* holes, void* header_local, void* scratch, void* dev) {
+  const SlabGeom gm = slab_geom(d, dev);
   const int nb = std::max(1, cdiv(d->n, kSlabBlock));
   uint8_t* cat = (uint8_t*)scratch;
   int* bc = (int*)((char*)scratch + (((size_t)nb * kSlabBlock + 255) & ~size_t(255)));
+  long long* tot = (long long*)(bc + (size_t)nb * 8);
   if (d->dt)
     JDB_LAUNCH((k_slab_classify<F, D, true>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)d->dt,
                (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
   else
     JDB_LAUNCH((k_slab_classify<F, D, false>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)nullptr,
                (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
-  const M lo(msg_lo, gm.cap_m, gm.cap_g), up(msg_up, gm.cap_m, gm.cap_g);
-  JDB_LAUNCH(k_slab_scan, dim3(1), 1024, s, nb, bc, lo.header, up.header, (long long*)header_local);
-  JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, msg_lo, msg_up, kept,
-             (int*)holes);
+  JDB_LAUNCH(k_slab_scan, dim3(1), 1024, s, gm, bc, tot);
+  JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, tot, out, kept, (int*)holes,
+             (long long*)header_local);
   return 0;
 }
 
 template <typename F, int D>
 int slab_unpack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, const int64_t* counts,
-                const void* from_lo, const void* from_up, const void* kept, void* holes) {
-  const SlabCounts cn{counts[0], counts[1], counts[2], counts[3], counts[4], counts[5], counts[6]};
-  const SlabGeom gm = slab_geom(d);
-  const long long l = cn.k_lo + cn.k_up, a = cn.a_lo + cn.a_up;
-  if (l > 0) JDB_LAUNCH(k_slab_merge_holes, dim3(cdiv(l, kSlabBlock)), kSlabBlock, s, gm, cn, (int*)holes);
-  if (l > a) JDB_LAUNCH((k_slab_tail_move<F, D>), dim3(1), 1024, s, gm, slab_rows<F>(rows), cn, (const int*)holes);
-  const long long tot = a + cn.k_lo + cn.k_up + cn.g_lo + cn.g_up;
+                SlabPorts in, const void* header_local, const void* kept, void* holes, void* dev, long long timeout_ns) {
+  SlabCounts cn{0, 0, 0, 0, 0, 0, 0};
+  if (counts) cn = SlabCounts{counts[0], counts[1], counts[2], counts[3], counts[4], counts[5], counts[6]};
+  const SlabGeom gm = slab_geom(d, dev);
+  const long long l = cn.k_lo + cn.k_up;
+  // host protocol: exact grids; device protocol: grids over the capacities, early exit on the live counts
+  const long long tot = dev ? 4 * d->cap_mig + 2 * d->cap_ghost : cn.a_lo + cn.a_up + l + cn.g_lo + cn.g_up;
+  if (dev || l > 0)
+    JDB_LAUNCH((k_slab_repair<F, D>), dim3(1), 1024, s, gm, slab_rows<F>(rows), cn, in, (const long long*)header_local,
+               (int*)holes, timeout_ns);
   if (tot > 0)
-    JDB_LAUNCH((k_slab_unpack<F, D>), dim3(cdiv(tot, kSlabBlock)), kSlabBlock, s, gm, slab_rows<F>(rows), cn, from_lo,
-               from_up, kept, (const int*)holes);
+    JDB_LAUNCH((k_slab_unpack<F, D>), dim3(cdiv(tot, kSlabBlock)), kSlabBlock, s, gm, slab_rows<F>(rows), cn, in, kept,
+               (const int*)holes);
   return 0;
 }
 
@@ -561,7 +709,8 @@ JDB200_API int jdb200_slab_pack(void* stream, const jdb200_slab_desc* d, const j
     return JDB200_ENULL;
   if (scratch_bytes < jdb200_slab_scratch_bytes(d)) return JDB200_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  SLAB_DISPATCH((slab_pack<F, D>(s, d, rows, msg_lo, msg_up, kept, holes, header_local, scratch)))
+  const SlabPorts out{{msg_lo, msg_lo}, {msg_up, msg_up}};
+  SLAB_DISPATCH((slab_pack<F, D>(s, d, rows, out, kept, holes, header_local, scratch, nullptr)))
 }
 
 JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
@@ -571,7 +720,36 @@ JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const
   if (rc) return rc;
   if (!rows || !counts || !from_lo || !from_up || !kept || !holes) return JDB200_ENULL;
   cudaStream_t s = (cudaStream_t)stream;
-  SLAB_DISPATCH((slab_unpack<F, D>(s, d, rows, counts, from_lo, from_up, kept, holes)))
+  const SlabPorts in{{(void*)from_lo, (void*)from_lo}, {(void*)from_up, (void*)from_up}};
+  SLAB_DISPATCH((slab_unpack<F, D>(s, d, rows, counts, in, nullptr, kept, holes, nullptr, 0)))
+}
+
+JDB200_API int jdb200_slab_pack_dev(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                    void* dev_state, void* const msg_lo[2], void* const msg_up[2], void* kept,
+                                    void* holes, void* header_local, void* scratch, size_t scratch_bytes) {
+  int rc = slab_check(d);
+  if (rc) return rc;
+  if (!rows || !dev_state || !msg_lo || !msg_up || !msg_lo[0] || !msg_lo[1] || !msg_up[0] || !msg_up[1] || !kept ||
+      !holes || !header_local || !scratch || !d->anchor || !d->box_size || !d->cell_size)
+    return JDB200_ENULL;
+  if (scratch_bytes < jdb200_slab_scratch_bytes(d)) return JDB200_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const SlabPorts out{{msg_lo[0], msg_lo[1]}, {msg_up[0], msg_up[1]}};
+  SLAB_DISPATCH((slab_pack<F, D>(s, d, rows, out, kept, holes, header_local, scratch, dev_state)))
+}
+
+JDB200_API int jdb200_slab_unpack_dev(void* stream, const jdb200_slab_desc* d, const jdb200_slab_rows* rows,
+                                      void* dev_state, const void* const from_lo[2], const void* const from_up[2],
+                                      const void* header_local, const void* kept, void* holes, int64_t timeout_ns) {
+  int rc = slab_check(d);
+  if (rc) return rc;
+  if (!rows || !dev_state || !from_lo || !from_up || !from_lo[0] || !from_lo[1] || !from_up[0] || !from_up[1] ||
+      !header_local || !kept || !holes)
+    return JDB200_ENULL;
+  if (timeout_ns <= 0) return JDB200_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const SlabPorts in{{(void*)from_lo[0], (void*)from_lo[1]}, {(void*)from_up[0], (void*)from_up[1]}};
+  SLAB_DISPATCH((slab_unpack<F, D>(s, d, rows, nullptr, in, header_local, kept, holes, dev_state, (long long)timeout_ns)))
 }
 
 }  // extern "C"

@@ -23,6 +23,7 @@ using T_ = RT<F>;
 template <typename F, bool HALF, bool DRIFT>
 __global__ void __launch_bounds__(256) k_linear(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // element of (N, D)
@@ -188,6 +189,7 @@ __device__ __forceinline__ void store_q_and_cache(const Ctx<F>& c, size_t gi, co
 template <typename F, int MODE>
 __global__ void __launch_bounds__(256) k_rotation(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   using T = RT<F>;
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,6 +373,7 @@ __device__ __forceinline__ void fm_totals(const Ctx<F>& c, int b, size_t gi, F c
 template <typename F>
 __global__ void __launch_bounds__(256) k_fm_spheres(Ctx<F> c) {
   pdl_prologue();
+  JDB_LIVE_ROWS(c);
   const int b = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.n) return;
