@@ -255,6 +255,11 @@ class ClockSampler:
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi takes 0.1 - 1 s to attach to the driver, during which kernel launches of this process can
+            # stall for milliseconds: wait for its first sample so the timed region only sees the steady 100 ms polls
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -872,6 +877,7 @@ def run_cuda_slab(args, world, rank, local, dev):
         b.record()
     barrier()
     launches = lib.jdb200_launch_count() - l0
+    slab.sync_counts()  # raises if any exchange of the timed region set a status bit (stray / capacity / timeout)
     per_step = [a.elapsed_time(b) for a, b in ev]
     ms = float(sum(per_step))
     clocks = sampler.stop() if rank == 0 else None
@@ -888,11 +894,13 @@ def run_cuda_slab(args, world, rank, local, dev):
 
     def e2e_step(first=False):
         nonlocal h2d, d2h
+        slab.sync_counts()  # device protocol: the owned-row count lives on the device (after the previous step's sync)
         m = slab.n_own
         if not first:
             for k in fields:
                 slab.buf[k][:m].copy_(host[k][:m], non_blocking=True)
         slab.step(1)
+        slab.sync_counts()
         m2 = slab.n_own
         for k in fields:
             host[k][:m2].copy_(slab.buf[k][:m2], non_blocking=True)
@@ -935,7 +943,9 @@ def run_cuda_slab(args, world, rank, local, dev):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n),
-            "launch": "stream launches, hook by hook",
+            "launch": ("stream launches, hook by hook; row counts, exchange flags and error bits stay on the device "
+                       "(no host synchronisation inside a step)" if slab.device_protocol else
+                       "stream launches, hook by hook; one host read of the exchange headers per step"),
             "n_particles_total": n_total,
             "owned_ghost_rows_per_rank": [[int(x) for x in o.tolist()] for o in owns],
             "clocks": clocks,

@@ -1440,6 +1440,18 @@ int launch_pair_force(cudaStream_t s, Ctx<F>& c, bool with_torque) {
                  : launch_pair_force_epi<F, D, 0>(s, c, with_torque);
 }
 
+// The four (dtype, dim) instantiations of the force launchers are the bulk of this file's compile
+// time: each is built by its own translation unit (pair_f32_3d.cu ... include this file with
+// JDB_PAIR_SLICE_F / JDB_PAIR_SLICE_D set), the rest by pair.cu itself.
+#ifdef JDB_PAIR_SLICE_F
+template int launch_pair_force<JDB_PAIR_SLICE_F, JDB_PAIR_SLICE_D>(cudaStream_t, Ctx<JDB_PAIR_SLICE_F>&, bool);
+#else
+extern template int launch_pair_force<float, 2>(cudaStream_t, Ctx<float>&, bool);
+extern template int launch_pair_force<float, 3>(cudaStream_t, Ctx<float>&, bool);
+extern template int launch_pair_force<double, 2>(cudaStream_t, Ctx<double>&, bool);
+extern template int launch_pair_force<double, 3>(cudaStream_t, Ctx<double>&, bool);
+#endif
+
 // hash_mode / ext: fusion of the linear integrator into the hash kernel (celllist.cu k_hash);
 // with_torque = false skips the torque store (fused driver only).
 template <typename F>
@@ -1526,7 +1538,9 @@ int naive_energy(cudaStream_t s, Ctx<F>& c, F* energy) {
   template int celllist_cross_neighbor_list<F>(cudaStream_t, Ctx<F>&, const F*, long long, const F*, RT<F>::I*, uint8_t*); \
   template int naive_force<F>(cudaStream_t, Ctx<F>&);                                   \
   template int naive_energy<F>(cudaStream_t, Ctx<F>&, F*);
+#ifndef JDB_PAIR_SLICE_F
 JDB_INST(float)
 JDB_INST(double)
+#endif
 
 }  // namespace jdb

@@ -217,7 +217,8 @@ template <typename F, int D, bool INTEGRATE>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, SlabRows<F> rows, const F* __restrict__ dtp,
                                                                const F* __restrict__ anchor, const F* __restrict__ box,
                                                                const F* __restrict__ cell_size,
-                                                               uint8_t* __restrict__ cat, int* __restrict__ bc) {
+                                                               uint8_t* __restrict__ cat, int* __restrict__ bc,
+                                                               int* __restrict__ sup) {
   pdl_prologue();
   using I = typename RT<F>::I;
   using T = RT<F>;
@@ -275,70 +276,66 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_classify(SlabGeom gm, SlabR
   if (threadIdx.x == 0) {
     int* o = bc + (size_t)blockIdx.x * 8;
     o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5;
+    // sums over groups of 32 blocks (integer atomics: exact, order-free), so the scan below is one
+    // short parallel pass; zeroed again by k_slab_pack
+    int* sp = sup + (size_t)(blockIdx.x >> 5) * 8;
+    if (n0) atomicAdd(sp + 0, n0);
+    if (n1) atomicAdd(sp + 1, n1);
+    if (n2) atomicAdd(sp + 2, n2);
+    if (n3) atomicAdd(sp + 3, n3);
+    if (n4) atomicAdd(sp + 4, n4);
+    if (n5) atomicAdd(sp + 5, n5);
   }
 }
 
-// exclusive scan of the block counts (one block: thread t owns a contiguous chunk of blocks,
-// the 1024 chunk sums are scanned with shuffles); totals -> tot[6] (stay, leave-lo, leave-up,
-// halo-lo, halo-up, stray)
-__global__ void __launch_bounds__(1024) k_slab_scan(SlabGeom gm, int* __restrict__ bc, long long* __restrict__ tot) {
+// exclusive scan of the block counts -> per-block offsets of the six lists, totals -> tot[6] (stay,
+// leave-lo, leave-up, halo-lo, halo-up, stray).  One warp per group of 32 blocks: its base is the sum of
+// the earlier groups' accumulators (k_slab_classify), its own 32 counts are scanned with shuffles.
+__global__ void __launch_bounds__(256) k_slab_scan(SlabGeom gm, int* __restrict__ bc, const int* __restrict__ sup,
+                                                   long long* __restrict__ tot) {
   pdl_prologue();
-  __shared__ int s_warp[32][6];
-  __shared__ int s_tot[6];
   const long long n = slab_rows_live(gm);
   const int nblocks = (int)max((n + kSlabBlock - 1) / kSlabBlock, 1LL);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (nblocks + 1023) / 1024;
-  const int b0 = min((int)threadIdx.x * per, nblocks), b1 = min(b0 + per, nblocks);
-  int sum[6] = {0, 0, 0, 0, 0, 0};
-  for (int b = b0; b < b1; ++b) {
-    const int4 lo4 = *reinterpret_cast<const int4*>(bc + (size_t)b * 8);
-    const int2 hi2 = *reinterpret_cast<const int2*>(bc + (size_t)b * 8 + 4);
-    sum[0] += lo4.x; sum[1] += lo4.y; sum[2] += lo4.z; sum[3] += lo4.w; sum[4] += hi2.x; sum[5] += hi2.y;
+  const int nsup = (nblocks + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (sg >= nsup) return;
+  int pre[6] = {0, 0, 0, 0, 0, 0};
+  for (int s2 = lane; s2 < sg; s2 += 32) {
+    const int4 a = *reinterpret_cast<const int4*>(sup + (size_t)s2 * 8);
+    const int2 h = *reinterpret_cast<const int2*>(sup + (size_t)s2 * 8 + 4);
+    pre[0] += a.x; pre[1] += a.y; pre[2] += a.z; pre[3] += a.w; pre[4] += h.x; pre[5] += h.y;
   }
-  int excl[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre[j] += __shfl_xor_sync(0xffffffffu, pre[j], o);
+  const int b = sg * 32 + lane;
+  int v[6] = {0, 0, 0, 0, 0, 0};
+  if (b < nblocks) {
+    const int4 a = *reinterpret_cast<const int4*>(bc + (size_t)b * 8);
+    const int2 h = *reinterpret_cast<const int2*>(bc + (size_t)b * 8 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = h.x; v[5] = h.y;
+  }
+  int incl[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    int incl = sum[j];
+    incl[j] = v[j];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp][j] = incl;
-    excl[j] = incl - sum[j];
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int v = s_warp[lane][j];
-      int incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      s_warp[lane][j] = incl - v;
-      if (lane == 31) s_tot[j] = incl;
+      const int t = __shfl_up_sync(0xffffffffu, incl[j], o);
+      if (lane >= o) incl[j] += t;
     }
   }
-  __syncthreads();
-  int run[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) run[j] = excl[j] + s_warp[warp][j];
-  for (int b = b0; b < b1; ++b) {
-    int4 lo4 = *reinterpret_cast<const int4*>(bc + (size_t)b * 8);
-    int2 hi2 = *reinterpret_cast<const int2*>(bc + (size_t)b * 8 + 4);
-    const int v[6] = {lo4.x, lo4.y, lo4.z, lo4.w, hi2.x, hi2.y};
-    lo4 = make_int4(run[0], run[1], run[2], run[3]);
-    hi2 = make_int2(run[4], run[5]);
-    *reinterpret_cast<int4*>(bc + (size_t)b * 8) = lo4;
-    *reinterpret_cast<int2*>(bc + (size_t)b * 8 + 4) = hi2;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) run[j] += v[j];
+  if (b < nblocks) {
+    *reinterpret_cast<int4*>(bc + (size_t)b * 8) =
+        make_int4(pre[0] + incl[0] - v[0], pre[1] + incl[1] - v[1], pre[2] + incl[2] - v[2], pre[3] + incl[3] - v[3]);
+    *reinterpret_cast<int2*>(bc + (size_t)b * 8 + 4) = make_int2(pre[4] + incl[4] - v[4], pre[5] + incl[5] - v[5]);
   }
-  if (threadIdx.x < 6) tot[threadIdx.x] = s_tot[threadIdx.x];
+  if (sg == nsup - 1 && lane == 31) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tot[j] = pre[j] + incl[j];
+  }
 }
 
 __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
@@ -367,10 +364,13 @@ template <typename F, int D>
 __global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, const uint8_t* __restrict__ cat,
                                                            const int* __restrict__ bc, const long long* __restrict__ tot,
                                                            SlabPorts out, void* kept, int* __restrict__ holes,
-                                                           long long* __restrict__ hdr_local) {
+                                                           long long* __restrict__ hdr_local, int* __restrict__ sup,
+                                                           int nsup) {
   pdl_prologue();
   using M = SlabMsg<F, D>;
   __shared__ int s_w[kSlabBlock / 32][kPackLists];
+  if (blockIdx.x == 0)  // the group accumulators of k_slab_classify: zero for the next exchange
+    for (int t = threadIdx.x; t < nsup * 8; t += blockDim.x) sup[t] = 0;
   const long long n = slab_rows_live(gm);
   const long long seq = gm.dev ? gm.dev[kDevSeq] : 0;
   const int par = (int)(seq & 1);
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<
   const bool fl[kPackLists] = {live && (c8 & 4) != 0, live && (c8 & 8) != 0, stay && (c8 & 1) != 0,
                                stay && (c8 & 2) != 0};
   const M lo(out.lo[par], gm.cap_m, gm.cap_g), up(out.up[par], gm.cap_m, gm.cap_g);
-  if (__syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3])) {  // interior blocks have nothing to pack
+  const bool wrote = __syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3]) != 0;
+  if (wrote) {  // interior blocks have nothing to pack
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int rank[kPackLists];
 #pragma unroll
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<
   // were fenced at system scope (the messages may live in a neighbour's memory)
   if (gm.dev) {
     __shared__ bool s_last;
-    __threadfence_system();
+    if (wrote) __threadfence_system();  // only blocks that stored records pay for the system-scope fence
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(gm.dev + kDevTicket), 1ULL);
@@ -437,6 +438,8 @@ __global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<
     hdr_local[0] = tot[0]; hdr_local[1] = tot[1]; hdr_local[2] = tot[2]; hdr_local[3] = tot[5];
     if (gm.dev) {
       gm.dev[kDevTicket] = 0;
+      if (tot[1] > gm.cap_m || tot[2] > gm.cap_m || tot[3] > gm.cap_g || tot[4] > gm.cap_g)
+        gm.dev[kDevStatus] |= JDB200_SLAB_MESSAGE_FULL;  // the receiver sees the same through the counts
       __threadfence_system();
       st_release_sys(lo.header + kHdrFlag, seq + 1);
       st_release_sys(up.header + kHdrFlag, seq + 1);
@@ -629,15 +632,17 @@ int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows*
   uint8_t* cat = (uint8_t*)scratch;
   int* bc = (int*)((char*)scratch + (((size_t)nb * kSlabBlock + 255) & ~size_t(255)));
   long long* tot = (long long*)(bc + (size_t)nb * 8);
+  const int nsup = cdiv(nb, 32);
+  int* sup = (int*)(tot + 8);  // zero before the first call (jdb200_slab_scratch_bytes), kept zero by k_slab_pack
   if (d->dt)
     JDB_LAUNCH((k_slab_classify<F, D, true>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)d->dt,
-               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc, sup);
   else
     JDB_LAUNCH((k_slab_classify<F, D, false>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)nullptr,
-               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc);
-  JDB_LAUNCH(k_slab_scan, dim3(1), 1024, s, gm, bc, tot);
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc, sup);
+  JDB_LAUNCH(k_slab_scan, dim3(cdiv(nsup, 8)), 256, s, gm, bc, (const int*)sup, tot);
   JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, tot, out, kept, (int*)holes,
-             (long long*)header_local);
+             (long long*)header_local, sup, nsup);
   return 0;
 }
 
@@ -691,7 +696,7 @@ JDB200_API size_t jdb200_slab_kept_bytes(const jdb200_slab_desc* d) {
 JDB200_API size_t jdb200_slab_scratch_bytes(const jdb200_slab_desc* d) {
   if (slab_check(d)) return 0;
   const size_t nb = (size_t)std::max(1, cdiv(d->n, kSlabBlock));
-  return ((nb * kSlabBlock + 255) & ~size_t(255)) + nb * 8 * sizeof(int) + 256;
+  return ((nb * kSlabBlock + 255) & ~size_t(255)) + nb * 8 * sizeof(int) + 64 + ((nb + 31) / 32) * 8 * sizeof(int) + 256;
 }
 
 JDB200_API size_t jdb200_slab_holes_bytes(const jdb200_slab_desc* d) {

@@ -79,9 +79,10 @@ GHOST_FLOAT_FIELDS = ("pos_c", "vel", "ang_vel", "rad", "mass")
 
 def message_layout(dim: int, fbytes: int, cap_m: int, cap_g: int) -> dict:
     """Byte layout of one exchange message (csrc/slab.cu: SlabMsg): int64 header[8] — [0] full
-    records, [1] ghost records, [2] strays —, full records (floats in ROW_FLOAT_FIELDS order, then
-    int64 gid / mat_id / fixed), ghost records (floats in GHOST_FLOAT_FIELDS order, then int64
-    gid / mat_id); sections 16-byte aligned."""
+    records, [1] ghost records, [2] strays, [7] device protocol: exchange number + 1 once the message
+    is complete —, full records (floats in ROW_FLOAT_FIELDS order, then int64 gid / mat_id / fixed),
+    ghost records (floats in GHOST_FLOAT_FIELDS order, then int64 gid / mat_id); sections 16-byte
+    aligned, records field-major inside a section."""
     A = _A(dim)
     WF, WG = 3 * dim + 3 * A + 1 + 3 + 2, 2 * dim + A + 2
     al = lambda x: (x + 15) & ~15
@@ -99,14 +100,16 @@ def message_layout(dim: int, fbytes: int, cap_m: int, cap_g: int) -> dict:
 
 
 def message_views(buf: torch.Tensor, L: dict, F: torch.dtype) -> dict:
+    """(records, words) views of one message.  Inside a section the records are FIELD-MAJOR (word c of
+    record r at base[c * capacity + r], csrc/slab.cu): the views are transposes, index them in place."""
     fb = torch.empty((), dtype=F).element_size()
     cm, cg, WF, WG = L["cap_m"], L["cap_g"], L["WF"], L["WG"]
     return dict(
         header=buf[0:64].view(torch.int64),
-        mig_f=buf[L["mig_f"]:L["mig_f"] + cm * WF * fb].view(F).view(cm, WF),
-        mig_i=buf[L["mig_i"]:L["mig_i"] + cm * 24].view(torch.int64).view(cm, 3),
-        gh_f=buf[L["gh_f"]:L["gh_f"] + cg * WG * fb].view(F).view(cg, WG),
-        gh_i=buf[L["gh_i"]:L["gh_i"] + cg * 16].view(torch.int64).view(cg, 2),
+        mig_f=buf[L["mig_f"]:L["mig_f"] + cm * WF * fb].view(F).view(WF, cm).t(),
+        mig_i=buf[L["mig_i"]:L["mig_i"] + cm * 24].view(torch.int64).view(3, cm).t(),
+        gh_f=buf[L["gh_f"]:L["gh_f"] + cg * WG * fb].view(F).view(WG, cg).t(),
+        gh_i=buf[L["gh_i"]:L["gh_i"] + cg * 16].view(torch.int64).view(2, cg).t(),
     )
 
 
@@ -158,12 +161,22 @@ class CudaEngine:
         self.fuse_before = self._fuse_after and slab.world > 1
         self._bound = dict(p=p, sv=_call.state_view(full), yv=_call.system_view(self.system), ws=ws, lib=L.lib(),
                            keep=full, dev=slab.device, C=C, check=L.check, stream=_call.stream_ptr)
+        if slab.dev_state is not None:
+            # device protocol: the hooks run over a launch bound and read the live row count themselves
+            # (jdb200_state.n_rows): word 0 = owned rows, word 1 = owned + ghost rows
+            for key, word in (("sv_own", 0), ("sv_local", 1)):
+                v = _call.state_view(full)
+                v.n_rows = slab.dev_state.data_ptr() + 8 * word
+                self._bound[key] = v
 
-    def _hook(self, name, n, ws=True):
+    def _hook(self, name, n, ws=True, rows=None):
+        """``rows``: None (n is the exact row count) or "own" / "local" (n is the launch bound, the live count is
+        the slab's device-side word)."""
         b = self._bound
         C = b["C"]
         b["p"].n = int(n)
-        args = [b["stream"](b["dev"]), C.byref(b["p"]), C.byref(b["sv"]), C.byref(b["yv"])]
+        sv = b["sv"] if rows is None else b["sv_" + rows]
+        args = [b["stream"](b["dev"]), C.byref(b["p"]), C.byref(sv), C.byref(b["yv"])]
         if ws:
             args += [C.c_void_p(b["ws"].data_ptr()), C.c_size_t(b["ws"].numel())]
         b["check"](getattr(b["lib"], name)(*args), name)
@@ -249,7 +262,8 @@ class CudaEngine:
             lib = L.lib()
             d = self._desc(slab, slab.cap)
             if self._scratch is None:
-                self._scratch = torch.empty(lib.jdb200_slab_scratch_bytes(C.byref(d)), dtype=torch.uint8,
+                # zero once: the kernels keep their block-group accumulators zeroed between exchanges
+                self._scratch = torch.zeros(lib.jdb200_slab_scratch_bytes(C.byref(d)), dtype=torch.uint8,
                                             device=slab.device)
             ex = self._ex = dict(key=key, d=d, rows=self._rows(slab.buf), lib=lib, C=C, check=L.check)
         return ex
@@ -265,6 +279,52 @@ class CudaEngine:
             _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), slab.send_ptr("lo"),
             slab.send_ptr("up"), slab.kept.data_ptr(), slab.holes.data_ptr(), slab.header_local.data_ptr(),
             self._scratch.data_ptr(), self._scratch.numel()), "jdb200_slab_pack")
+
+    def pack_dev(self, slab, integrate=False):
+        """Device protocol: classify / pack over the launch bound, messages stored into the neighbours'
+        receive buffers of the current parity, "complete" flag behind them (jdb200_slab_pack_dev)."""
+        from . import _call
+        ex = self._exchange_args(slab)
+        C = ex["C"]
+        ex["d"].n = int(slab.bound)
+        ex["d"].dt = self.system.dt.data_ptr() if integrate else None
+        pr = slab.ports
+        ex["check"](ex["lib"].jdb200_slab_pack_dev(
+            _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), slab.dev_state.data_ptr(),
+            pr["send_lo"], pr["send_up"], slab.kept.data_ptr(), slab.holes.data_ptr(), slab.header_local.data_ptr(),
+            self._scratch.data_ptr(), self._scratch.numel()), "jdb200_slab_pack_dev")
+
+    def unpack_dev(self, slab):
+        from . import _call
+        ex = self._exchange_args(slab)
+        C = ex["C"]
+        ex["d"].n = int(slab.bound)
+        pr = slab.ports
+        ex["check"](ex["lib"].jdb200_slab_unpack_dev(
+            _call.stream_ptr(slab.device), C.byref(ex["d"]), C.byref(ex["rows"]), slab.dev_state.data_ptr(),
+            pr["recv_lo"], pr["recv_up"], slab.header_local.data_ptr(), slab.kept.data_ptr(), slab.holes.data_ptr(),
+            C.c_int64(int(slab.timeout_s * 1e9))), "jdb200_slab_unpack_dev")
+
+    def step_dev(self, slab):
+        """One _step_once on the decomposed system, device protocol: no host synchronisation."""
+        sy, B = self.system, slab.bound
+        torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
+        if not self.fuse_before:
+            if sy.linear_integrator.native_kind:
+                self._hook("jdb200_linear_step_before_force", B, ws=False, rows="own")
+            if sy.rotation_integrator.native_kind:
+                self._hook("jdb200_rotation_step_before_force", B, ws=False, rows="own")
+        self.pack_dev(slab, integrate=self.fuse_before)
+        self.unpack_dev(slab)
+        if self._fuse_after:
+            self._hook("jdb200_celllist_force_step_after", B, rows="local")
+        else:
+            self._hook("jdb200_celllist_compute_force", B, rows="local")
+            self._hook("jdb200_force_manager_apply", B, rows="own")
+            if sy.linear_integrator.native_kind:
+                self._hook("jdb200_linear_step_after_force", B, ws=False, rows="own")
+            if sy.rotation_integrator.native_kind:
+                self._hook("jdb200_rotation_step_after_force", B, ws=False, rows="own")
 
     def unpack(self, slab, counts):
         from . import _call
@@ -327,6 +387,13 @@ class SlabSystem:
         lo, up = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         self.lo_rank, self.up_rank = lo, up
         self.header_local = torch.zeros(8, dtype=torch.int64, device=dev)
+        # device protocol (peer transport only): row counts, exchange number and status bits live on the device
+        # (csrc/slab.cu: kDev*), the host only looks at them every `check_every` steps, asynchronously
+        self.dev_state = None
+        self.bound = self.cap      # rows the kernels are launched over (>= the live owned + ghost rows)
+        self.check_every = 32
+        self.timeout_s = 5.0       # a neighbour's message that takes longer sets JDB200_SLAB_TIMEOUT
+        self._pending = None
         self._host_headers = torch.zeros((3, 8), dtype=torch.int64)
         if dev.type == "cuda":
             self._host_headers = self._host_headers.pin_memory()
@@ -337,6 +404,7 @@ class SlabSystem:
     def set_capacities(self, ghost_cap: int, migrant_cap: int) -> None:
         """(Re)allocate the exchange messages: collective, every rank must use the same capacities."""
         self.ghost_cap, self.migrant_cap = int(ghost_cap), int(migrant_cap)
+        self._dev_synced = False
         fb = torch.empty((), dtype=self.dtype).element_size()
         self.msg_layout = message_layout(self.dim, fb, self.migrant_cap, self.ghost_cap)
         self.kept_layout = message_layout(self.dim, fb, 0, 2 * self.migrant_cap)
@@ -360,8 +428,23 @@ class SlabSystem:
         if self._symm is None:
             self.send_lo, self.send_up = mk(nb), mk(nb)
             self.recv_lo, self.recv_up = mk(nb), mk(nb)
+            self.dev_state = None
         else:
+            self._parity = 0
             self._select_parity()
+            import ctypes as C
+            sm = self._symm
+            mine = sm["ptrs"][self.rank]
+            arr = lambda f: (C.c_void_p * 2)(*[C.c_void_p(f(q)) for q in (0, 1)])
+            # [parity] pointers: what goes down arrives in the lower neighbour's "from above" buffer and vice versa
+            self.ports = dict(send_lo=arr(lambda q: sm["ptrs"][self.lo_rank] + (2 * q + 1) * nb),
+                              send_up=arr(lambda q: sm["ptrs"][self.up_rank] + (2 * q) * nb),
+                              recv_lo=arr(lambda q: mine + (2 * q) * nb), recv_up=arr(lambda q: mine + (2 * q + 1) * nb))
+            self.dev_state = torch.zeros(16, dtype=torch.int64, device=self.device)
+            self._dev_host = torch.zeros((2, 16), dtype=torch.int64).pin_memory()
+            self._pending = None
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # every pool is zeroed (flag words 0) before anyone sends
         self.kept = mk(self.kept_layout["bytes"])
         # row indices of the leavers: [0, cap_m) downwards, [cap_m, 2 cap_m) upwards, [2 cap_m, 4 cap_m) merged
         self.holes = torch.zeros(4 * self.migrant_cap + 16, dtype=torch.int32, device=self.device)
@@ -388,6 +471,7 @@ class SlabSystem:
         if self.world == 1:
             return
         self.exchange()
+        self.sync_counts()
         seen = torch.tensor(self.last_counts, dtype=torch.int64, device=self.device)
         dist.all_reduce(seen, op=dist.ReduceOp.MAX, group=self.group)
         mig, gh = int(seen[0]), int(seen[1])
@@ -425,6 +509,7 @@ class SlabSystem:
         if "fixed" in arrays:
             self.buf["fixed"][:m] = torch.as_tensor(np.asarray(arrays["fixed"])[mine], dtype=torch.bool).to(self.device)
         self.n_own, self.n_ghost = m, 0
+        self._dev_synced = False
 
     def load_local(self, arrays: dict, gid) -> None:
         """Take rows this rank generated itself (they should lie in or next to its slab: rows that
@@ -449,6 +534,7 @@ class SlabSystem:
         self.buf["mat_id"][:m] = 0
         self.buf["fixed"][:m] = False
         self.n_own, self.n_ghost = m, 0
+        self._dev_synced = False
 
     def view(self, n: int) -> State:
         b, s = self.buf, self.static
@@ -459,12 +545,72 @@ class SlabSystem:
             clump_id=s["clump_id"][:n], bond_id=s["bond_id"][:n], mat_id=b["mat_id"][:n],
             species_id=s["species_id"][:n], fixed=b["fixed"][:n], _pos_p_rot=s["_pos_p_rot"][:n], has_clumps=False)
 
+    # ------------------------------------------------------------------ device protocol
+    @property
+    def device_protocol(self) -> bool:
+        return self.dev_state is not None and hasattr(self.engine, "pack_dev")
+
+    def _push_counts(self) -> None:
+        """Host row counts -> device words (start of the device protocol / after a host-side load)."""
+        st = torch.zeros(16, dtype=torch.int64)
+        st[0], st[1] = self.n_own, self.n_own + self.n_ghost
+        st[2:4] = self.dev_state[2:4].cpu()
+        self.dev_state.copy_(st.to(self.device))
+        self._dev_synced = True
+
+    _STATUS = {1: "a particle moved further than the halo in one step, or the box changed under the static slab layout",
+               2: "migrants / ghosts exceed the message capacities", 4: "owned + ghost rows exceed the launch bound",
+               8: "a neighbour's message did not arrive in time"}
+
+    def _digest(self, words) -> None:
+        """Look at one read-back of the device words: raise on status bits, refresh the host copies of the
+        counts and grow the launch bound when the live rows come close to it."""
+        st = int(words[3])
+        if st:
+            raise RuntimeError("slab exchange: " + "; ".join(m for b, m in self._STATUS.items() if st & b)
+                               + f" (rank {self.rank}, status {st})")
+        self.n_own, self.n_ghost = int(words[0]), int(words[1]) - int(words[0])
+        self.last_counts = (int(words[11]), int(words[12]))
+        live = int(words[1])
+        target = min(self.cap, live + live // 32 + 4096)
+        if live + live // 64 + 1024 > self.bound or target < self.bound - max(8192, self.bound // 16):
+            self.bound = target
+
+    def sync_counts(self) -> None:
+        """Blocking read of the device-side row counts and status (gather, capacity tuning, tests)."""
+        if not self.device_protocol:
+            return
+        self._pending = None
+        self._digest(self.dev_state.cpu().tolist())
+
+    def _poll(self) -> None:
+        """Every `check_every` steps: digest the previous asynchronous read-back if it has landed and start
+        the next one.  Never blocks the stream."""
+        if self._pending is not None:
+            slot, ev = self._pending
+            if not ev.query():
+                return
+            self._pending = None
+            self._digest(self._dev_host[slot].tolist())
+        if self.steps_done % self.check_every == 0:
+            slot = (self.steps_done // self.check_every) & 1
+            self._dev_host[slot].copy_(self.dev_state, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pending = (slot, ev)
+
     # ------------------------------------------------------------------ the exchange
     def exchange(self, integrate: bool = False) -> None:
         """Migration + halo exchange after the drift (one neighbour exchange, one host sync).
         ``integrate``: the engine's pack also applies the before-force kick + drift (fused step)."""
         if self.world == 1:
             self.n_ghost = 0
+            return
+        if self.device_protocol:
+            if not getattr(self, "_dev_synced", False):
+                self._push_counts()
+            self.engine.pack_dev(self, integrate=integrate)
+            self.engine.unpack_dev(self)
             return
         pack = (lambda: self.engine.pack(self, integrate=True)) if integrate else (lambda: self.engine.pack(self))
         if self._symm is not None:
@@ -523,6 +669,14 @@ class SlabSystem:
         eng = self.engine
         rows = (lambda k: k) if getattr(eng, "_bound", None) is not None else self.view
         fused = getattr(eng, "_bound", None) is not None
+        if fused and self.world > 1 and self.device_protocol:
+            if not getattr(self, "_dev_synced", False):
+                self._push_counts()
+            for _ in range(int(n)):
+                eng.step_dev(self)
+                self.steps_done += 1
+                self._poll()
+            return
         for _ in range(int(n)):
             eng.before_force(rows(self.n_own))
             self.exchange(integrate=bool(getattr(eng, "fuse_before", False)))
@@ -536,11 +690,17 @@ class SlabSystem:
     def compute_force(self) -> None:
         """collider.compute_force on the decomposed system at the current positions."""
         self.exchange()
+        if self.device_protocol and self.world > 1:
+            if getattr(self.engine, "_bound", None) is not None:
+                self.engine._hook("jdb200_celllist_compute_force", self.bound, rows="local")
+                return
+            self.sync_counts()
         self.engine.compute_force(self.view(self.n_own + self.n_ghost))
 
     # ------------------------------------------------------------------ results
     def gather(self, fields=("pos_c", "vel", "force", "torque", "ang_vel")) -> dict | None:
         """Owned rows of every rank, ordered by global particle id (all ranks get the result)."""
+        self.sync_counts()
         n = self.n_own
         local = {k: self.buf[k][:n].detach().cpu() for k in (*fields, "gid")}
         if self.world == 1:

@@ -508,6 +508,81 @@ def test_slab_pack_unpack_kernels_bit_exact(dtype, dim):
 
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("dim", [2, 3])
+def test_slab_device_protocol_loopback(dtype, dim):
+    """jdb200_slab_pack_dev / _unpack_dev (row counts, parities, "message complete" flags and status
+    bits on the device, no host in the loop) on ONE GPU that is its own lower and upper neighbour:
+    rows, counts and exchange number after two exchanges (both parities) equal the host-protocol
+    restatement the gloo tests use, byte for byte; a message that never arrives sets the timeout bit
+    and leaves the rows alone."""
+    import copy
+    import ctypes as C
+    from jaxdem_b200.slab import create_slab_system, message_views
+    from test_slab_gloo import OracleEngine
+    n = 20000
+    inp = make_inputs(n, dim, seed=19, dtype=dtype, phi=0.5)
+    F = torch.float32 if dtype == np.float32 else torch.float64
+    slab = create_slab_system(dict(pos=inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"],
+                                   mass=inp["mass"]), box_size=inp["box"], dtype=F, device="cuda")
+    G = slab.layout.n_layers
+    slab.layout.bounds = [G // 3, (2 * G) // 3]
+    slab.set_capacities(4096, 4096)
+    twin = copy.copy(slab)
+    twin.device = torch.device("cpu")
+    twin.buf = {k: v.cpu().clone() for k, v in slab.buf.items()}
+    twin.header_local = torch.zeros(8, dtype=torch.int64)
+    twin.set_capacities(4096, 4096)
+    ref = OracleEngine(twin, box=inp["box"], law="spring", lin="verlet", rot="", dt=1e-3, dtype=dtype)
+    # loopback ports: what goes down arrives "from above" and vice versa, [parity] buffers
+    nb = slab.msg_layout["bytes"]
+    pool = torch.zeros(4 * nb, dtype=torch.uint8, device="cuda")
+    base = pool.data_ptr()
+    arr = lambda f: (C.c_void_p * 2)(*[C.c_void_p(f(q)) for q in (0, 1)])
+    slab.ports = dict(send_lo=arr(lambda q: base + (2 * q + 1) * nb), send_up=arr(lambda q: base + (2 * q) * nb),
+                      recv_lo=arr(lambda q: base + (2 * q) * nb), recv_up=arr(lambda q: base + (2 * q + 1) * nb))
+    slab.dev_state = torch.zeros(16, dtype=torch.int64, device="cuda")
+    slab.bound = slab.cap
+    slab._push_counts()
+    for it in range(2):
+        slab.engine.pack_dev(slab)
+        slab.engine.unpack_dev(slab)
+        ref.pack(twin)
+        twin.recv_up.copy_(twin.send_lo)
+        twin.recv_lo.copy_(twin.send_up)
+        hl = twin.header_local
+        h = [message_views(twin.recv_lo, twin.msg_layout, F)["header"], message_views(twin.recv_up, twin.msg_layout, F)["header"]]
+        k_lo, k_up, a_lo, a_up, g_lo, g_up = int(hl[1]), int(hl[2]), int(h[0][0]), int(h[1][0]), int(h[0][1]), int(h[1][1])
+        assert min(k_lo, k_up, g_lo, g_up) > 0
+        ref.unpack(twin, (twin.n_own, a_lo, a_up, k_lo, k_up, g_lo, g_up))
+        n_old = twin.n_own
+        twin.n_own = n_old - k_lo - k_up + a_lo + a_up
+        tot = twin.n_own + k_lo + k_up + g_lo + g_up
+        torch.cuda.synchronize()
+        ds = slab.dev_state.cpu().tolist()
+        assert ds[0] == twin.n_own and ds[1] == tot and ds[2] == it + 1, (ds, twin.n_own, tot)
+        assert ds[3] == 1  # strays exist in this set-up (reported, kept as owned rows), nothing else
+        assert ds[4:11] == [n_old, a_lo, a_up, k_lo, k_up, g_lo, g_up]
+        assert ds[11] == max(k_lo, k_up, a_lo, a_up) or it == 1
+        for k in slab.buf:
+            assert torch.equal(slab.buf[k][:tot].cpu(), twin.buf[k][:tot]), (k, it)
+        # a second pair of exchanges moves the rows again: drift them a little
+        for s_ in (slab, twin):
+            s_.buf["pos_c"][:twin.n_own, -1] += 0.37
+    # the neighbour never answers: unpack without a pack -> timeout bit, rows and counts untouched
+    before = {k: v.clone() for k, v in slab.buf.items()}
+    ds0 = slab.dev_state.cpu().tolist()
+    slab.timeout_s = 0.02
+    slab.engine.unpack_dev(slab)
+    torch.cuda.synchronize()
+    ds = slab.dev_state.cpu().tolist()
+    assert ds[3] & 8 and ds[0] == ds0[0] and ds[1] == ds0[0]
+    for k in ("pos_c", "vel", "gid"):
+        assert torch.equal(slab.buf[k][:ds0[0]], before[k][:ds0[0]])
+    with pytest.raises(RuntimeError, match="did not arrive"):
+        slab.sync_counts()
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("domain", ["periodic", "reflect"])
 @pytest.mark.parametrize("K", [48, 5])
 def test_cross_neighbor_list_bit_exact(dtype, dim, domain, K):
