@@ -252,7 +252,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
             # nvidia-smi takes 0.1 - 1 s to attach to the driver, during which kernel launches of this process can
@@ -870,12 +870,15 @@ def run_cuda_slab(args, world, rank, local, dev):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = lib.jdb200_launch_count()
     barrier()
+    t_host0 = time.perf_counter()
     for a, b in ev:
         flush_l2()
         a.record()
         slab.step(1)
         b.record()
+    t_host1 = time.perf_counter()
     barrier()
+    t_host2 = time.perf_counter()
     launches = lib.jdb200_launch_count() - l0
     slab.sync_counts()  # raises if any exchange of the timed region set a status bit (stray / capacity / timeout)
     per_step = [a.elapsed_time(b) for a, b in ev]
@@ -884,6 +887,16 @@ def run_cuda_slab(args, world, rank, local, dev):
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    # per-rank view of the timed loop (diagnostic): median step, host time to enqueue the loop, wall time of the
+    # loop incl. L2 flushes — ranks are coupled only through the neighbour flags, so a rank that starts its step
+    # early waits for its neighbour INSIDE its own events
+    top = sorted(per_step)[-3:] if len(per_step) >= 3 else [0.0, 0.0, 0.0]
+    mine = torch.tensor([float(np.median(per_step)), 1e3 * (t_host1 - t_host0) / args.steps,
+                         1e3 * (t_host2 - t_host0) / args.steps, float(np.mean(per_step)), *top,
+                         float(int(np.argmax(per_step)))], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(x), 4) for x in r.tolist()] for r in per_rank]
     value = n_total * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: every rank's owned rows host -> device before the step, device -> host after it ----
@@ -955,6 +968,9 @@ def run_cuda_slab(args, world, rank, local, dev):
             "gpu_launches": int(launches),
             "parity": parity,
             "step_ms_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)},
+            "per_rank_ms": {"columns": ["median step (events)", "host enqueue per step", "wall per step incl. L2 flush",
+                                        "mean step", "3rd slowest step", "2nd slowest", "slowest", "index of the slowest"],
+                            "rows": per_rank},
             "roofline": dominant_roofline(kernels, n, peak, peak_src, cfg),
             "kernels_rank0": kernels,
             "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s",

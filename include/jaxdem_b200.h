@@ -410,9 +410,10 @@ JDB200_API int jdb200_slab_unpack(void* stream, const jdb200_slab_desc* d, const
  * BOUND (rows the kernels may touch, <= the row capacity).  msg_lo / msg_up and from_lo / from_up
  * hold one pointer per PARITY (exchange number & 1): the messages this rank writes — normally
  * straight into the neighbours' receive buffers over NVLink — and the buffers the neighbours
- * write into.  jdb200_slab_pack_dev stores the records, then the counts, then — from the block
- * that finishes last, after a system-scope fence — header word 7 = exchange number + 1 with
- * release semantics.  jdb200_slab_unpack_dev starts with one block that spins (acquire loads, at
+ * write into.  jdb200_slab_pack_dev stores the records (every storing thread fences them at system
+ * scope), then — from the block that finishes last — the counts and, behind another system-scope
+ * fence, header word 7 = exchange number + 1.  `scratch` must be zero before the first call (the
+ * calls leave their accumulators zeroed).  jdb200_slab_unpack_dev starts with one block that spins (acquire loads, at
  * most timeout_ns nanoseconds) on word 7 of both of its receive buffers, derives the counts, checks
  * them against the capacities and the bound, publishes the new row counts and repairs the rows as
  * jdb200_slab_unpack does.  Two parities are enough: a neighbour can only write the message of

@@ -360,90 +360,119 @@ struct SlabPorts {
   void* up[2];
 };
 
-template <typename F, int D>
-__global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, const uint8_t* __restrict__ cat,
-                                                           const int* __restrict__ bc, const long long* __restrict__ tot,
-                                                           SlabPorts out, void* kept, int* __restrict__ holes,
-                                                           long long* __restrict__ hdr_local, int* __restrict__ sup,
-                                                           int nsup) {
+// Row indices of the four lists, in index order: one WARP per 256-row chunk of k_slab_classify (lane l
+// owns rows 8 l .. 8 l + 7 of the chunk: one 8-byte load of the category bytes), offsets from the scanned
+// block counts.  The leavers' lists are `holes` itself ([0, cap_m) downwards, [cap_m, 2 cap_m) upwards),
+// the halo lists go to halo[0, cap_g) and halo[cap_g, 2 cap_g).  No particle row is touched here, so the
+// pass is short whatever the particle order is (the rows of a face are scattered over all chunks when
+// the particle index carries no spatial order).
+__global__ void __launch_bounds__(256) k_slab_compact(SlabGeom gm, const uint8_t* __restrict__ cat,
+                                                      const int* __restrict__ bc, int* __restrict__ holes,
+                                                      int* __restrict__ halo, int* __restrict__ sup, int nsup) {
   pdl_prologue();
-  using M = SlabMsg<F, D>;
-  __shared__ int s_w[kSlabBlock / 32][kPackLists];
   if (blockIdx.x == 0)  // the group accumulators of k_slab_classify: zero for the next exchange
     for (int t = threadIdx.x; t < nsup * 8; t += blockDim.x) sup[t] = 0;
   const long long n = slab_rows_live(gm);
+  const int lane = threadIdx.x & 31;
+  const long long chunk = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long base = chunk * kSlabBlock + lane * 8;
+  if (chunk * kSlabBlock >= n) return;
+  unsigned long long w = 0;
+  if (base + 8 <= n) {
+    w = *reinterpret_cast<const unsigned long long*>(cat + base);
+  } else {
+    for (int k = 0; k < 8; ++k)
+      if (base + k < n) w |= (unsigned long long)cat[base + k] << (8 * k);
+  }
+  // per-byte masks: bit k of m[j] <=> row base + k is in list j
+  unsigned m[kPackLists] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned c8 = (unsigned)(w >> (8 * k)) & 0xffu;
+    const bool stay = !(c8 & 12u);
+    m[0] |= ((c8 >> 2) & 1u) << k;
+    m[1] |= ((c8 >> 3) & 1u) << k;
+    m[2] |= (stay ? (c8 & 1u) : 0u) << k;
+    m[3] |= (stay ? ((c8 >> 1) & 1u) : 0u) << k;
+  }
+  if (!__any_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) != 0)) return;
+  const int4 off = *reinterpret_cast<const int4*>(bc + (size_t)chunk * 8);  // columns 0..3
+  const int off4 = bc[(size_t)chunk * 8 + 4];
+  const int start[kPackLists] = {off.y, off.z, off.w, off4};
+  int* const dst[kPackLists] = {holes, holes + gm.cap_m, halo, halo + gm.cap_g};
+  const long long cap[kPackLists] = {gm.cap_m, gm.cap_m, gm.cap_g, gm.cap_g};
+#pragma unroll
+  for (int j = 0; j < kPackLists; ++j) {
+    if (!__any_sync(0xffffffffu, m[j] != 0)) continue;
+    const int cnt = __popc(m[j]);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    long long r = start[j] + incl - cnt;
+    unsigned mm = m[j];
+    while (mm) {
+      const int k = __ffs(mm) - 1;
+      mm &= mm - 1;
+      if (r < cap[j]) dst[j][r] = (int)(base + k);
+      ++r;
+    }
+  }
+}
+
+// One thread per list entry: gather the row, store the record — consecutive threads store consecutive
+// records of a field-major section, i.e. coalesced 128-byte stores into the neighbour's memory.  The
+// block that finishes last (ticket) then writes the headers — [0] full records, [1] ghost records, [2]
+// strays seen by the sender — and, device protocol, the "message complete" flag behind a system-scope
+// fence (every storing thread fenced its own records before it took the ticket).
+template <typename F, int D>
+__global__ void __launch_bounds__(kSlabBlock) k_slab_pack(SlabGeom gm, SlabRows<F> src, const long long* __restrict__ tot,
+                                                           SlabPorts out, void* kept, const int* __restrict__ holes,
+                                                           const int* __restrict__ halo, long long* __restrict__ hdr_local,
+                                                           unsigned* __restrict__ ticket) {
+  pdl_prologue();
+  using M = SlabMsg<F, D>;
+  __shared__ bool s_last;
   const long long seq = gm.dev ? gm.dev[kDevSeq] : 0;
   const int par = (int)(seq & 1);
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const int c8 = live ? cat[i] : 0;
-  const bool stay = live && !(c8 & 12);
-  const bool fl[kPackLists] = {live && (c8 & 4) != 0, live && (c8 & 8) != 0, stay && (c8 & 1) != 0,
-                               stay && (c8 & 2) != 0};
-  const M lo(out.lo[par], gm.cap_m, gm.cap_g), up(out.up[par], gm.cap_m, gm.cap_g);
-  const bool wrote = __syncthreads_or(fl[0] | fl[1] | fl[2] | fl[3]) != 0;
-  if (wrote) {  // interior blocks have nothing to pack
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int rank[kPackLists];
-#pragma unroll
-    for (int j = 0; j < kPackLists; ++j) {
-      const unsigned m = __ballot_sync(0xffffffffu, fl[j]);
-      rank[j] = __popc(m & ((1u << lane) - 1u));
-      if (lane == 0) s_w[warp][j] = __popc(m);
-    }
-    __syncthreads();
-    const int* base = bc + (size_t)blockIdx.x * 8 + 1;
-#pragma unroll
-    for (int j = 0; j < kPackLists; ++j) {
-      int woff = 0;
-      for (int w = 0; w < warp; ++w) woff += s_w[w][j];
-      rank[j] += woff + base[j];
-    }
-    // kept: ghost records of the leavers, lower direction in records [0, cap_m), upper in [cap_m, 2 cap_m);
-    // holes: their row indices, same split
-    const M kp(kept, 0, 2 * gm.cap_m);
-    const size_t cm = (size_t)gm.cap_m, cg = (size_t)gm.cap_g;
-    if (fl[0] && rank[0] < gm.cap_m) {
-      write_full<F, D>(src, i, lo.mig_f, lo.mig_i, cm, rank[0]);
-      write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, rank[0]);
-      holes[rank[0]] = (int)i;
-    }
-    if (fl[1] && rank[1] < gm.cap_m) {
-      write_full<F, D>(src, i, up.mig_f, up.mig_i, cm, rank[1]);
-      write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, cm + rank[1]);
-      holes[gm.cap_m + rank[1]] = (int)i;
-    }
-    if (fl[2] && rank[2] < gm.cap_g) write_ghost<F, D>(src, i, lo.gh_f, lo.gh_i, cg, rank[2]);
-    if (fl[3] && rank[3] < gm.cap_g) write_ghost<F, D>(src, i, up.gh_f, up.gh_i, cg, rank[3]);
+  const M lo(out.lo[par], gm.cap_m, gm.cap_g), up(out.up[par], gm.cap_m, gm.cap_g), kp(kept, 0, 2 * gm.cap_m);
+  const size_t cm = (size_t)gm.cap_m, cg = (size_t)gm.cap_g;
+  const long long c1 = min(tot[1], gm.cap_m), c2 = min(tot[2], gm.cap_m), c3 = min(tot[3], gm.cap_g),
+                  c4 = min(tot[4], gm.cap_g);
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool wrote = true;
+  if (t < c1) {
+    const long long i = holes[t];
+    write_full<F, D>(src, i, lo.mig_f, lo.mig_i, cm, t);
+    write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, t);
+  } else if ((t -= c1) < c2) {
+    const long long i = holes[cm + t];
+    write_full<F, D>(src, i, up.mig_f, up.mig_i, cm, t);
+    write_ghost<F, D>(src, i, kp.gh_f, kp.gh_i, 2 * cm, cm + t);
+  } else if ((t -= c2) < c3) {
+    write_ghost<F, D>(src, halo[t], lo.gh_f, lo.gh_i, cg, t);
+  } else if ((t -= c3) < c4) {
+    write_ghost<F, D>(src, halo[cg + t], up.gh_f, up.gh_i, cg, t);
+  } else {
+    wrote = false;
   }
-  // headers — [0] full records, [1] ghost records, [2] strays seen by the sender — and, device protocol,
-  // the "message complete" flag: written by the block that finishes last, after every block's stores
-  // were fenced at system scope (the messages may live in a neighbour's memory)
+  if (wrote) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  *ticket = 0;
+  lo.header[0] = tot[1]; lo.header[1] = tot[3]; lo.header[2] = tot[5];
+  up.header[0] = tot[2]; up.header[1] = tot[4]; up.header[2] = tot[5];
+  hdr_local[0] = tot[0]; hdr_local[1] = tot[1]; hdr_local[2] = tot[2]; hdr_local[3] = tot[5];
   if (gm.dev) {
-    __shared__ bool s_last;
-    if (wrote) __threadfence_system();  // only blocks that stored records pay for the system-scope fence
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(gm.dev + kDevTicket), 1ULL);
-      s_last = t == (unsigned long long)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-  } else if (blockIdx.x != 0) {
-    return;
-  }
-  if (threadIdx.x == 0) {
-    lo.header[0] = tot[1]; lo.header[1] = tot[3]; lo.header[2] = tot[5];
-    up.header[0] = tot[2]; up.header[1] = tot[4]; up.header[2] = tot[5];
-    hdr_local[0] = tot[0]; hdr_local[1] = tot[1]; hdr_local[2] = tot[2]; hdr_local[3] = tot[5];
-    if (gm.dev) {
-      gm.dev[kDevTicket] = 0;
-      if (tot[1] > gm.cap_m || tot[2] > gm.cap_m || tot[3] > gm.cap_g || tot[4] > gm.cap_g)
-        gm.dev[kDevStatus] |= JDB200_SLAB_MESSAGE_FULL;  // the receiver sees the same through the counts
-      __threadfence_system();
-      st_release_sys(lo.header + kHdrFlag, seq + 1);
-      st_release_sys(up.header + kHdrFlag, seq + 1);
-    }
+    if (tot[1] > gm.cap_m || tot[2] > gm.cap_m || tot[3] > gm.cap_g || tot[4] > gm.cap_g)
+      gm.dev[kDevStatus] |= JDB200_SLAB_MESSAGE_FULL;  // the receiver sees the same through the counts
+    __threadfence_system();  // orders the counts above and (cumulatively) every block's fenced records
+    *reinterpret_cast<volatile long long*>(lo.header + kHdrFlag) = seq + 1;
+    *reinterpret_cast<volatile long long*>(up.header + kHdrFlag) = seq + 1;
   }
 }
 
@@ -624,25 +653,56 @@ static inline SlabGeom slab_geom(const jdb200_slab_desc* d, void* dev) {
   return SlabGeom{d->n, d->n_layers, d->lo_layer, d->up_layer, d->search_range, d->cap_mig, d->cap_ghost, (long long*)dev};
 }
 
+// scratch layout (jdb200_slab_scratch_bytes): category bytes | block counts | totals | group accumulators |
+// ticket | halo row lists.  The accumulators and the ticket must be zero before the first call and are
+// left zero by every call.
+struct SlabScratch {
+  uint8_t* cat;
+  int* bc;
+  long long* tot;
+  int* sup;
+  unsigned* ticket;
+  int* halo;
+  int nb, nsup;
+  size_t bytes;
+  SlabScratch(void* base, long long n, long long cap_g) {
+    nb = std::max(1, cdiv(n, kSlabBlock));
+    nsup = cdiv(nb, 32);
+    size_t o = 0;
+    cat = (uint8_t*)base;
+    o = ((size_t)nb * kSlabBlock + 255) & ~size_t(255);
+    bc = (int*)((char*)base + o);
+    o += (size_t)nb * 8 * sizeof(int);
+    tot = (long long*)((char*)base + o);
+    o += 64;
+    sup = (int*)((char*)base + o);
+    o += (size_t)nsup * 8 * sizeof(int);
+    ticket = (unsigned*)((char*)base + o);
+    o += 64;
+    halo = (int*)((char*)base + o);
+    o += (size_t)2 * cap_g * sizeof(int);
+    bytes = o + 256;
+  }
+};
+
 template <typename F, int D>
 int slab_pack(cudaStream_t s, const jdb200_slab_desc* d, const jdb200_slab_rows* rows, SlabPorts out, void* kept,
               void* holes, void* header_local, void* scratch, void* dev) {
   const SlabGeom gm = slab_geom(d, dev);
-  const int nb = std::max(1, cdiv(d->n, kSlabBlock));
-  uint8_t* cat = (uint8_t*)scratch;
-  int* bc = (int*)((char*)scratch + (((size_t)nb * kSlabBlock + 255) & ~size_t(255)));
-  long long* tot = (long long*)(bc + (size_t)nb * 8);
-  const int nsup = cdiv(nb, 32);
-  int* sup = (int*)(tot + 8);  // zero before the first call (jdb200_slab_scratch_bytes), kept zero by k_slab_pack
+  const SlabScratch sc(scratch, d->n, d->cap_ghost);
   if (d->dt)
-    JDB_LAUNCH((k_slab_classify<F, D, true>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)d->dt,
-               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc, sup);
+    JDB_LAUNCH((k_slab_classify<F, D, true>), dim3(sc.nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)d->dt,
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, sc.cat, sc.bc, sc.sup);
   else
-    JDB_LAUNCH((k_slab_classify<F, D, false>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)nullptr,
-               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, cat, bc, sup);
-  JDB_LAUNCH(k_slab_scan, dim3(cdiv(nsup, 8)), 256, s, gm, bc, (const int*)sup, tot);
-  JDB_LAUNCH((k_slab_pack<F, D>), dim3(nb), kSlabBlock, s, gm, slab_rows<F>(rows), cat, bc, tot, out, kept, (int*)holes,
-             (long long*)header_local, sup, nsup);
+    JDB_LAUNCH((k_slab_classify<F, D, false>), dim3(sc.nb), kSlabBlock, s, gm, slab_rows<F>(rows), (const F*)nullptr,
+               (const F*)d->anchor, (const F*)d->box_size, (const F*)d->cell_size, sc.cat, sc.bc, sc.sup);
+  JDB_LAUNCH(k_slab_scan, dim3(cdiv(sc.nsup, 8)), 256, s, gm, sc.bc, (const int*)sc.sup, sc.tot);
+  JDB_LAUNCH(k_slab_compact, dim3(cdiv(sc.nb, 8)), 256, s, gm, (const uint8_t*)sc.cat, (const int*)sc.bc, (int*)holes,
+             sc.halo, sc.sup, sc.nsup);
+  const long long entries = 2 * d->cap_mig + 2 * d->cap_ghost;
+  JDB_LAUNCH((k_slab_pack<F, D>), dim3(std::max(1, cdiv(entries, kSlabBlock))), kSlabBlock, s, gm, slab_rows<F>(rows),
+             (const long long*)sc.tot, out, kept, (const int*)holes, (const int*)sc.halo, (long long*)header_local,
+             sc.ticket);
   return 0;
 }
 
@@ -695,8 +755,7 @@ JDB200_API size_t jdb200_slab_kept_bytes(const jdb200_slab_desc* d) {
 
 JDB200_API size_t jdb200_slab_scratch_bytes(const jdb200_slab_desc* d) {
   if (slab_check(d)) return 0;
-  const size_t nb = (size_t)std::max(1, cdiv(d->n, kSlabBlock));
-  return ((nb * kSlabBlock + 255) & ~size_t(255)) + nb * 8 * sizeof(int) + 64 + ((nb + 31) / 32) * 8 * sizeof(int) + 256;
+  return SlabScratch(nullptr, d->n, d->cap_ghost).bytes;
 }
 
 JDB200_API size_t jdb200_slab_holes_bytes(const jdb200_slab_desc* d) {

@@ -261,10 +261,10 @@ class CudaEngine:
         if ex is None or ex["key"] != key:
             lib = L.lib()
             d = self._desc(slab, slab.cap)
-            if self._scratch is None:
-                # zero once: the kernels keep their block-group accumulators zeroed between exchanges
-                self._scratch = torch.zeros(lib.jdb200_slab_scratch_bytes(C.byref(d)), dtype=torch.uint8,
-                                            device=slab.device)
+            need = lib.jdb200_slab_scratch_bytes(C.byref(d))
+            if self._scratch is None or self._scratch.numel() < need:
+                # zero once: the kernels keep their accumulators and the block ticket zeroed between exchanges
+                self._scratch = torch.zeros(need, dtype=torch.uint8, device=slab.device)
             ex = self._ex = dict(key=key, d=d, rows=self._rows(slab.buf), lib=lib, C=C, check=L.check)
         return ex
 

@@ -12,5 +12,5 @@ python - <<'PY'
 import json
 for l in open('gpurun_out/r2_bench_c2_n2c.json'):
     if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_step'], d['step_ms_rank0'], d['parity']); print({k:round(v['us_per_step'],1) for k,v in d['kernels_rank0'].items()})
+        d=json.loads(l); print(d["value"], d["ms_per_step"], d["step_ms_rank0"], d["per_rank_ms"]); print({k:round(v['us_per_step'],1) for k,v in d['kernels_rank0'].items()})
 PY
