@@ -335,12 +335,13 @@ JDB200_API int jdb200_system_step(void* stream, const jdb200_params* p, const jd
 JDB200_API int jdb200_frame_pack(void* stream, const jdb200_params* p, const jdb200_state* st,
                                  const jdb200_system* sys, int32_t fields, void* out);
 
-/* collider.compute_force -> force_manager.apply -> linear_integrator.step_after_force in one
- * call for sphere systems (clumps == 0) with velocity Verlet and no rotation integrator: the
- * tail of _step_once (system.py:75-80) behind a point where the caller has to intervene
- * between the drift and the force evaluation (the slab exchange below).  Same arithmetic per
- * particle as the three hooks in sequence (the pair kernel's epilogue applies the manager and
- * the kick to the particle it owns).  JDB200_EINVAL for other configurations. */
+/* collider.compute_force -> force_manager.apply -> linear_integrator.step_after_force ->
+ * rotation_integrator.step_after_force in one call for sphere systems (clumps == 0) with
+ * velocity Verlet (any rotation integrator): the tail of _step_once (system.py:75-80) behind a
+ * point where the caller has to intervene between the drift and the force evaluation (the slab
+ * exchange below).  Same arithmetic per particle as the hooks in sequence (the pair kernel's
+ * epilogue applies the manager, the kick and the rotation update to the particle it owns).
+ * JDB200_EINVAL for other configurations. */
 JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_params* p, const jdb200_state* st,
                                                 const jdb200_system* sys, void* ws, size_t ws_bytes);
 

@@ -149,13 +149,18 @@ int system_step(cudaStream_t s, Ctx<F>& c, int collider, long long n_steps) {
   // epilogue, ForceManager.apply and step_after_force to the particle it owns.  Same
   // arithmetic, same order per particle as the hook-by-hook sequence; the torque store is
   // skipped on steps whose torque nothing can observe.
+  // With a rotation integrator (fused == 2) its step_before_force stays a streaming launch in front of the
+  // partition and its step_after_force joins the epilogue (the torque is then stored on every step: the next
+  // step_before_force reads it).
   const bool fused = collider == JDB200_COLLIDER_CELLLIST && !c.clumps && c.lin == JDB200_LIN_VERLET &&
-                     c.rot == JDB200_ROT_NONE && c.domain == JDB200_DOMAIN_PERIODIC && c.n > 0;
+                     c.domain == JDB200_DOMAIN_PERIODIC && c.n > 0;
   if (fused) {
-    c.fused = 1;
+    c.fused = c.rot == JDB200_ROT_NONE ? 1 : 2;
     c.tick = 1;  // the setup kernel of every step advances System.time / step_count
-    for (long long it = 0; it < n_steps && !rc; ++it)
-      rc = celllist_force<F>(s, c, 3, false, it == n_steps - 1);
+    for (long long it = 0; it < n_steps && !rc; ++it) {
+      if (c.fused == 2 && (rc = rotation_before<F>(s, c))) break;
+      rc = celllist_force<F>(s, c, 3, false, c.fused == 2 || it == n_steps - 1);
+    }
     return rc;
   }
   if (c.time || c.step_count) {  // hook-by-hook flow: one tiny launch per call
@@ -372,19 +377,19 @@ JDB200_API int jdb200_domain_apply(void* stream, const jdb200_params* p, const j
 JDB200_API int jdb200_celllist_force_step_after(void* stream, const jdb200_params* p, const jdb200_state* st,
                                                 const jdb200_system* sys, void* ws, size_t ws_bytes) {
   JDB_ENTER(true)
-  if (p->clumps || p->linear_integrator != JDB200_LIN_VERLET || p->rotation_integrator != JDB200_ROT_NONE)
-    return JDB200_EINVAL;
+  if (p->clumps || p->linear_integrator != JDB200_LIN_VERLET) return JDB200_EINVAL;
+  const int fused = p->rotation_integrator == JDB200_ROT_NONE ? 1 : 2;  // 2: + rotation step_after_force
   if (p->dtype == JDB200_F32) {
     using F = float;
     Ctx<F> c;
     make_ctx<F>(c, p, st, sys, ws);
-    c.fused = 1;
+    c.fused = fused;
     return celllist_force<F>(s, c, 4, false, true);
   } else {
     using F = double;
     Ctx<F> c;
     make_ctx<F>(c, p, st, sys, ws);
-    c.fused = 1;
+    c.fused = fused;
     return celllist_force<F>(s, c, 4, false, true);
   }
 }

@@ -8,6 +8,7 @@
 // in sorted order: a fixed summation order, no atomics => deterministic.
 #include "laws.cuh"
 #include "launch.cuh"
+#include "rot.cuh"
 
 namespace jdb {
 
@@ -428,6 +429,12 @@ __device__ __forceinline__ void fused_sphere_epilogue(const Ctx<F>& c, int b,
   if (with_torque) {
 #pragma unroll
     for (int a = 0; a < A; ++a) c.torque[gi * A + a] = ot[a];
+  }
+  // fused == 2: the rotation integrator's step_after_force on the same particle, with the torque still in
+  // registers (velocity_verlet_spiral.py:156-180 / spiral.py:104-141; callers pass with_torque = true)
+  if (c.fused == 2) {
+    if (c.rot == JDB200_ROT_VERLETSPIRAL) rotation_update<F, 1>(c, b, gi, ot);
+    else rotation_update<F, 2>(c, b, gi, ot);
   }
 }
 
@@ -996,7 +1003,7 @@ static bool launch_after4(cudaStream_t, Ctx<double>&, int) { return false; }
 template <int D, int EPI>
 static bool launch_after4(cudaStream_t s, Ctx<float>& c, int wt) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (c.n % 4 != 0 || c.n_dev || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
+  if (c.n % 4 != 0 || c.n_dev || c.fused == 2 || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
   auto go = [&]() -> int {
     JDB_LAUNCH((k_after4<D, EPI>), dim3(cdiv(c.n, 4 * 128), c.batch), 128, s, c, wt);
     return 0;

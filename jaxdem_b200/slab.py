@@ -155,8 +155,8 @@ class CudaEngine:
         ws = _call.workspace(p, slab.device)
         sy = self.system
         # collider + force manager + after-kick in ONE call when the configuration allows it
-        self._fuse_after = (sy.linear_integrator.native_kind == "verlet" and not sy.rotation_integrator.native_kind
-                            and sy.domain.native_kind == "periodic")
+        # (with a rotation integrator the fused call also applies its step_after_force)
+        self._fuse_after = sy.linear_integrator.native_kind == "verlet" and sy.domain.native_kind == "periodic"
         # ... and the before-force kick + drift inside the exchange's classify kernel
         self.fuse_before = self._fuse_after and slab.world > 1
         self._bound = dict(p=p, sv=_call.state_view(full), yv=_call.system_view(self.system), ws=ws, lib=L.lib(),
@@ -192,7 +192,10 @@ class CudaEngine:
         n = state if isinstance(state, int) else state.N
         torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
         if getattr(self, "fuse_before", False):
-            return  # done by jdb200_slab_pack (SlabSystem.step passes integrate=True)
+            # the linear part is done by jdb200_slab_pack (SlabSystem.step passes integrate=True)
+            if sy.rotation_integrator.native_kind:
+                self._hook("jdb200_rotation_step_before_force", n, ws=False)
+            return
         if sy.linear_integrator.native_kind:
             self._hook("jdb200_linear_step_before_force", n, ws=False)
         if sy.rotation_integrator.native_kind:
@@ -309,11 +312,10 @@ class CudaEngine:
         """One _step_once on the decomposed system, device protocol: no host synchronisation."""
         sy, B = self.system, slab.bound
         torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
-        if not self.fuse_before:
-            if sy.linear_integrator.native_kind:
-                self._hook("jdb200_linear_step_before_force", B, ws=False, rows="own")
-            if sy.rotation_integrator.native_kind:
-                self._hook("jdb200_rotation_step_before_force", B, ws=False, rows="own")
+        if not self.fuse_before and sy.linear_integrator.native_kind:
+            self._hook("jdb200_linear_step_before_force", B, ws=False, rows="own")
+        if sy.rotation_integrator.native_kind:
+            self._hook("jdb200_rotation_step_before_force", B, ws=False, rows="own")
         self.pack_dev(slab, integrate=self.fuse_before)
         self.unpack_dev(slab)
         if self._fuse_after:

@@ -247,6 +247,7 @@ def test_full_step_matches_oracle(dtype, cfg):
         compare_states(gst, ost, dtype, factor=4.0 * (step + 1))
         for f in ("pos_c", "vel", "force", "torque", "ang_vel", "_pos_p_rot"):  # same kernels, same order
             assert torch.equal(getattr(gst, f), getattr(hst, f)), f
+        assert torch.equal(gst.q.w, hst.q.w) and torch.equal(gst.q.xyz, hst.q.xyz)
     assert float(gsy.step_count) == 3
 
 

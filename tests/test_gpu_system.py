@@ -235,7 +235,10 @@ def test_readme_config_full_1000_steps_f64():
     assert abs(e1 - e0) < 1e-2 * abs(e0), (e0, e1)  # measured 2.4e-3: dt = 0.005 against k = 1e4 contacts
     p = gst.pos_c.cpu().numpy()
     assert np.abs(p - pos0).max() > 1.0  # the gas really evolved
-    assert (p - 0.1 >= -1e-9).all() and (p + 0.1 <= 20.0 + 1e-9).all()
+    # the drift follows domain.apply inside a step (system.py:66-74), so at the END of a step a sphere may stand
+    # in a wall by at most one drift, |v| dt; the next apply mirrors it back
+    slack = float(gst.vel.abs().max()) * 0.005 + 1e-9
+    assert (p - 0.1 >= -slack).all() and (p + 0.1 <= 20.0 + slack).all()
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -255,5 +258,7 @@ def test_one_step_elementwise_relative_error(dtype):
         want = getattr(ost, f).astype(np.float64)
         got = getattr(gst, f).cpu().numpy().astype(np.float64)
         floor = 1e-3 * np.abs(want).max()
+        if f == "ang_vel":  # the kick dt * torque / I of a cancelling contact-torque sum: its scale, not the element's
+            floor += 1e-3 * np.abs(ost.torque).max() / float(ost.inertia.min())
         bad = np.abs(got - want) > t * (np.abs(want) + floor)
         assert not bad.any(), (f, int(bad.sum()), float(np.abs(got - want).max()))
