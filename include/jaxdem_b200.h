@@ -137,6 +137,11 @@ typedef struct jdb200_state {
                          (batch == 1, dense cell table): params.n is only the launch bound; every kernel reads the
                          live count itself and leaves rows [n_rows, n) alone.  Used by the slab decomposition, whose
                          owned + ghost row count changes every step and is known on the device only. */
+  const void* order_id; /* optional (B,N) int64 on the device, or NULL: particles that share a cell are ordered by this
+                           id instead of their row index (dense cell table only).  The reference's perm is the stable
+                           sort of (hash, iota) (colliders/_partition.py:91-93); with order_id = the GLOBAL particle id
+                           a rank of the slab decomposition orders each cell exactly as the undecomposed system does,
+                           so every particle sums its contacts in the same order (bit-identical forces). */
 } jdb200_state;
 
 /* System leaves (jaxdem/system.py:123-228 and the components it holds). */

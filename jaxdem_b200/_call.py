@@ -85,6 +85,11 @@ def state_view(state) -> L.StateView:
     v.q_w = state.q.w.data_ptr()
     v.q_xyz = state.q.xyz.data_ptr()
     v.pos_p_rot = state._pos_p_rot.data_ptr()
+    oid = getattr(state, "order_id", None)  # optional (B,N) int64: in-cell order of the partition (jdb200_state.order_id)
+    if oid is not None:
+        if oid.dtype != torch.int64 or not oid.is_contiguous() or oid.device != state.pos_c.device:
+            raise RuntimeError("State.order_id must be a contiguous int64 tensor on the State's device")
+        v.order_id = oid.data_ptr()
     return v
 
 

@@ -41,7 +41,7 @@ class Params(C.Structure):
 
 
 STATE_FIELDS = ("pos_c", "pos_p", "vel", "force", "q_w", "q_xyz", "ang_vel", "torque", "inertia",
-                "rad", "mass", "clump_id", "mat_id", "bond_id", "fixed", "pos_p_rot", "n_rows")
+                "rad", "mass", "clump_id", "mat_id", "bond_id", "fixed", "pos_p_rot", "n_rows", "order_id")
 SYSTEM_FIELDS = ("dt", "box_size", "inv_box_size", "anchor", "restitution", "cell_size",
                  "neighbor_mask", "collider_overflow", "interact_same_bond_id", "gravity",
                  "external_force", "external_force_com", "external_torque", "mat_young",

@@ -738,7 +738,17 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
     c.tmp_key[off + k] = key;  // cells stay in place: the key of arrival slot k is the key of final slot k
     const int s = cs[key], e = cs[key + 1];
     int r = 0;
-    if (e - s > 1) {  // rank = members of the cell with a smaller original index
+    if (e - s > 1 && c.order_id) {  // rank = members of the cell with a smaller order id (jdb200_state.order_id)
+      const long long* oid = c.order_id + off;
+      const long long mine_id = oid[i];
+      if (sizeof(F) == 4) {
+        const int* ids = reinterpret_cast<const int*>(c.arec + 32 * off) + 4;
+        for (int kk = s; kk < e; ++kk) r += oid[ids[8 * (size_t)kk]] < mine_id;
+      } else {
+        const int2* __restrict__ tmp = c.slot_rec + off;
+        for (int kk = s; kk < e; ++kk) r += oid[tmp[kk].x] < mine_id;
+      }
+    } else if (e - s > 1) {  // rank = members of the cell with a smaller original index
       if (sizeof(F) == 4) {
         const int* ids = reinterpret_cast<const int*>(c.arec + 32 * off) + 4;
         for (int kk = s; kk < e; ++kk) r += ids[8 * (size_t)kk] < i;

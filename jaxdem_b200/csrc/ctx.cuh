@@ -79,6 +79,7 @@ struct Ctx {
   // ---- ragged rows (slab decomposition without host synchronisation) ----
   const long long* n_dev;      // jdb200_state.n_rows or NULL: the LIVE row count, read on the device by every kernel
                                // (n above is then the launch bound: grids cover it, rows >= *n_dev are not touched)
+  const long long* order_id;   // jdb200_state.order_id or NULL: in-cell order by this id instead of the row index
   // ---- MultiCellList (loose-grid AABB pruning, pair.cu) ----
   int prune;                   // 1: every stencil cell is tested against its expandable AABB before its run is walked
   const F* prune_cut;          // [B] or NULL: neighbour-list builds prune with a query box of +-cutoff around the point
@@ -186,6 +187,7 @@ inline int make_ctx(Ctx<F>& c, const jdb200_params* p, const jdb200_state* st,
     c.clump_id = (I*)st->clump_id; c.mat_id = (I*)st->mat_id; c.bond_id = (I*)st->bond_id;
     c.fixed = (uint8_t*)st->fixed;
     c.n_dev = (const long long*)st->n_rows;
+    c.order_id = (const long long*)st->order_id;
   }
   if (sys) {
     c.dt = (F*)sys->dt; c.box = (F*)sys->box_size; c.inv_box = (F*)sys->inv_box_size;

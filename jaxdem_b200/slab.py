@@ -540,12 +540,16 @@ class SlabSystem:
 
     def view(self, n: int) -> State:
         b, s = self.buf, self.static
-        return State(
+        st = State(
             pos_c=b["pos_c"][:n], pos_p=s["pos_p"][:n], vel=b["vel"][:n], force=b["force"][:n],
             q=Quaternion(b["q_w"][:n], b["q_xyz"][:n]), ang_vel=b["ang_vel"][:n], torque=b["torque"][:n],
             rad=b["rad"][:n], _rad=b["rad"][:n], volume=b["rad"][:n], mass=b["mass"][:n], inertia=b["inertia"][:n],
             clump_id=s["clump_id"][:n], bond_id=s["bond_id"][:n], mat_id=b["mat_id"][:n],
             species_id=s["species_id"][:n], fixed=b["fixed"][:n], _pos_p_rot=s["_pos_p_rot"][:n], has_clumps=False)
+        # particles that share a cell are ordered by GLOBAL id: every rank orders a cell exactly as the undecomposed
+        # system does (stable sort of (hash, iota), colliders/_partition.py:91-93), so contact sums keep their order
+        st.order_id = b["gid"][:n]
+        return st
 
     # ------------------------------------------------------------------ device protocol
     @property

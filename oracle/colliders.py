@@ -168,10 +168,12 @@ def grid_params(box_size, cell_size, periodic, idtype):
     return gd, strides, cell_size, overflow
 
 
-def get_spatial_partition(pos, system, cell_size, neighbor_mask, idtype):
+def get_spatial_partition(pos, system, cell_size, neighbor_mask, idtype, order_id=None):
     """_get_spatial_partition (cell_list.py:35-87).
 
-    Returns (perm, sorted_hash, neighbor_cell_hashes (N, M), hash_overflow)."""
+    Returns (perm, sorted_hash, neighbor_cell_hashes (N, M), hash_overflow).  ``order_id`` (not in the
+    reference): the iota of the stable sort, for a State whose rows are a subset / permutation of a larger
+    system's particles (slab decomposition: the global particle ids)."""
     dom = system.domain
     F = pos.dtype
     gd, strides, cs_eff, overflow = grid_params(dom.box_size, cell_size, dom.periodic, idtype)
@@ -187,7 +189,10 @@ def get_spatial_partition(pos, system, cell_size, neighbor_mask, idtype):
             coords = float_to_int(np.floor((pos - dom.anchor) / cell_size), idtype)
         hashes = (coords * strides).sum(axis=-1, dtype=idtype)  # wrapping integer dot
         N = pos.shape[0]
-        perm = np.argsort(hashes, kind="stable").astype(idtype)  # lax.sort(num_keys=1) is stable
+        if order_id is None:
+            perm = np.argsort(hashes, kind="stable").astype(idtype)  # lax.sort(num_keys=1) is stable
+        else:
+            perm = np.lexsort((np.asarray(order_id), hashes)).astype(idtype)  # (hash, global iota)
         sorted_hash = hashes[perm]
 
         ncoords = coords[:, None, :] + neighbor_mask[None, :, :]
@@ -218,7 +223,8 @@ def dedup_stencil_hashes(nh: np.ndarray) -> np.ndarray:
 def _partition_for(state, system, cell_size):
     col = system.collider
     pos = state.pos
-    perm, sh, nh, ovf, hashes = get_spatial_partition(pos, system, cell_size, col.neighbor_mask, state.idtype)
+    perm, sh, nh, ovf, hashes = get_spatial_partition(pos, system, cell_size, col.neighbor_mask, state.idtype,
+                                                      order_id=getattr(state, "order_id", None))
     if system.domain.periodic:
         nh = dedup_stencil_hashes(nh)
     return pos, perm, sh, nh, ovf

@@ -509,6 +509,36 @@ def test_slab_pack_unpack_kernels_bit_exact(dtype, dim):
 
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("dim", [2, 3])
+def test_partition_order_id_bit_exact(dtype, dim):
+    """jdb200_state.order_id: particles that share a cell are ordered by the given id instead of the row index
+    — the stable sort of (hash, iota) of a system whose particle index is that id (colliders/_partition.py:91-93).
+    perm and sorted hashes bit for bit against the oracle's lexsort; forces equal the ones of the same particles
+    laid out in id order (same cells, same in-cell order => same contact-sum order => bitwise)."""
+    inp = make_inputs(6000, dim, seed=31, dtype=dtype, phi=0.7, poly=1.6)  # dense: many multi-occupancy cells
+    ost, osy = build_oracle(inp, dtype=dtype)
+    gst, gsy = build_gpu(inp, dtype=dtype)
+    n = gst.N
+    ids = np.random.default_rng(5).permutation(n).astype(np.int64) * 3 + 7
+    gst.order_id = torch.as_tensor(ids, device="cuda")
+    ost.order_id = ids
+    perm, sh, _, dense = gsy.collider.partition(gst, gsy)
+    assert bool(dense)
+    want_perm, want_sh, _, _, _ = ocol.get_spatial_partition(ost.pos, osy, osy.collider.cell_size,
+                                                              osy.collider.neighbor_mask, ost.idtype, order_id=ids)
+    assert np.array_equal(perm.cpu().numpy(), want_perm) and np.array_equal(sh.cpu().numpy(), want_sh)
+    counts = np.bincount(want_sh - want_sh.min())
+    assert counts.max() >= 3  # the in-cell order really matters here
+    gsy.collider.compute_force(gst, gsy)
+    # the same particles with rows in id order and no order_id
+    order = np.argsort(ids)
+    inp2 = {k: (v[order] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in inp.items()}
+    gst2, gsy2 = build_gpu(inp2, dtype=dtype)
+    gsy2.collider.compute_force(gst2, gsy2)
+    assert torch.equal(gst.force[torch.as_tensor(order, device="cuda")], gst2.force)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim", [2, 3])
 def test_slab_device_protocol_loopback(dtype, dim):
     """jdb200_slab_pack_dev / _unpack_dev (row counts, parities, "message complete" flags and status
     bits on the device, no host in the loop) on ONE GPU that is its own lower and upper neighbour:
