@@ -14,7 +14,7 @@ from typing import Any
 
 import torch
 
-from . import _call
+from . import _call, pair_laws
 from .factory import Factory
 from .state import State, int_dtype_for
 
@@ -115,9 +115,29 @@ class ReflectDomain(Domain):
 # name; its arithmetic lives in csrc/laws.cuh.
 # ---------------------------------------------------------------------------
 class ForceModel(Factory):
+    """``force(i, j, pos, state, system) -> (force, torque)`` on i due to j and ``energy(i, j, pos, state,
+    system)`` are the reference's per-pair contract (forces/__init__.py:55-150), here in torch
+    (jaxdem_b200/pair_laws.py) for code that calls a law directly; the colliders evaluate the same formulas
+    inside their CUDA kernels."""
     native_kind = "spring"
     required_material_properties: tuple = ()
     requires_history = False
+
+    @staticmethod
+    def force(i, j, pos, state, system):
+        raise NotImplementedError
+
+    @staticmethod
+    def energy(i, j, pos, state, system):
+        raise NotImplementedError
+
+    def init_history(self, shape):
+        return None
+
+    @staticmethod
+    def force_and_history(i, j, pos, state, system, history):
+        f, t = system.force_model.force(i, j, pos, state, system)
+        return f, t, history
 
 
 @ForceModel.register("spring")
@@ -125,6 +145,8 @@ class SpringForce(ForceModel):
     """reference jaxdem/forces/spring.py:69-147."""
     native_kind = "spring"
     required_material_properties = ("young_eff",)
+    force = staticmethod(pair_laws.spring_force)
+    energy = staticmethod(pair_laws.spring_energy)
 
 
 @ForceModel.register("hertz")
@@ -132,6 +154,8 @@ class HertzianForce(ForceModel):
     """reference jaxdem/forces/hertz.py:69-162."""
     native_kind = "hertz"
     required_material_properties = ("young", "poisson")
+    force = staticmethod(pair_laws.hertz_force)
+    energy = staticmethod(pair_laws.hertz_energy)
 
 
 @ForceModel.register("cundallstrack")
@@ -139,6 +163,8 @@ class CundallStrackForce(ForceModel):
     """reference jaxdem/forces/cundall_strack.py:99-235."""
     native_kind = "cundallstrack"
     required_material_properties = ("young", "poisson", "e", "mu", "mu_r")
+    force = staticmethod(pair_laws.cundallstrack_force)
+    energy = staticmethod(pair_laws.cundallstrack_energy)
 
 
 # ---------------------------------------------------------------------------

@@ -186,3 +186,60 @@ def test_params_argument_errors_of_new_fields():
     assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
     p.key_window_lo[1], p.key_window_len[0] = 4096, -1
     assert lib.jdb200_workspace_bytes(ctypes.byref(p)) == 0
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("law", ["spring", "hertz", "cundallstrack"])
+def test_force_model_pair_contract_matches_oracle(dim, law):
+    """ForceModel.force / energy (the reference's per-pair contract, forces/__init__.py:55-150) in torch
+    (jaxdem_b200/pair_laws.py; pure host-side code, runs on CPU tensors) against the oracle's restatement of the
+    same laws on random pairs — periodic minimum image, two materials, self pairs give zero."""
+    import jaxdem_b200 as jd
+    from helpers import MATS, make_inputs
+    import oracle
+    from oracle import forces as oforces
+    inp = make_inputs(300, dim, seed=5, dtype=np.float64, phi=0.7, nmat=2)
+    ost = oracle.create_state(inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"], mass=inp["mass"],
+                              mat_id=inp["mat_id"], dtype=np.float64)
+    osy = oracle.create_system(ost, domain_type="periodic", domain_kw=dict(box_size=inp["box"]), force_model_type=law,
+                               mat_table=oracle.make_material_table(MATS[:2], "harmonic"))
+    st = jd.State.create(inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"], mass=inp["mass"],
+                         mat_id=inp["mat_id"], dtype=torch.float64, device="cpu")
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **m) for m in MATS[:2]],
+                                         matcher=jd.MaterialMatchmaker.create("harmonic"))
+    sy = jd.System.create(st.shape, domain_type="periodic", domain_kw=dict(box_size=inp["box"]), force_model_type=law,
+                          mat_table=mt, collider_type="naive", dtype=torch.float64, device="cpu")
+    rng = np.random.default_rng(1)
+    # pairs that really touch (nearest periodic neighbours) plus random ones and a few self pairs
+    d = inp["pos"][:, None, :] - inp["pos"][None, :, :]
+    d -= inp["box"] * np.round(d / inp["box"])
+    near = np.argsort((d**2).sum(-1), axis=1)[:, 1]
+    i = np.concatenate([np.arange(300), rng.integers(0, 300, 200), np.arange(5)])
+    j = np.concatenate([near, rng.integers(0, 300, 200), np.arange(5)])
+    ti, tj = torch.as_tensor(i), torch.as_tensor(j)
+    f, t = sy.force_model.force(ti, tj, st.pos, st, sy)
+    e = sy.force_model.energy(ti, tj, st.pos, st, sy)
+    wf, wt = getattr(oforces, law + "_force")(i, j, ost.pos, ost, osy)
+    we = getattr(oforces, law + "_energy")(i, j, ost.pos, ost, osy)
+    assert np.abs(wf).max() > 0 and (law != "cundallstrack" or np.abs(wt).max() > 0)
+    for got, want in ((f, wf), (t, wt), (e, we)):
+        want = np.asarray(want)
+        assert got.shape == want.shape
+        assert np.abs(got.numpy() - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
+    assert float(f[-5:].abs().max()) == 0.0 and float(e[-5:].abs().max()) == 0.0
+
+
+def test_force_model_pair_reference_pin():
+    """The reference's own pin of the per-pair call (tests/test_clump_pair_friction.py:167-186): two unit spheres
+    across the periodic boundary of a box of 10, centres 0.3 and 9.2 on the diagonal plane."""
+    import jaxdem_b200 as jd
+    pos = np.array([[0.5, 0.5], [9.7, 9.7]])
+    st = jd.State.create(pos, rad=np.array([1.0, 1.0]), dtype=torch.float64, device="cpu")
+    sy = jd.System.create(st.shape, domain_type="periodic", domain_kw=dict(box_size=[10.0, 10.0]),
+                          collider_type="naive", dtype=torch.float64, device="cpu")
+    f, t = sy.force_model.force(0, 1, st.pos, st, sy)
+    rij = np.array([0.8, 0.8])
+    r = np.linalg.norm(rij)
+    k = float(sy.mat_table.young_eff[0, 0])
+    assert np.allclose(f.numpy(), k * (2.0 - r) * rij / r, rtol=1e-13)
+    assert t.shape == (1,) and float(t.abs().max()) == 0.0
