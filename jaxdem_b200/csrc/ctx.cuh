@@ -14,6 +14,7 @@ struct Ctx {
   int batch, dim, A, periodic, domain, law, M, W, nmat, K, grid_mode, clumps, lin, rot;
   long long win_lo[2], win_len[2];  // dense cell-table windows in use (jdb200_params.key_window_*; len 0: whole table)
   int promises;  // jdb200_params.promises (JDB200_PROMISE_*)
+  int want_energy;  // minimiser loop: the row kernel also accumulates each particle's share of the pair energy (sforce.w)
   int fused;  // fused sphere step driver (abi.cu system_step): hash kernel integrates, pair kernel finishes the step
   // state (in place)
   F *pos_c, *pos_p, *vel, *force, *q_w, *q_xyz, *ang_vel, *torque, *inertia, *rad, *mass, *pos_p_rot;

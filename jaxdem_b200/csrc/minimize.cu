@@ -289,8 +289,12 @@ template <typename F>
 static int fire_eval(cudaStream_t s, Ctx<F>& c, int collider) {
   int rc = 0;
   if (collider == JDB200_COLLIDER_CELLLIST || collider == JDB200_COLLIDER_MULTICELLLIST) {
+    // default stencil on a dense table: the row kernel walks every pair once for force AND energy (each particle's
+    // share lands in sforce.w); whatever it does not serve keeps the separate energy walk
+    c.want_energy = (c.max_cells > 0 && c.M == (c.dim == 3 ? 27 : 9) && !c.prune && c.reduce_blocks == cdiv(c.n, kReduceBlock)) ? 1 : 0;
     if ((rc = celllist_force<F>(s, c, 0, false, true))) return rc;
     if ((rc = celllist_energy<F>(s, c, c.min_pe, true))) return rc;  // same positions: the partition is reused
+    c.want_energy = 0;
   } else if (collider == JDB200_COLLIDER_NAIVE) {
     if ((rc = naive_force<F>(s, c))) return rc;
     if ((rc = naive_energy<F>(s, c, c.min_pe))) return rc;

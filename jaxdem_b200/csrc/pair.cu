@@ -261,6 +261,7 @@ struct ForceVis {
   bool interact;
   F hb[3];  // |rij| below this => the minimum-image term is exactly zero
   F f[3], t[3];
+  F e = F(0);  // c.want_energy: this particle's share 0.5 * sum_j E_ij (non-overlapping pairs carry exactly 0)
 
   __device__ __forceinline__ void one(int kj, const Vec4<F>& q) {
     constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
@@ -299,6 +300,7 @@ struct ForceVis {
     pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
     f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
     if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+    if (c.want_energy) e += F(0.5) * pair_energy_rij<F, LAW>(lc, a, bj, rij);
   }
   // two-segment iterator: [s1, e1) then [s2, e2)
   __device__ __forceinline__ void run(int s1, int e1, int s2, int e2) {
@@ -630,7 +632,7 @@ struct RowTest<float, D, PERIODIC, kU> {
 template <typename F, int LAW, int D, bool PERIODIC, bool SIMPLE>
 __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
                                                const GridInfo<typename RT<F>::I>& g, unsigned sbase, F* f,
-                                               F* t) {
+                                               F* t, F* en) {
   using T = RT<F>;
   using Cfg = RowsCfg<D>;
   constexpr bool CS = LAW == JDB200_LAW_CUNDALLSTRACK;
@@ -789,6 +791,7 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
   // ---- C: the force law on the hits ----
   f[0] = f[1] = f[2] = F(0);
   t[0] = t[1] = t[2] = F(0);
+  F e_acc = F(0);
   auto contact = [&](int kcur) {
     const Vec4<F> qc = ldg_vec4(sp + kcur);
     if (SIMPLE) {
@@ -819,6 +822,8 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
     pair_force_rij<F, LAW>(lc, a, bj, rij, ff, tt);
     f[0] += ff[0]; f[1] += ff[1]; f[2] += ff[2];
     if (CS) { t[0] += tt[0]; t[1] += tt[1]; t[2] += tt[2]; }
+    // minimiser loop: the pair energy from the same displacement (0.5 per side, _partition.py:39-51)
+    if (c.want_energy) e_acc += F(0.5) * pair_energy_rij<F, LAW>(lc, a, bj, rij);
   };
   if (!ovf) {
     int e = 0;
@@ -858,7 +863,9 @@ __device__ __forceinline__ void pair_rows_body(const Ctx<F>& c, int b, int k,
       f[d] = vis.f[d];
       t[d] = vis.t[d];
     }
+    e_acc = vis.e;
   }
+  *en = e_acc;
 }
 
 // The systems the row kernel cannot serve (sorted fallback, periodic de-dup, particles outside the grid)
@@ -900,12 +907,12 @@ __global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW ==
   // the body uses warp-wide votes: lanes past the end of the array redo the last particle and store nothing
   const long long k = live ? k0 : n_live - 1;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-  F f[3], t[3];
-  if (!c.clumps && !g.any_bond) pair_rows_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, sbase, f, t);
-  else pair_rows_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, sbase, f, t);
+  F f[3], t[3], en;
+  if (!c.clumps && !g.any_bond) pair_rows_body<F, LAW, D, PERIODIC, true>(c, b, (int)k, g, sbase, f, t, &en);
+  else pair_rows_body<F, LAW, D, PERIODIC, false>(c, b, (int)k, g, sbase, f, t, &en);
   if (!live) return;
   const size_t off = (size_t)b * c.n;
-  c.sforce[off + k] = Vec4<F>{f[0], f[1], f[2], F(0)};
+  c.sforce[off + k] = Vec4<F>{f[0], f[1], f[2], en};  // .w: the particle's energy share (c.want_energy), else 0
   if (LAW == JDB200_LAW_CUNDALLSTRACK) c.storque[off + k] = Vec4<F>{t[0], t[1], t[2], F(0)};
 }
 
@@ -1084,11 +1091,25 @@ __device__ __forceinline__ F block_sum_256(F v) {  // fixed tree order => determ
   return sm[0];
 }
 
+// Minimiser loop (c.want_energy): the systems the row kernel served already hold every particle's energy share in
+// sforce.w — block sums of those, in the partial layout of k_pair_energy (which then skips these systems).
+template <typename F>
+__global__ void __launch_bounds__(kReduceBlock) k_rows_energy_partial(Ctx<F> c) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  if (!rows_ok(c, c.gi[b])) return;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const F e = k < c.n ? c.sforce[(size_t)b * c.n + k].w : F(0);
+  const F tot = block_sum_256(e);
+  if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blockIdx.x] = tot;
+}
+
 template <typename F, int LAW>
 __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
+  if (c.want_energy && rows_ok(c, c.gi[b])) return;  // summed from the row kernel's per-particle shares
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t off = (size_t)b * c.n;
   F e = F(0);
@@ -1478,6 +1499,7 @@ int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy, bool reuse) {
   if (rc) return rc;
   if (c.prune && !reuse && (rc = cell_aabbs<F>(s, c, 1))) return rc;
   const dim3 grid(c.reduce_blocks, c.batch);
+  if (c.want_energy) JDB_LAUNCH(k_rows_energy_partial<F>, grid, kReduceBlock, s, c);
   JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
   JDB_LAUNCH(k_final_sum<F>, dim3(c.batch), kReduceBlock, s, c.partial, c.reduce_blocks, energy);
   return 0;

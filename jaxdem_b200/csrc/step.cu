@@ -158,22 +158,35 @@ __device__ __forceinline__ void fm_totals(const Ctx<F>& c, int b, size_t gi, F c
   using T = RT<F>;
   const int D = c.dim, A = c.A;
   const F mc = T::div(c.mass[gi], count);
+  // streams the caller vouches for (jdb200_params.promises) are not read: clean external buffers and
+  // pos_p == 0 contribute exact zeros to the same expressions
+  const bool ext = !(c.promises & JDB200_PROMISE_NO_EXT), ppr = !(c.promises & JDB200_PROMISE_NO_POS_P);
   F fp[3] = {0, 0, 0}, r[3] = {0, 0, 0};
   for (int d = 0; d < D; ++d) {
-    fp[d] = c.ext_force[gi * D + d];
-    r[d] = c.pos_p_rot[gi * D + d];
-    const F fcom = T::add(c.ext_force_com[gi * D + d], T::mul(c.gravity[b * D + d], mc));
+    if (ext) fp[d] = c.ext_force[gi * D + d];
+    if (ppr) r[d] = c.pos_p_rot[gi * D + d];
+    const F fcom = T::add(ext ? c.ext_force_com[gi * D + d] : F(0), T::mul(c.gravity[b * D + d], mc));
     Ft[d] = T::add(T::add(c.force[gi * D + d], fp[d]), fcom);
   }
   if (D == 3) {
     const V3<F> cr = xcross(V3<F>{r[0], r[1], r[2]}, V3<F>{fp[0], fp[1], fp[2]});
     const F crv[3] = {cr.x, cr.y, cr.z};
     for (int a = 0; a < 3; ++a)
-      Tt[a] = T::add(c.torque[gi * 3 + a], T::add(c.ext_torque[gi * 3 + a], crv[a]));
+      Tt[a] = T::add(c.torque[gi * 3 + a], T::add(ext ? c.ext_torque[gi * 3 + a] : F(0), crv[a]));
   } else {
     const F cr = T::sub(T::mul(r[0], fp[1]), T::mul(r[1], fp[0]));
-    Tt[0] = T::add(c.torque[gi * A], T::add(c.ext_torque[gi * A], cr));
+    Tt[0] = T::add(c.torque[gi * A], T::add(ext ? c.ext_torque[gi * A] : F(0), cr));
   }
+}
+// the external buffers are cleared by ForceManager.apply (force_manager.py:419-423); already clean under the promise
+template <typename F>
+__device__ __forceinline__ void fm_clear_ext(const Ctx<F>& c, size_t gi) {
+  if (c.promises & JDB200_PROMISE_NO_EXT) return;
+  for (int d = 0; d < c.dim; ++d) {
+    c.ext_force[gi * c.dim + d] = F(0);
+    c.ext_force_com[gi * c.dim + d] = F(0);
+  }
+  for (int a = 0; a < c.A; ++a) c.ext_torque[gi * c.A + a] = F(0);
 }
 
 template <typename F>
@@ -186,15 +199,9 @@ __global__ void __launch_bounds__(256) k_fm_spheres(Ctx<F> c) {
   const size_t gi = (size_t)b * c.n + i;
   F Ft[3], Tt[3];
   fm_totals(c, b, gi, F(1), Ft, Tt);
-  for (int d = 0; d < c.dim; ++d) {
-    c.force[gi * c.dim + d] = Ft[d];
-    c.ext_force[gi * c.dim + d] = F(0);
-    c.ext_force_com[gi * c.dim + d] = F(0);
-  }
-  for (int a = 0; a < c.A; ++a) {
-    c.torque[gi * c.A + a] = Tt[a];
-    c.ext_torque[gi * c.A + a] = F(0);
-  }
+  for (int d = 0; d < c.dim; ++d) c.force[gi * c.dim + d] = Ft[d];
+  for (int a = 0; a < c.A; ++a) c.torque[gi * c.A + a] = Tt[a];
+  fm_clear_ext(c, gi);
 }
 
 template <typename F>
@@ -227,15 +234,9 @@ __global__ void __launch_bounds__(256) k_fm_reduce(Ctx<F> c, ClumpCsr<F> csr) {
     const F* o = c.segf + (off + csr.members[off + k]) * 8;
     for (int q = 0; q < 6; ++q) acc[q] = T::add(acc[q], o[q]);
   }
-  for (int d = 0; d < c.dim; ++d) {
-    c.force[gi * c.dim + d] = acc[d];
-    c.ext_force[gi * c.dim + d] = F(0);
-    c.ext_force_com[gi * c.dim + d] = F(0);
-  }
-  for (int a = 0; a < c.A; ++a) {
-    c.torque[gi * c.A + a] = acc[3 + a];
-    c.ext_torque[gi * c.A + a] = F(0);
-  }
+  for (int d = 0; d < c.dim; ++d) c.force[gi * c.dim + d] = acc[d];
+  for (int a = 0; a < c.A; ++a) c.torque[gi * c.A + a] = acc[3 + a];
+  fm_clear_ext(c, gi);
 }
 
 // ForceManager.compute_potential_energy (force_manager.py:427-479), gravity part: -sum(dot(g, pos_c) * mass / count)
