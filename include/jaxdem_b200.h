@@ -71,8 +71,11 @@ enum { JDB200_COLLIDER_NONE = 0, JDB200_COLLIDER_CELLLIST = 1, JDB200_COLLIDER_N
 /* cell-table strategy.  AUTO picks, per system and per call, ON THE DEVICE:
  * DENSE (counting sort into a dense cell table) when every cell hash lies in
  * [0, max_cells) and no cell holds more than JDB200_DENSE_MAX_OCC particles,
- * else SORTED (stable LSD radix sort + binary search; any hash values).
- * Both produce bit-identical perm / sorted hashes / neighbour lists. */
+ * else — force / energy / neighbour-list calls on a grid with fewer than 2^31 cells — the same
+ * counting sort into a HASHED table (row = hash of the cell key, rows sorted by (key, index),
+ * look-ups filter by the exact key), else SORTED (stable LSD radix sort + binary search; any
+ * hash values).  All produce identical pair sets and neighbour lists; perm / sorted hashes
+ * come from DENSE or SORTED and are bit-identical. */
 enum { JDB200_GRID_AUTO = 0, JDB200_GRID_DENSE = 1, JDB200_GRID_SORTED = 2 };
 #define JDB200_DENSE_MAX_OCC 64
 
@@ -183,7 +186,11 @@ JDB200_API size_t jdb200_workspace_bytes(const jdb200_params* p);
  *   sorted_hash (B,N) I   sorted cell hashes
  *   nbr_hash    (B,N,M) I neighbour-cell hashes after the periodic de-dup
  *                         (_dedup_stencil_hashes, cell_list.py:90-96)
- *   used_dense  (B,) uint8  which cell-table strategy ran */
+ *   used_dense  (B,) uint8  which cell-table strategy ran: 0 sorted keys + binary search, 1 dense
+ *                         table, 2 hashed table (a grid with more cells than max_cells: the table is
+ *                         addressed by a hash of the cell key, rows sorted by (key, index), look-ups
+ *                         filter by the exact key — same pair sets, no sort; never chosen when perm or
+ *                         sorted_hash are requested, those need the global order) */
 JDB200_API int jdb200_celllist_partition(void* stream, const jdb200_params* p, const jdb200_state* st,
                               const jdb200_system* sys, void* ws, size_t ws_bytes, void* perm,
                               void* sorted_hash, void* nbr_hash, void* used_dense);

@@ -335,6 +335,17 @@ class DynamicCellList(Collider):
         return perm, sh, nh, dense
 
 
+    @staticmethod
+    def table_strategy(state, system):
+        """How force / energy / neighbour-list calls would address the cells of this State right now:
+        0 = sorted keys + binary search (radix sort), 1 = dense cell table, 2 = hashed cell table (grid larger than
+        the table; csrc/common.cuh GridInfo.hashed).  Per system of a batch."""
+        lead = state.pos_c.shape[:-2]
+        out = torch.zeros(lead, dtype=torch.uint8, device=state.device)
+        _call.call("jdb200_celllist_partition", state, system, None, None, None, out)
+        return out
+
+
 Collider.register("b200celllist")(DynamicCellList)
 
 

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_export_partition(Ctx<F> c, typename RT<
   const GridInfo<I> g = c.gi[b];
   if (perm) perm[off + k] = (I)c.perm[off + k];
   if (sorted_hash) sorted_hash[off + k] = c.skey[off + k];
-  if (k == 0 && used_dense) used_dense[b] = (uint8_t)(g.dense && !g.dense_fail);
+  if (k == 0 && used_dense) used_dense[b] = (uint8_t)((g.dense && !g.dense_fail) ? (g.hashed ? 2 : 1) : 0);
   if (nbr_hash) {
     // row k here is ORIGINAL particle k (the reference builds the table from unsorted coords)
     const F* pc = c.pos_c + (off + k) * c.dim;
@@ -97,7 +97,7 @@ template <typename F>
 int partition_entry(cudaStream_t s, Ctx<F>& c, void* perm, void* sorted_hash, void* nbr_hash,
                     void* used_dense) {
   using I = typename RT<F>::I;
-  c.want_skey = 1;
+  c.want_skey = (perm || sorted_hash) ? 1 : 0;  // the sorted outputs need the globally sorted order (never the hashed table)
   int rc = build_partition<F>(s, c, nullptr, 0, false);
   if (rc || c.n == 0) return rc;
   JDB_LAUNCH(k_export_partition<F>, dim3(cdiv(c.n, 256), c.batch), 256, s, c, (I*)perm, (I*)sorted_hash,

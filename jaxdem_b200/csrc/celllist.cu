@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
     return;
   }
   __shared__ I s_gd[3], s_stride[3];
-  __shared__ int s_ovf, s_dense;
+  __shared__ int s_ovf, s_dense, s_hashed, s_hshift;
   __shared__ long long s_bound;
   if (threadIdx.x == 0) {
     const F cs = cell_size_override ? cell_size_override[b] : c.cell_size[b];
@@ -41,7 +41,21 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
       bound = 1;
       for (int d = 0; d < c.dim; ++d) bound *= (double)s_gd[d];
     }
-    const bool dense = c.max_cells > 0 && !s_ovf && bound <= (double)c.max_cells;
+    bool dense = c.max_cells > 0 && !s_ovf && bound <= (double)c.max_cells;
+    s_hashed = 0;
+    s_hshift = 0;
+    // a grid with more cells than the table has rows (dilute systems, the reference's own benchmark box): the
+    // table is addressed by a hash of the cell key instead of falling back to the radix sort.  Not when the
+    // caller wants the globally sorted permutation (partition export, MultiCellList AABB runs) or key windows.
+    if (!dense && c.max_cells >= 4096 && !s_ovf && bound < 2147483647.0 && c.grid_mode == JDB200_GRID_AUTO &&
+        !c.want_skey && !c.prune && c.win_len[0] == 0) {
+      int bits = 12;
+      while (bits < 30 && (2ll << bits) <= c.max_cells) ++bits;  // rows = 2^bits <= max_cells
+      s_hashed = 1;
+      s_hshift = 32 - bits;
+      dense = true;
+      bound = (double)(1ll << bits);
+    }
     s_dense = dense;
     s_bound = dense ? (long long)bound : 0;
   }
@@ -126,6 +140,8 @@ __global__ void __launch_bounds__(256) k_setup(Ctx<F> c, const F* __restrict__ c
       g.stride[d] = s_stride[d];
     }
     g.bound = s_bound;
+    g.hashed = s_hashed;
+    g.hshift = s_hshift;
     g.hash_overflow = s_ovf;
     g.need_dedup = dedup;
     g.dense = s_dense;
@@ -252,14 +268,15 @@ __global__ void __launch_bounds__(256) k_hash(Ctx<F> c, const F* __restrict__ ce
     c.key[gidx] = key;
     c.urec[gidx] = Vec4<F>{p[0], p[1], p[2], rad};
     if (g.dense) {
-      bool in_table = key >= 0 && (long long)key < g.bound;
+      // hashed table: any key that fits the 32-bit records (keys of particles far outside a non-periodic grid may not)
+      bool in_table = g.hashed ? (long long)key == (long long)(int)key : (key >= 0 && (long long)key < g.bound);
       if (in_table && c.win_len[0] > 0) {
         const long long k = (long long)key;
         in_table = (k >= c.win_lo[0] && k < c.win_lo[0] + c.win_len[0]) ||
                    (k >= c.win_lo[1] && k < c.win_lo[1] + c.win_len[1]);
       }
       if (in_table) {
-        c.rank[gidx] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + key, 1);
+        c.rank[gidx] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + table_row(g, (long long)key), 1);
       } else {
         c.gi[b].dense_fail = 1;  // hash outside the dense table: the sorted fallback takes over
       }
@@ -400,13 +417,13 @@ __global__ void __launch_bounds__(128) k_hash4(Ctx<float> c, const float* __rest
     if (g.dense) {
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        bool in_table = key[p] >= 0 && (long long)key[p] < g.bound;
+        bool in_table = g.hashed || (key[p] >= 0 && (long long)key[p] < g.bound);  // (f32: keys are int32)
         if (in_table && c.win_len[0] > 0) {
           const long long k = (long long)key[p];
           in_table = (k >= c.win_lo[0] && k < c.win_lo[0] + c.win_len[0]) ||
                      (k >= c.win_lo[1] && k < c.win_lo[1] + c.win_len[1]);
         }
-        if (in_table) rk[p] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + key[p], 1);
+        if (in_table) rk[p] = atomicAdd(c.cell_count + (size_t)b * c.cell_stride + table_row(g, (long long)key[p]), 1);
         else c.gi[b].dense_fail = 1;
       }
       *reinterpret_cast<int4*>(c.rank + g0) = make_int4(rk[0], rk[1], rk[2], rk[3]);
@@ -495,7 +512,7 @@ __global__ void __launch_bounds__(256) k_scatter(Ctx<F> c) {
   const size_t gidx = (size_t)b * c.n + i;
   const int key = (int)c.key[gidx];
   const Vec4<F> p = c.urec[gidx];
-  const size_t slot = (size_t)b * c.n + c.cell_start[(size_t)b * c.cell_stride + key] + c.rank[gidx];
+  const size_t slot = (size_t)b * c.n + c.cell_start[(size_t)b * c.cell_stride + table_row(g, (long long)key)] + c.rank[gidx];
   if (sizeof(F) == 4) {
     st256(c.arec + 32 * slot, (float)p.x, (float)p.y, (float)p.z, (float)p.w, __int_as_float((int)i),
           __int_as_float(key), 0.f, 0.f);
@@ -735,10 +752,25 @@ __global__ void __launch_bounds__(256) k_finalize(Ctx<F> c, const int* __restric
       i = me.x;
       key = me.y;
     }
-    c.tmp_key[off + k] = key;  // cells stay in place: the key of arrival slot k is the key of final slot k
-    const int s = cs[key], e = cs[key + 1];
+    if (!g.hashed) c.tmp_key[off + k] = key;  // cells stay in place: the key of arrival slot k is the key of final slot k
+    const long long row = table_row(g, (long long)key);
+    const int s = cs[row], e = cs[row + 1];
     int r = 0;
-    if (e - s > 1 && c.order_id) {  // rank = members of the cell with a smaller order id (jdb200_state.order_id)
+    if (g.hashed) {  // a row may hold several cells: order by (key, original index)
+      if (e - s > 1) {
+        if (sizeof(F) == 4) {
+          const int* rec = reinterpret_cast<const int*>(c.arec + 32 * off) + 4;  // (index, key) of every arrival slot
+          for (int kk = s; kk < e; ++kk) {
+            const int ik = rec[8 * (size_t)kk], kk_key = rec[8 * (size_t)kk + 1];
+            r += kk_key < key || (kk_key == key && ik < i);
+          }
+        } else {
+          const int2* __restrict__ tmp = c.slot_rec + off;
+          for (int kk = s; kk < e; ++kk) r += tmp[kk].y < key || (tmp[kk].y == key && tmp[kk].x < i);
+        }
+      }
+      c.tmp_key[off + s + r] = key;
+    } else if (e - s > 1 && c.order_id) {  // rank = members of the cell with a smaller order id (jdb200_state.order_id)
       const long long* oid = c.order_id + off;
       const long long mine_id = oid[i];
       if (sizeof(F) == 4) {

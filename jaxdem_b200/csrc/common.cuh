@@ -122,7 +122,17 @@ struct GridInfo {
   int any_ext;       // some external force / torque buffer entry is non-zero (fused hash kernel)
   int any_fixed;     // some particle is fixed (fused hash kernel)
   int edge;          // some cell coordinate lies outside [0, g) (periodic: rounded up to g), so its hash aliases another cell: keys cannot be decoded
+  int hashed;        // 1: the grid has more cells than the table has rows — the table is addressed by a HASH of the cell
+                     //    key (rows = 2^(32 - hshift)); a row may hold several cells, kept sorted by (key, index), and
+                     //    every look-up filters by the exact key.  Same pair sets as the sorted strategy, no sort.
+  int hshift;
 };
+
+// row of the cell table that holds cell `key`
+template <typename I>
+__device__ __forceinline__ long long table_row(const GridInfo<I>& g, long long key) {
+  return g.hashed ? (long long)(((unsigned)key * 2654435761u) >> g.hshift) : key;
+}
 
 template <typename F, typename I>
 __device__ __forceinline__ void grid_dims(const F* __restrict__ box, F cell_size, int dim,

@@ -133,7 +133,16 @@ __device__ __forceinline__ void walk_stencil_at(const Ctx<F>& c, int b, const F*
       if (dup) continue;
     }
     int s, e;
-    if (dense) {
+    if (dense && g.hashed) {  // the row of the hashed table, narrowed to the run of cell h (rows are sorted by key)
+      const int hk = (int)h;
+      const long long row = table_row(g, (long long)hk);
+      const int* tk = c.tmp_key + off;
+      s = cstart[row];
+      const int re = cstart[row + 1];
+      while (s < re && tk[s] < hk) ++s;
+      e = s;
+      while (e < re && tk[e] == hk) ++e;
+    } else if (dense) {
       if (h < 0 || (long long)h >= g.bound) continue;
       s = cstart[h];
       e = cstart[h + 1];
@@ -175,7 +184,7 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
 // ---------------------------------------------------------------------------
 template <typename I>
 __device__ __forceinline__ bool fast_walk_ok(const GridInfo<I>& g) {
-  return g.dense && !g.dense_fail && g.canonical && !g.need_dedup;
+  return g.dense && !g.dense_fail && !g.hashed && g.canonical && !g.need_dedup;  // hashed rows: adjacent cells are not adjacent rows
 }
 
 // the flat kernel (k_pair_flat) additionally wants the default stencil range R = 1

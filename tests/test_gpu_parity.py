@@ -508,6 +508,46 @@ def test_slab_pack_unpack_kernels_bit_exact(dtype, dim):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dim,domain", [(3, "periodic"), (3, "free"), (2, "reflect")])
+@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
+def test_hashed_cell_table_dilute_system(dtype, dim, domain, law):
+    """A grid with far more cells than the cell table has rows (dilute gas, the reference's own benchmark
+    recipe benchmarks/base.py:10-34 scaled down): the table is addressed by a hash of the cell key instead of
+    falling back to the radix sort.  Forces, torques, energy and neighbour lists against the oracle; forces also
+    against the sorted strategy of the same build; particles outside a non-periodic grid included."""
+    inp = make_inputs(6000, dim, seed=41, dtype=dtype, phi=0.03 if dim == 3 else 0.05, poly=1.5)
+    if domain != "periodic":
+        inp["pos"][::97] -= 0.6 * inp["box"]  # a few particles outside the box / grid
+    ost, osy = build_oracle(inp, dtype=dtype, domain=domain, law=law)
+    gst, gsy = build_gpu(inp, dtype=dtype, domain=domain, law=law)
+    assert int(gsy.collider.table_strategy(gst, gsy)) == 2
+    ocol.celllist_compute_force(ost, osy)
+    gsy.collider.compute_force(gst, gsy)
+    assert float(np.abs(ost.force).max()) > 0
+    assert_close(gst.force, ost.force, dtype, "force")
+    assert_close(gst.torque, ost.torque, dtype, "torque")
+    assert not bool(gsy.collider.overflow)
+    _, _, e = gsy.collider.compute_potential_energy(gst, gsy)
+    want_e = ocol.celllist_compute_potential_energy(ost, osy)
+    assert abs(float(e) - float(want_e)) <= (1e-5 if dtype == np.float32 else 1e-12) * max(1.0, abs(float(want_e)))
+    # neighbour list: rows, padding and overflow bit for bit
+    K = 12
+    want, wovf = ocol.celllist_create_neighbor_list(ost, osy, 1.5, K)
+    _, _, got, govf = gsy.collider.create_neighbor_list(gst, gsy, 1.5, K)
+    assert np.array_equal(got.cpu().numpy(), want) and bool(govf) == bool(wovf)
+    # the sorted strategy (radix sort + binary search) on the same inputs: same contacts, same per-contact arithmetic
+    sst, ssy = build_gpu(inp, dtype=dtype, domain=domain, law=law, grid_mode="sorted")
+    assert int(ssy.collider.table_strategy(sst, ssy)) == 0
+    ssy.collider.compute_force(sst, ssy)
+    assert_close(gst.force, sst.force.cpu().numpy(), dtype, "force vs sorted", factor=4)
+    # a full step through the driver stays on the oracle's trajectory
+    import jaxdem_b200 as jd
+    oracle.step(ost, osy, 2)
+    jd.System.step(gst, gsy, n=2)
+    compare_states(gst, ost, dtype, factor=8.0)
+
+
+@pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("dim", [2, 3])
 def test_partition_order_id_bit_exact(dtype, dim):
     """jdb200_state.order_id: particles that share a cell are ordered by the given id instead of the row index
