@@ -441,8 +441,9 @@ def workload_config(args, n):
                 "parallelism": par}
     if args.gpus > 1 and args.mode == "slab":
         par = (f"ONE periodic system of {args.gpus} x {n} spheres (box L x L x {args.gpus}L), z-slab decomposition, "
-               "one slab per GPU; halo + migration exchange every step by peer-memory stores over NVLink "
-               "(symmetric memory; NCCL send/recv is the fallback transport)")
+               "one slab per GPU; halo + migration exchange every step by peer-memory stores over NVLink with "
+               "neighbour-to-neighbour flags and device-side row counts, no host synchronisation inside a step "
+               "(symmetric memory; NCCL only sets up the group, send/recv is the fallback transport)")
     elif args.gpus > 1:
         par = "1 system per GPU (replicas)"
     else:
