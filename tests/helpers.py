@@ -135,3 +135,34 @@ def compare_states(gst, ost, dtype, factor=1.0, fields=("pos_c", "vel", "force",
     assert_close(gst.q.w, ost.q_w, dtype, "q_w", factor=factor)
     assert_close(gst.q.xyz, ost.q_xyz, dtype, "q_xyz", factor=factor, scale=1.0)
     assert_close(gst._pos_p_rot, ost._pos_p_rot, dtype, "_pos_p_rot", factor=factor, scale=1.0)
+
+
+# ---- committed fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py from the oracle) ----
+def golden_cases():
+    import glob
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(here, "*.npz")))
+
+
+def load_golden(path):
+    """-> (inputs dict as make_inputs returns it, build kwargs, stored outputs, meta)."""
+    z = np.load(path)
+    meta = eval(str(z["meta"]), {"__builtins__": {}}, {"True": True, "False": False})
+    dtype = np.dtype(meta["dtype"]).type
+    inp = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    kw = dict(dtype=dtype, domain=meta["domain"], law=meta["law"], lin=meta["lin"], rot=meta["rot"], dt=1e-3,
+              nmat=meta["nmat"])
+    out = {k: z[k] for k in z.files if not k.startswith("in_") and k != "meta"}
+    return inp, kw, out, meta
+
+
+def golden_close(got, want, dtype, name):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    if want.dtype.kind in "iub":
+        assert np.array_equal(got, want), name
+        return
+    tol = 1e-5 if np.dtype(dtype) == np.float32 else 1e-11
+    scale = max(1.0, float(np.abs(want).max()))
+    assert float(np.abs(got.astype(np.float64) - want).max()) <= 8 * tol * scale, (name, float(np.abs(got - want).max()), scale)

@@ -243,3 +243,32 @@ def test_force_model_pair_reference_pin():
     k = float(sy.mat_table.young_eff[0, 0])
     assert np.allclose(f.numpy(), k * (2.0 - r) * rij / r, rtol=1e-13)
     assert t.shape == (1,) and float(t.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("path", __import__("helpers").golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_golden(path):
+    """The oracle against its committed outputs (tests/golden/, see make_golden.py for what they are): partition,
+    neighbour hashes and neighbour lists bit for bit, forces / torques / energy / a 3-step trajectory to rounding."""
+    from helpers import build_oracle, golden_close, load_golden
+    import oracle
+    from oracle import colliders as ocol
+    inp, kw, want, meta = load_golden(path)
+    ost, osy = build_oracle(inp, **kw)
+    perm, sh, nh, _, _ = ocol.get_spatial_partition(ost.pos, osy, osy.collider.cell_size, osy.collider.neighbor_mask,
+                                                     ost.idtype)
+    if osy.domain.periodic:
+        nh = ocol.dedup_stencil_hashes(nh)
+    dt = kw["dtype"]
+    golden_close(perm, want["perm"], dt, "perm")
+    golden_close(sh, want["sorted_hash"], dt, "sorted_hash")
+    golden_close(nh, want["nbr_hash"], dt, "nbr_hash")
+    ocol.celllist_compute_force(ost, osy)
+    golden_close(ost.force, want["force0"], dt, "force0")
+    golden_close(ost.torque, want["torque0"], dt, "torque0")
+    golden_close(ocol.celllist_compute_potential_energy(ost, osy), want["energy0"], dt, "energy0")
+    nl, ovf = ocol.celllist_create_neighbor_list(ost, osy, 1.1, 24)
+    golden_close(nl, want["nlist"], dt, "nlist")
+    assert bool(ovf) == bool(want["nlist_overflow"])
+    oracle.step(ost, osy, meta["steps"])
+    for f in ("pos_c", "vel", "force", "torque", "ang_vel"):
+        golden_close(getattr(ost, f), want[f + "_after"], dt, f)
