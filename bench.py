@@ -653,10 +653,10 @@ def dominant_roofline(kernels, n, peak, peak_src, cfg):
             "algorithmic_bytes_per_launch": (bpp * n) if bpp else None,
             "us_per_launch": kernels[dom]["us_per_launch"], "peak_source": peak_src}
     tr = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the last ncu --set full
-    if os.path.exists(tr) and cfg == "c2":
+    if os.path.exists(tr) and cfg in ("c2", "c3"):
         try:
-            roof["traffic"] = json.load(open(tr)).get(dom)
-        except (OSError, ValueError):
+            roof["traffic"] = json.load(open(tr)).get(cfg, {}).get(dom)
+        except (OSError, ValueError, AttributeError):
             pass
     return roof
 

@@ -4,7 +4,7 @@ lines = open(sys.argv[1]).read().splitlines()
 start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
 rows = list(csv.reader(lines[start:]))
 hdr, units = rows[0], rows[1]
-want = [("gpu__time_duration.sum", "ns"), ("dram__bytes_read.sum", "rdB"), ("dram__bytes_write.sum", "wrB"),
+want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rdB"), ("dram__bytes_write.sum", "wrB"),
         ("smsp__inst_executed.sum", "winst"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
         ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1wf%"),
