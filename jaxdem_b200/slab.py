@@ -396,6 +396,8 @@ class SlabSystem:
         self.check_every = 32
         self.timeout_s = 5.0       # a neighbour's message that takes longer sets JDB200_SLAB_TIMEOUT
         self._pending = None
+        self._graph = None         # (CUDAGraph of one step, the bound it was captured with), see compile_step
+        self.graph_steps = False
         self._host_headers = torch.zeros((3, 8), dtype=torch.int64)
         if dev.type == "cuda":
             self._host_headers = self._host_headers.pin_memory()
@@ -679,7 +681,19 @@ class SlabSystem:
             if not getattr(self, "_dev_synced", False):
                 self._push_counts()
             for _ in range(int(n)):
-                eng.step_dev(self)
+                g = self._graph
+                if g is not None and g[1] == self.bound:
+                    g[0].replay()
+                else:
+                    if g is not None:  # the launch bound moved: the captured grids are stale
+                        self._graph = None
+                        if self.graph_steps:
+                            self.compile_step()
+                            self._graph[0].replay()
+                            self.steps_done += 1
+                            self._poll()
+                            continue
+                    eng.step_dev(self)
                 self.steps_done += 1
                 self._poll()
             return
@@ -692,6 +706,23 @@ class SlabSystem:
                 eng.compute_force(rows(self.n_own + self.n_ghost))
                 eng.after_force(rows(self.n_own))
             self.steps_done += 1
+
+    def compile_step(self) -> None:
+        """Capture ONE decomposed step — integrator hooks, the whole exchange, partition, pair kernel, epilogue — in
+        a CUDA graph (the counterpart of ``jax.jit`` for this path; System.compile_step does the same on one GPU).
+        Possible because the device protocol changes no argument from step to step: row counts, buffer parities
+        and the exchange number are read on the device.  ``step`` replays it from then on (collectively: every
+        rank replays the same number of steps) and re-captures when the launch bound is adjusted."""
+        if not (self.device_protocol and self.world > 1 and getattr(self.engine, "_bound", None) is not None):
+            raise RuntimeError("compile_step needs the device protocol (peer transport, CUDA engine, world > 1)")
+        if not getattr(self, "_dev_synced", False):
+            self._push_counts()
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            self.engine.step_dev(self)
+        self._graph = (graph, self.bound)
+        self.graph_steps = True
 
     def compute_force(self) -> None:
         """collider.compute_force on the decomposed system at the current positions."""

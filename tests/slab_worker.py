@@ -46,7 +46,13 @@ def main():
                               rotation_integrator_type=rot, mat_table=mt, dtype=torch.float32, device=dev,
                               transport=transport)
     slab.compute_force()
-    slab.step(steps)
+    if os.environ.get("SLAB_GRAPH") == "1" and world > 1:
+        slab.step(2)            # two stream-launched steps, then the rest replayed from a CUDA graph
+        slab.compile_step()
+        slab.step(steps - 2)
+        print(f"[slab] rank {rank}: {steps - 2} steps replayed from a CUDA graph")
+    else:
+        slab.step(steps)
     torch.cuda.synchronize()
     res = slab.gather(("pos_c", "vel", "force", "ang_vel"))
     ok = True

@@ -415,17 +415,19 @@ def test_full_size_parity_vs_c_oracle_1m():
     assert not bool(gsy.collider.overflow)
 
 
-def _run_slab_worker(world, *args):
+def _run_slab_worker(world, *args, graph=False):
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAB_GRAPH="1" if graph else "0")
     worker = os.path.join(root, "tests", "slab_worker.py")
     if world == 1:
         cmd = [sys.executable, worker, *map(str, args)]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", worker, *map(str, args)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "SLAB-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert not graph or "replayed from a CUDA graph" in r.stdout
 
 
 @pytest.mark.parametrize("law", ["spring", "cundallstrack"])
@@ -441,6 +443,15 @@ def test_slab_system_two_gpus(law, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_slab_worker(2, 200000, 10, law, transport)
+
+
+@pytest.mark.parametrize("law", ["spring", "cundallstrack"])
+def test_slab_step_cuda_graph_two_gpus(law):
+    """The whole decomposed step (hooks + exchange + partition + pair kernel + epilogue) replayed from a CUDA graph
+    on two GPUs: same bitwise agreement with the single-GPU trajectory as the stream-launched step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_slab_worker(2, 200000, 10, law, "peer", graph=True)
 
 
 @pytest.mark.parametrize("dtype", DT)
