@@ -856,7 +856,10 @@ static bool launch_hash4(cudaStream_t s, Ctx<float>& c, const float* cso, int mo
 
 template <typename F, int D>
 static int launch_hash(cudaStream_t s, Ctx<F>& c, const F* cso, int mode, bool ext) {
-  if ((mode == 0 || mode == 3 || mode == 4) && launch_hash4<D>(s, c, cso, mode)) return 0;
+  // The four-particles-per-thread kernel wins where the hash runs on its own (mode 0: 321 vs 913 us on the 4 M-sphere
+  // clump workload, whose members are neighbours in index AND in space) and loses where the integrator rides along
+  // (modes 3 / 4: 33 vs 29 us at 1 M spheres, 102-128 registers at 22 % occupancy): measured, profiles/README.md.
+  if (mode == 0 && launch_hash4<D>(s, c, cso, mode)) return 0;
   const dim3 grid(cdiv(c.n, 256), c.batch);
   if (mode == 0) JDB_LAUNCH((k_hash<F, D, 0>), grid, 256, s, c, cso);
   else if (mode == 3) JDB_LAUNCH((k_hash<F, D, 3>), grid, 256, s, c, cso);
