@@ -889,6 +889,7 @@ __global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW ==
     else c.overflow[b] = 1;  // JDB200_GRID_DENSE and the dense table cannot hold this system
   }
   const long long n_live = c.n_dev ? *c.n_dev : c.n;  // ragged rows (batch == 1: offsets do not depend on n)
+  if ((long long)blockIdx.x * blockDim.x >= n_live) return;  // a block of the launch bound past the live rows
   const long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = k0 < n_live;
   if (!mine) {

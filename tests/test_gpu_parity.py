@@ -251,6 +251,30 @@ def test_full_step_matches_oracle(dtype, cfg):
     assert float(gsy.step_count) == 3
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_fused_step_with_sphere_reference_offsets(dtype):
+    """Sphere system (clump_id == arange) whose spheres carry a non-zero pos_p: the rotation integrator's
+    step_before_force moves them (_pos_p_rot = R(q) pos_p) before the collider hashes them: the fused driver
+    (k_rotation in front of the hash kernel, rotation after-kick in the pair epilogue) == hook-by-hook bitwise,
+    both on the oracle."""
+    import jaxdem_b200 as jd
+    inp = make_inputs(1500, 3, seed=29, dtype=dtype, phi=0.5, poly=1.3, nmat=2)
+    inp["pos_p"] = (np.random.default_rng(3).normal(0, 0.15, inp["pos"].shape)).astype(dtype)
+    kw = dict(dtype=dtype, domain="periodic", law="cundallstrack", lin="verlet", rot="verletspiral", dt=1e-3, nmat=2)
+    ost, osy = build_oracle(inp, **kw)
+    gst, gsy = build_gpu(inp, **kw)
+    hst, hsy = build_gpu(inp, **kw)
+    assert not gst.has_clumps and float(gst._pos_p_rot.abs().max()) > 0
+    for step in range(3):
+        oracle.step(ost, osy, 1)
+        jd.System.step(gst, gsy, n=1)
+        jd.System.step(hst, hsy, n=1, fused=False)
+        compare_states(gst, ost, dtype, factor=4.0 * (step + 1))
+        for f in ("pos_c", "vel", "force", "torque", "ang_vel", "_pos_p_rot"):
+            assert torch.equal(getattr(gst, f), getattr(hst, f)), f
+        assert torch.equal(gst.q.w, hst.q.w) and torch.equal(gst.q.xyz, hst.q.xyz)
+
+
 def test_readme_config_naive_reflect():
     # BASELINE config 1: 10x10x10 grid, spacing 0.5, r 0.1, reflect box 20, naive collider,
     # defaults of System.create (dt 0.005, verlet + verletspiral, spring, young_eff 1e4)
