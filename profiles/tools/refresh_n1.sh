@@ -22,3 +22,11 @@ for l in open('gpurun_out/r2_final_reference.json'):
         d=json.loads(l); print("reference", d["value"], d["cpu_baseline"]["cores"])
 PY
 ls -la gpurun_out/*.ncu-rep
+# the 64 M-sphere single-GPU baseline of the strong-scaling claim
+timeout 1200 python bench.py --config c3 --n-total 67108864 --steps 10 --warmup 3 --no-cpu > gpurun_out/r2_final_c3_64m_n1.json 2> gpurun_out/r2_final_c3_64m_n1.err; echo "64m rc=$?"
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2_final_c3_64m_n1.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print("c3 64M n1", d["value"], d["ms_per_step"], {k:round(v['us_per_step'],1) for k,v in d['kernels'].items()})
+PY
