@@ -21,6 +21,7 @@ template <typename F> int naive_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int neighborlist_force(cudaStream_t, Ctx<F>&);
 template <typename F> int neighborlist_energy(cudaStream_t, Ctx<F>&, F*);
 template <typename F> int force_manager_apply_pe(cudaStream_t, Ctx<F>&, F*);
+template <typename F> int force_manager_fire_tail(cudaStream_t, Ctx<F>&, const F*, const F*, const F*);
 
 template <typename F>
 struct Fire {  // device view of jdb200_fire_state + the scalars of jdb200_fire_params in F
@@ -238,17 +239,21 @@ __global__ void __launch_bounds__(kReduceBlock) k_fire_maxgrad(Ctx<F> c) {
 
 // loop carry + cond_fun (routines.py:284-310, 364-372)
 template <typename F>
-__global__ void __launch_bounds__(kReduceBlock) k_fire_cond(Ctx<F> c, Fire<F> fs, int init) {
+__global__ void __launch_bounds__(kReduceBlock) k_fire_cond(Ctx<F> c, Fire<F> fs, int init, int fm_in_parts) {
   pdl_prologue();
   __shared__ F sm[kReduceBlock];
   const int b = blockIdx.x;
   if (!init && !fs.active[b]) return;
-  F m = F(0);
-  for (int i = threadIdx.x; i < c.reduce_blocks; i += kReduceBlock)
+  F m = F(0), ge = F(0);
+  for (int i = threadIdx.x; i < c.reduce_blocks; i += kReduceBlock) {
     m = RT<F>::fmax(m, c.min_part[((size_t)b * c.reduce_blocks + i) * 4 + 2]);
+    if (fm_in_parts) ge += c.min_part[((size_t)b * c.reduce_blocks + i) * 4 + 3];  // k_fm_fire_tail (the order of k_fm_energy_final)
+  }
   m = blk_max(m, sm);
+  if (fm_in_parts) ge = blk_sum(ge, sm);
   if (threadIdx.x != 0) return;
-  const F pe_new = c.min_pe[c.batch + b] + c.min_pe[b];  // force manager + collider (thermal.py:148-150)
+  const F pe_fm = fm_in_parts ? -ge : c.min_pe[c.batch + b];
+  const F pe_new = pe_fm + c.min_pe[b];  // force manager + collider (thermal.py:148-150)
   F pe, prev;
   long long steps;
   if (init) {
@@ -324,11 +329,17 @@ int minimize_fire(cudaStream_t s, Ctx<F>& c, int collider, const jdb200_fire_sta
   const dim3 gr(c.reduce_blocks, B), gp(cdiv(c.n, 256), B), gb(cdiv(B, 64));
   F* pe_fm = c.min_pe + B;  // min_pe = [collider energies (B) | force-manager energies (B)]
   int rc = 0;
+  // sphere systems: force manager, its energy, max |grad| and the NEXT iteration's FIRE power in one pass
+  const bool tail = !c.clumps;
   auto evaluate = [&](int is_init) -> int {
     if ((rc = fire_eval<F>(s, c, collider))) return rc;
-    if ((rc = force_manager_apply_pe<F>(s, c, pe_fm))) return rc;
-    JDB_LAUNCH(k_fire_maxgrad<F>, gr, kReduceBlock, s, c);
-    JDB_LAUNCH(k_fire_cond<F>, dim3(B), kReduceBlock, s, c, fs, is_init);
+    if (tail) {
+      if ((rc = force_manager_fire_tail<F>(s, c, fs.vel_pos, fs.vel_rot, fs.dt))) return rc;
+    } else {
+      if ((rc = force_manager_apply_pe<F>(s, c, pe_fm))) return rc;
+      JDB_LAUNCH(k_fire_maxgrad<F>, gr, kReduceBlock, s, c);
+    }
+    JDB_LAUNCH(k_fire_cond<F>, dim3(B), kReduceBlock, s, c, fs, is_init, tail ? 1 : 0);
     return 0;
   };
   if (init) {
@@ -338,8 +349,10 @@ int minimize_fire(cudaStream_t s, Ctx<F>& c, int collider, const jdb200_fire_sta
     if ((rc = evaluate(1))) return rc;
   }
   for (long long it = 0; it < n_iter; ++it) {
-    if (c.dim == 3) JDB_LAUNCH((k_fire_power<F, 3>), gr, kReduceBlock, s, c, fs);
-    else JDB_LAUNCH((k_fire_power<F, 2>), gr, kReduceBlock, s, c, fs);
+    if (!tail || (it == 0 && !init)) {  // (a call that continues a run: the partials of the previous call are gone)
+      if (c.dim == 3) JDB_LAUNCH((k_fire_power<F, 3>), gr, kReduceBlock, s, c, fs);
+      else JDB_LAUNCH((k_fire_power<F, 2>), gr, kReduceBlock, s, c, fs);
+    }
     JDB_LAUNCH(k_fire_scalars<F>, dim3(B), kReduceBlock, s, c, fs);
     if (c.dim == 3) JDB_LAUNCH((k_fire_update<F, 3>), gp, 256, s, c, fs);
     else JDB_LAUNCH((k_fire_update<F, 2>), gp, 256, s, c, fs);

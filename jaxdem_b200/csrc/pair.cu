@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(RowsCfg<D>::kThreads, sizeof(F) == 4 ? (LAW ==
 // D of the row kernel: one thread per ORIGINAL particle i.  EPI 0: the epilogue of
 // DynamicCellList.compute_force (cell_list.py:461-462); EPI 1: the fused sphere driver
 // (fused_sphere_epilogue: collider epilogue + ForceManager.apply + step_after_force).
-template <typename F, int D, int EPI>
+template <typename F, int D, int EPI, bool WITH_E>
 __global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
   pdl_prologue();
   JDB_LIVE_ROWS(c);
@@ -923,17 +923,32 @@ __global__ void __launch_bounds__(256) k_after(Ctx<F> c, int with_torque) {
   // being launched; then Collider.overflow is up and the hook still completes, with zero contact forces
   if (!served && c.grid_mode != JDB200_GRID_DENSE) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
+  const bool live = i < c.n;
+  if (!live && !WITH_E) return;
   const size_t off = (size_t)b * c.n;
   Vec4<F> fs = Vec4<F>{0, 0, 0, 0}, ts = Vec4<F>{0, 0, 0, 0};
-  if (served) {
-    const int slot = c.inv[off + i];
-    fs = ldg_vec4(c.sforce + off + slot);
-    if (c.law == JDB200_LAW_CUNDALLSTRACK) ts = ldg_vec4(c.storque + off + slot);
+  if (live) {
+    if (served) {
+      const int slot = c.inv[off + i];
+      fs = ldg_vec4(c.sforce + off + slot);
+      if (c.law == JDB200_LAW_CUNDALLSTRACK) ts = ldg_vec4(c.storque + off + slot);
+    }
+    const F f[3] = {fs.x, fs.y, fs.z}, t[3] = {ts.x, ts.y, ts.z};
+    if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.uvm[off + i], (int)i, f, t, with_torque != 0);
+    else store_force_torque<F, D>(c, off + i, f, t, g.any_ppr != 0, with_torque != 0);
   }
-  const F f[3] = {fs.x, fs.y, fs.z}, t[3] = {ts.x, ts.y, ts.z};
-  if (EPI == 1) fused_sphere_epilogue<F, D>(c, b, g, c.uvm[off + i], (int)i, f, t, with_torque != 0);
-  else store_force_torque<F, D>(c, off + i, f, t, g.any_ppr != 0, with_torque != 0);
+  // minimiser loop: the gathered record also carries the particle's energy share — block sums in the partial
+  // layout of k_pair_energy (same block size), which then skips the systems served here
+  if (WITH_E && served) {  // (its own instantiation: the shared array and the barriers stay off the step path)
+    __shared__ F sm_e[256];
+    sm_e[threadIdx.x] = live ? fs.w : F(0);
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) sm_e[threadIdx.x] += sm_e[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blockIdx.x] = sm_e[0];
+  }
 }
 
 // FAST = true: systems whose partition allows the x-run walk; FAST = false: the rest
@@ -1009,25 +1024,12 @@ __device__ __forceinline__ F block_sum_256(F v) {  // fixed tree order => determ
   return sm[0];
 }
 
-// Minimiser loop (c.want_energy): the systems the row kernel served already hold every particle's energy share in
-// sforce.w — block sums of those, in the partial layout of k_pair_energy (which then skips these systems).
-template <typename F>
-__global__ void __launch_bounds__(kReduceBlock) k_rows_energy_partial(Ctx<F> c) {
-  pdl_prologue();
-  const int b = blockIdx.y;
-  if (!rows_ok(c, c.gi[b])) return;
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const F e = k < c.n ? c.sforce[(size_t)b * c.n + k].w : F(0);
-  const F tot = block_sum_256(e);
-  if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blockIdx.x] = tot;
-}
-
 template <typename F, int LAW>
 __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
-  if (c.want_energy && rows_ok(c, c.gi[b])) return;  // summed from the row kernel's per-particle shares
+  if (c.want_energy && rows_ok(c, c.gi[b])) return;  // block sums of the row kernel's per-particle shares: k_after
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t off = (size_t)b * c.n;
   F e = F(0);
@@ -1362,7 +1364,8 @@ int launch_pair_force_epi(cudaStream_t s, Ctx<F>& c, bool with_torque) {
       }
       // (a four-particles-per-thread variant with 128-bit stores was measured slower in every configuration:
       // 24.7 vs 22.6 us fused, 81 vs 69 us on the 4 M-sphere clump workload)
-      JDB_LAUNCH((k_after<F, D, EPI>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
+      if (c.want_energy) JDB_LAUNCH((k_after<F, D, EPI, true>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
+      else JDB_LAUNCH((k_after<F, D, EPI, false>), dim3(cdiv(c.n, 256), c.batch), 256, s, c, wt);
       return 0;  // the systems it cannot serve took the generic walk inside the same launch
     } else if (c.periodic) {         // wider canonical stencils: x-run kernel
       JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_force<F, L, D, true, true, EPI>), grid, 128, s, c, wt));
@@ -1418,7 +1421,6 @@ int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy, bool reuse) {
   if (rc) return rc;
   if (c.prune && !reuse && (rc = cell_aabbs<F>(s, c, 1))) return rc;
   const dim3 grid(c.reduce_blocks, c.batch);
-  if (c.want_energy) JDB_LAUNCH(k_rows_energy_partial<F>, grid, kReduceBlock, s, c);
   JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
   JDB_LAUNCH(k_final_sum<F>, dim3(c.batch), kReduceBlock, s, c.partial, c.reduce_blocks, energy);
   return 0;

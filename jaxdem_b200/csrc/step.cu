@@ -302,6 +302,83 @@ int force_manager_apply_pe(cudaStream_t s, Ctx<F>& c, F* pe_out) {
   return 0;
 }
 
+// Minimiser loop, sphere systems: ForceManager.apply, the gravity part of its potential energy, max |grad| of the
+// termination test (routines.py:299-305) and the FIRE power of the NEXT iteration (optimizers.py:233-238) in ONE
+// pass over the particles — the four quantities read the same force / torque.  Per-block partials in
+// min_part[block][0..3] = (power of the pos_c leaf, power of the rotvec leaf, max |grad|, gravity energy), same block
+// decomposition, same fixed-order trees and the same per-particle expressions as the stand-alone kernels
+// (k_fire_power, k_fire_maxgrad, k_fm_energy) => bit-identical iterates.
+template <typename F, int D>
+__global__ void __launch_bounds__(kReduceBlock) k_fm_fire_tail(Ctx<F> c, const F* __restrict__ vel_pos,
+                                                               const F* __restrict__ vel_rot, const F* __restrict__ fdt) {
+  pdl_prologue();
+  constexpr int A = D == 3 ? 3 : 1;
+  __shared__ F sm[kReduceBlock];
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  F pl = F(0), pr = F(0), mg = F(0), ge = F(0);
+  if (i < c.n) {
+    const size_t gi = (size_t)b * c.n + i;
+    F Ft[3], Tt[3];
+    fm_totals(c, b, gi, F(1), Ft, Tt);
+#pragma unroll
+    for (int d = 0; d < D; ++d) c.force[gi * D + d] = Ft[d];
+#pragma unroll
+    for (int a = 0; a < A; ++a) c.torque[gi * A + a] = Tt[a];
+    fm_clear_ext(c, gi);
+    const F m = c.fixed[gi] ? F(0) : F(1);
+    const F dt = fdt[b];
+    F gd = F(0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      mg = RT<F>::fmax(mg, RT<F>::abs(Ft[d]));
+      const F f = Ft[d] * m;
+      const F vo = vel_pos[gi * D + d] + f * dt / F(2);
+      pl += f * vo;
+      gd += c.gravity[b * D + d] * c.pos_c[gi * D + d];
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      mg = RT<F>::fmax(mg, RT<F>::abs(Tt[a]));
+      const F f = Tt[a] * m;
+      const F vo = vel_rot[gi * A + a] + f * dt / F(2);
+      pr += f * vo;
+    }
+    ge = gd * c.mass[gi] / F(1);
+  }
+  auto tree_sum = [&](F v) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int st = kReduceBlock / 2; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+      __syncthreads();
+    }
+    const F r = sm[0];
+    __syncthreads();
+    return r;
+  };
+  const F sl = tree_sum(pl), sr = tree_sum(pr), sg = tree_sum(ge);
+  sm[threadIdx.x] = mg;
+  __syncthreads();
+  for (int st = kReduceBlock / 2; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) sm[threadIdx.x] = RT<F>::fmax(sm[threadIdx.x], sm[threadIdx.x + st]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    F* o = c.min_part + ((size_t)b * c.reduce_blocks + blockIdx.x) * 4;
+    o[0] = sl; o[1] = sr; o[2] = sm[0]; o[3] = sg;
+  }
+}
+
+// -> true when the fused tail ran (sphere systems); the caller then takes the gravity energy from min_part[..][3]
+template <typename F>
+int force_manager_fire_tail(cudaStream_t s, Ctx<F>& c, const F* vel_pos, const F* vel_rot, const F* fdt) {
+  const dim3 gr(c.reduce_blocks, c.batch);
+  if (c.dim == 3) JDB_LAUNCH((k_fm_fire_tail<F, 3>), gr, kReduceBlock, s, c, vel_pos, vel_rot, fdt);
+  else JDB_LAUNCH((k_fm_fire_tail<F, 2>), gr, kReduceBlock, s, c, vel_pos, vel_rot, fdt);
+  return 0;
+}
+
 template <typename F>
 int force_manager_apply(cudaStream_t s, Ctx<F>& c) {
   if (c.n == 0) return 0;
@@ -836,6 +913,7 @@ int frame_pack(cudaStream_t s, Ctx<F>& c, int fields, void* out) {
   template int frame_pack<F>(cudaStream_t, Ctx<F>&, int, void*);      \
   template int force_manager_apply<F>(cudaStream_t, Ctx<F>&);         \
   template int force_manager_apply_pe<F>(cudaStream_t, Ctx<F>&, F*);  \
+  template int force_manager_fire_tail<F>(cudaStream_t, Ctx<F>&, const F*, const F*, const F*);  \
   template int domain_apply<F>(cudaStream_t, Ctx<F>&);                \
   template int refresh_inv_box<F>(cudaStream_t, Ctx<F>&);             \
   template int linear_before<F>(cudaStream_t, Ctx<F>&);               \
