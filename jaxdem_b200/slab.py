@@ -311,7 +311,8 @@ class CudaEngine:
     def step_dev(self, slab):
         """One _step_once on the decomposed system, device protocol: no host synchronisation."""
         sy, B = self.system, slab.bound
-        torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
+        if not self._fuse_after:  # (the fused tail refreshes inv_box_size in its setup kernel; nothing before it reads it)
+            torch.reciprocal(sy.domain.box_size, out=sy.domain.inv_box_size)
         if not self.fuse_before and sy.linear_integrator.native_kind:
             self._hook("jdb200_linear_step_before_force", B, ws=False, rows="own")
         if sy.rotation_integrator.native_kind:
