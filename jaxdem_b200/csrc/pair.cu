@@ -172,6 +172,52 @@ __device__ __forceinline__ void walk_stencil(const Ctx<F>& c, int b, int k, cons
   walk_stencil_at<F>(c, b, pp, cell_size_override, vis, p.w);
 }
 
+// Hashed table + the default 3^D stencil, every particle inside the grid, no de-dup, no pruning: the cells in mask
+// order (last axis fastest) with their keys taken from the strides — a short loop instead of the general walk above
+// (mask loads, wrapped hashes, de-dup and prune tests per cell).  Used by the force kernels (the dilute systems whose
+// grid outgrows the dense table spend their time there); energy and neighbour-list builds keep the general walk.
+template <typename I>
+__device__ __forceinline__ bool hashed_walk_ok(const GridInfo<I>& g) {
+  return g.dense && !g.dense_fail && g.hashed && g.canonical && g.range == 1 && !g.need_dedup && !g.edge;
+}
+template <typename F, typename Vis>
+__device__ __forceinline__ void walk_hashed(const Ctx<F>& c, int b, const GridInfo<typename RT<F>::I>& g, const F* pp,
+                                            Vis& vis) {
+  using I = typename RT<F>::I;
+  const size_t off = (size_t)b * c.n;
+  const F cs = c.cell_size[b];
+  I cc[3] = {0, 0, 0};
+  for (int d = 0; d < c.dim; ++d)
+    cc[d] = cell_coord<F, I>(pp[d], c.anchor[b * c.dim + d], c.box[b * c.dim + d], cs, g.gd[d], c.periodic);
+  const int* cst = c.cell_start + (size_t)b * c.cell_stride;
+  const int* tk = c.tmp_key + off;
+  const int D = c.dim;
+  const long long g0 = (long long)g.gd[0], g1 = (long long)g.gd[1], g2 = D == 3 ? (long long)g.gd[2] : 1;
+  const long long s0 = (long long)g.stride[0], s1 = (long long)g.stride[1], s2 = D == 3 ? (long long)g.stride[2] : 0;
+  const int M = D == 3 ? 27 : 9;
+#pragma unroll 1
+  for (int m = 0; m < M; ++m) {
+    // offsets of stencil row m: digits of m in base 3, last axis fastest
+    const int o0 = (D == 3 ? m / 9 : m / 3) - 1, o1 = (D == 3 ? (m / 3) % 3 : m % 3) - 1, o2 = D == 3 ? m % 3 - 1 : 0;
+    long long n0 = (long long)cc[0] + o0, n1 = (long long)cc[1] + o1, n2 = (long long)cc[2] + o2;
+    if (c.periodic) {
+      n0 = n0 < 0 ? n0 + g0 : (n0 >= g0 ? n0 - g0 : n0);
+      n1 = n1 < 0 ? n1 + g1 : (n1 >= g1 ? n1 - g1 : n1);
+      n2 = n2 < 0 ? n2 + g2 : (n2 >= g2 ? n2 - g2 : n2);
+    } else if (n0 < 0 || n0 >= g0 || n1 < 0 || n1 >= g1 || n2 < 0 || n2 >= g2) {
+      continue;  // outside a non-periodic grid: no particle lives there (no edge particles in this branch)
+    }
+    const int hk = (int)(n0 * s0 + n1 * s1 + n2 * s2);
+    const long long row = table_row(g, (long long)hk);
+    int s = cst[row];
+    const int re = cst[row + 1];
+    while (s < re && tk[s] < hk) ++s;
+    int e = s;
+    while (e < re && tk[e] == hk) ++e;
+    if (e > s) vis.cell(m, s, e);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Fast stencil walk (dense table, canonical cubic stencil, no periodic de-dup needed):
 // the x-fastest linear hash makes the cells (cx-R .. cx+R, ny, nz) ONE contiguous run of
@@ -468,6 +514,9 @@ __device__ __forceinline__ void pair_force_body(const Ctx<F>& c, int b, int k,
   if (fast) {
     const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
     walk_runs<F, D, PERIODIC>(c, b, g, pp, vis);
+  } else if (hashed_walk_ok(g) && !c.prune) {
+    const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
+    walk_hashed<F>(c, b, g, pp, vis);
   } else {
     walk_stencil<F>(c, b, k, nullptr, vis);
   }
