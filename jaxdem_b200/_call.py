@@ -85,6 +85,13 @@ def state_view(state) -> L.StateView:
     v.q_w = state.q.w.data_ptr()
     v.q_xyz = state.q.xyz.data_ptr()
     v.pos_p_rot = state._pos_p_rot.data_ptr()
+    nr = getattr(state, "n_rows", None)  # optional () int64 on the device: live row count, State.N is then the launch bound
+    if nr is not None:
+        if nr.dtype != torch.int64 or nr.numel() != 1 or nr.device != state.pos_c.device:
+            raise RuntimeError("State.n_rows must be a one-element int64 tensor on the State's device")
+        if state.pos_c.ndim == 3:
+            raise RuntimeError("State.n_rows (ragged rows) is not available for batched States")
+        v.n_rows = nr.data_ptr()
     oid = getattr(state, "order_id", None)  # optional (B,N) int64: in-cell order of the partition (jdb200_state.order_id)
     if oid is not None:
         if oid.dtype != torch.int64 or not oid.is_contiguous() or oid.device != state.pos_c.device:

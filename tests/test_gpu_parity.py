@@ -583,6 +583,36 @@ def test_hashed_cell_table_dilute_system(dtype, dim, domain, law):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("law,rot", [("spring", ""), ("cundallstrack", "verletspiral")])
+def test_ragged_rows_device_count(dtype, law, rot):
+    """jdb200_state.n_rows: the live row count read on the device, State.N only the launch bound.  Forces and a
+    few steps on the first m rows of a larger State equal, bit for bit, the same calls on a State of exactly those
+    m rows; rows [m, N) are never touched."""
+    import jaxdem_b200 as jd
+    n, m = 6000, 4321
+    inp = make_inputs(n, 3, seed=37, dtype=dtype, phi=0.5, poly=1.3, nmat=2 if law != "spring" else 1)
+    kw = dict(dtype=dtype, domain="periodic", law=law, lin="verlet", rot=rot, dt=1e-3, nmat=2 if law != "spring" else 1)
+    big, bsy = build_gpu(inp, **kw)
+    cut = {k: (v[:m] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in inp.items()}
+    small, ssy = build_gpu(cut, **kw)
+    # same grid for both: the cell size of the full set
+    ssy.collider.cell_size.copy_(bsy.collider.cell_size)
+    big.n_rows = torch.tensor([m], dtype=torch.int64, device="cuda")
+    before = {f: getattr(big, f).clone() for f in ("pos_c", "vel", "force", "torque", "ang_vel")}
+    bsy.collider.compute_force(big, bsy)
+    ssy.collider.compute_force(small, ssy)
+    assert torch.equal(big.force[:m], small.force) and torch.equal(big.torque[:m], small.torque)
+    assert float(small.force.abs().max()) > 0
+    for fused in (True, False):
+        jd.System.step(big, bsy, n=2, fused=fused)
+        jd.System.step(small, ssy, n=2, fused=fused)
+        for f in ("pos_c", "vel", "force", "torque", "ang_vel"):
+            assert torch.equal(getattr(big, f)[:m], getattr(small, f)), (f, fused)
+    for f, t in before.items():  # the rows past the live count were left alone
+        assert torch.equal(getattr(big, f)[m:], t[m:]), f
+
+
+@pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("dim", [2, 3])
 def test_partition_order_id_bit_exact(dtype, dim):
     """jdb200_state.order_id: particles that share a cell are ordered by the given id instead of the row index
