@@ -228,7 +228,7 @@ __device__ __forceinline__ F pair_energy_rij(const LawCtx<F>& lc, const Body<F>&
   if (LAW == JDB200_LAW_SPRING) {
     // spring.py:136-147
     const F d2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-    const F k = lc.young_eff[a.mat * lc.nmat + b.mat];
+    const F k = lc.nmat == 1 ? lc.k0 : lc.young_eff[a.mat * lc.nmat + b.mat];  // (k0: preloaded, as in the force law)
     const F inv = d2 == F(0) ? F(0) : T::rsqrt(T::fmax(d2, F(1e-16)));
     const F s = T::fmax(F(0), a.r + b.r - d2 * inv);
     return F(0.5) * k * s * s;

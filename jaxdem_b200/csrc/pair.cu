@@ -1073,43 +1073,44 @@ __device__ __forceinline__ F block_sum_256(F v) {  // fixed tree order => determ
   return sm[0];
 }
 
-template <typename F, int LAW>
+// One instantiation per (law, dim, periodic) — like the force kernels — so that each kernel carries ONE x-run walk
+// next to the general one (the single four-way kernel was very large, see DESIGN.md "open observation").
+template <typename F, int LAW, int D, bool PERIODIC>
 __global__ void __launch_bounds__(kReduceBlock) k_pair_energy(Ctx<F> c) {
   pdl_prologue();
   using I = typename RT<F>::I;
   const int b = blockIdx.y;
   if (c.want_energy && rows_ok(c, c.gi[b])) return;  // block sums of the row kernel's per-particle shares: k_after
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t off = (size_t)b * c.n;
-  F e = F(0);
-  if (k < c.n) {
-    const GridInfo<I> g = c.gi[b];
-    const LawCtx<F> lc = make_law_ctx(c, b);
-    EnergyVis<F, LAW> vis{c, lc, off};
-    vis.a = load_sorted(c, off, k, false);
-    vis.k = k;
-    vis.idx = c.perm[off + k];
-    vis.simple = !c.clumps && !g.any_bond;
-    vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
-    vis.interact = c.interact && c.interact[b];
-    vis.e = F(0);
-    if (fast_walk_ok(g) && !c.prune) {
-      const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
-      if (c.dim == 3) {
-        if (c.periodic) walk_runs<F, 3, true>(c, b, g, pp, vis);
-        else walk_runs<F, 3, false>(c, b, g, pp, vis);
+  // one chunk of kReduceBlock particles per trip: gridDim.x == reduce_blocks in the stand-alone hook; the minimiser
+  // loop launches ONE block per system (this kernel is then only the fallback for systems the row kernel skipped)
+  for (int blk = blockIdx.x; blk < c.reduce_blocks; blk += gridDim.x) {
+    const int k = blk * blockDim.x + threadIdx.x;
+    F e = F(0);
+    if (k < c.n) {
+      const GridInfo<I> g = c.gi[b];
+      const LawCtx<F> lc = make_law_ctx(c, b);
+      EnergyVis<F, LAW> vis{c, lc, off};
+      vis.a = load_sorted(c, off, k, false);
+      vis.k = k;
+      vis.idx = c.perm[off + k];
+      vis.simple = !c.clumps && !g.any_bond;
+      vis.clump = vis.simple ? 0 : (c.sclump[off + k] & 0x7fffffff);
+      vis.interact = c.interact && c.interact[b];
+      vis.e = F(0);
+      if (fast_walk_ok(g) && !c.prune) {
+        const F pp[3] = {vis.a.x, vis.a.y, vis.a.z};
+        walk_runs<F, D, PERIODIC>(c, b, g, pp, vis);
       } else {
-        if (c.periodic) walk_runs<F, 2, true>(c, b, g, pp, vis);
-        else walk_runs<F, 2, false>(c, b, g, pp, vis);
+        walk_stencil<F>(c, b, k, nullptr, vis);
       }
-    } else {
-      walk_stencil<F>(c, b, k, nullptr, vis);
+      e = vis.e;
     }
-    e = vis.e;
+    const F tot = block_sum_256(e);
+    if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blk] = tot;
+    __syncthreads();  // block_sum_256's shared array is reused by the next trip
   }
-  const F tot = block_sum_256(e);
-  if (threadIdx.x == 0) c.partial[(size_t)b * c.reduce_blocks + blockIdx.x] = tot;
-  if (k == 0 && c.overflow) c.overflow[b] = (uint8_t)c.gi[b].hash_overflow;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.overflow) c.overflow[b] = (uint8_t)c.gi[b].hash_overflow;
 }
 
 template <typename F>
@@ -1469,8 +1470,14 @@ int celllist_energy(cudaStream_t s, Ctx<F>& c, F* energy, bool reuse) {
   int rc = reuse ? 0 : build_partition<F>(s, c, nullptr, 0, false);
   if (rc) return rc;
   if (c.prune && !reuse && (rc = cell_aabbs<F>(s, c, 1))) return rc;
-  const dim3 grid(c.reduce_blocks, c.batch);
-  JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L>), grid, kReduceBlock, s, c));
+  const dim3 grid(c.want_energy ? 1 : c.reduce_blocks, c.batch);
+  if (c.dim == 3) {
+    if (c.periodic) { JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L, 3, true>), grid, kReduceBlock, s, c)); }
+    else { JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L, 3, false>), grid, kReduceBlock, s, c)); }
+  } else {
+    if (c.periodic) { JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L, 2, true>), grid, kReduceBlock, s, c)); }
+    else { JDB_LAW_SWITCH(c.law, JDB_LAUNCH((k_pair_energy<F, L, 2, false>), grid, kReduceBlock, s, c)); }
+  }
   JDB_LAUNCH(k_final_sum<F>, dim3(c.batch), kReduceBlock, s, c.partial, c.reduce_blocks, energy);
   return 0;
 }
