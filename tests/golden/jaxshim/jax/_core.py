@@ -380,10 +380,24 @@ def _broadcast_prefix(prefix, tree, is_leaf=lambda x: x is None):
 
 
 # ----------------------------------------------------------------------------- transformations
+def fresh(tree):
+    """New pytree containers around the same (immutable) leaves.  JAX hands every traced function freshly
+    unflattened arguments, so a body that assigns to a field of a dataclass argument (the reference's hooks do:
+    ``state.pos_c = ...``) never changes the caller's object; the stand-in keeps that by rebuilding containers at
+    the same boundaries (jit, vmap, scan, while_loop, fori_loop, cond)."""
+    leaves, td = tree_flatten(tree)
+    return tree_unflatten(td, leaves)
+
+
 def jit(fun=None, **kw):
     if fun is None:
-        return lambda f: f
-    return fun
+        return lambda f: jit(f, **kw)
+
+    @functools.wraps(fun)
+    def jitted(*args, **kwargs):
+        return fun(*fresh(tuple(args)), **fresh(kwargs))
+
+    return jitted
 
 
 def named_call(fun=None, *, name=None):

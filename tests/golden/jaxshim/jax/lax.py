@@ -1,6 +1,6 @@
 """jax.lax control flow and a few primitives, eagerly on numpy."""
 import numpy as np
-from ._core import asarr, wrap, tree_flatten, tree_leaves, tree_map, tree_unflatten
+from ._core import asarr, fresh, wrap, tree_flatten, tree_leaves, tree_map, tree_unflatten
 
 
 def iota(dtype, size):
@@ -27,26 +27,29 @@ def select(pred, on_true, on_false):
     return wrap(np.where(np.asarray(pred), np.asarray(on_true), np.asarray(on_false)))
 
 
-def cond(pred, true_fun, false_fun, *operands):
+def cond(pred, true_fun, false_fun, *operands, **kw):
+    if "operand" in kw:  # the older single-operand spelling
+        operands = (kw["operand"],)
+    operands = fresh(tuple(operands))
     return true_fun(*operands) if bool(np.asarray(pred)) else false_fun(*operands)
 
 
 def switch(index, branches, *operands):
     i = int(np.clip(int(np.asarray(index)), 0, len(branches) - 1))
-    return branches[i](*operands)
+    return branches[i](*fresh(tuple(operands)))
 
 
 def while_loop(cond_fun, body_fun, init_val):
-    val = init_val
-    while bool(np.asarray(cond_fun(val))):
-        val = body_fun(val)
+    val = fresh(init_val)
+    while bool(np.asarray(cond_fun(fresh(val)))):
+        val = body_fun(fresh(val))
     return val
 
 
 def fori_loop(lower, upper, body_fun, init_val, **kw):
-    val = init_val
+    val = fresh(init_val)
     for i in range(int(np.asarray(lower)), int(np.asarray(upper))):
-        val = body_fun(asarr(i), val)
+        val = body_fun(asarr(i), fresh(val))
     return val
 
 
@@ -60,8 +63,8 @@ def scan(f, init, xs=None, length=None, reverse=False, unroll=1, **kw):
     order = range(n - 1, -1, -1) if reverse else range(n)
     for i in order:
         x = None if xs is None else tree_map(lambda a: wrap(np.asarray(a)[i]), xs)
-        carry, y = f(carry, x)
-        ys.append(y)
+        carry, y = f(fresh(carry), x)
+        ys.append(fresh(y))
     if reverse:
         ys = ys[::-1]
     if not ys:

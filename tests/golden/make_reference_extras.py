@@ -1,0 +1,232 @@
+"""Regenerate tests/golden/extras/*.npz:  python tests/golden/make_reference_extras.py   (build container only)
+
+REFERENCE OUTPUTS for the rows of SURVEY §8 beyond the cell-list step (see make_reference_golden.py for how
+the unmodified reference runs here on the numpy stand-in for JAX, and what that pins): the FIRE minimiser
+loop (f1), the Verlet NeighborList collider (f2), MultiCellList (f3), trajectory_rollout frames (f4), the naive
+collider with clumps and bonds, ForceManager with gravity and external forces on clumps, a reflecting box
+with restitution, and a vmap-batched step.  One .npz per feature: inputs (``in_*``), outputs, ``meta``.
+Consumed by tests/test_reference_golden.py (CPU: oracle vs these; GPU: CUDA path vs these)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+OUT = os.path.join(HERE, "extras")
+
+from helpers import make_inputs  # noqa: E402
+from make_reference_golden import build_reference  # noqa: E402
+
+F64 = np.float64
+
+
+def _np(x):
+    return np.array(np.asarray(x))
+
+
+def _state_out(st, prefix=""):
+    d = {prefix + f: _np(getattr(st, f)) for f in ("pos_c", "vel", "force", "torque", "ang_vel")}
+    d[prefix + "q"] = np.concatenate([_np(st.q.w), _np(st.q.xyz)], axis=-1)
+    return d
+
+
+def _inputs(inp):
+    return {f"in_{k}": np.asarray(v) for k, v in inp.items() if not isinstance(v, list)}
+
+
+def case_fire(jd, jax, jnp):
+    """minimizers/routines.py:151-383 + optimizers.py:150-340: K iterations with every stop test disabled, and a
+    run to convergence of the examples/jam_spheres.py recipe (bidisperse discs, phi 0.4, spring k = 1)."""
+    out = {}
+    for tag, dim, clumps, law in (("a", 2, False, "spring"), ("b", 3, True, "hertz")):
+        inp = make_inputs(90, dim, seed=3, dtype=F64, phi=0.7, poly=1.4, clumps=clumps, fixed_frac=0.05,
+                          nmat=2 if law != "spring" else 1)
+        kw = dict(domain="periodic", law=law, lin="verlet", rot="verletspiral", dt=1e-2, nmat=2 if law != "spring" else 1)
+        st, sy = build_reference(jd, jnp, inp, **kw)
+        K = 10
+        st, sy, steps, pe = jd.minimize(st, sy, max_steps=K, pe_tol=0.0, pe_diff_tol=0.0, force_tol=-1.0)
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out.update(_state_out(st, f"{tag}_"))
+        out[f"{tag}_steps"], out[f"{tag}_pe"] = _np(steps), _np(pe)
+        out[f"{tag}_pos_p_rot"] = _np(st._pos_p_rot)
+    # convergence: unjammed packing relaxes to pe / N <= 1e-16
+    rng = np.random.default_rng(0)
+    N = 60
+    rad = np.where(np.arange(N) < N // 2, 0.5, 0.7)
+    L = (np.sum(np.pi * rad**2) / 0.4) ** 0.5
+    pos = rng.uniform(0, L, (N, 2))
+    st = jd.State.create(jnp.asarray(pos), rad=jnp.asarray(rad), mass=jnp.ones(N))
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elastic", young=1.0, poisson=0.5, density=1.0)])
+    sy = jd.System.create(st.shape, dt=1e-2, collider_type="celllist", collider_kw=dict(state=st),
+                          domain_type="periodic", domain_kw=dict(box_size=jnp.asarray([L, L])),
+                          force_model_type="spring", mat_table=mt, minimizer_kw=dict(dt=1e-2))
+    st, sy, steps, pe = jd.minimize(st, sy, max_steps=5000)
+    out.update(c_in_pos=pos, c_in_rad=rad, c_in_box=np.array([L, L]), c_steps=_np(steps), c_pe=_np(pe),
+               c_pos_c=_np(st.pos_c))
+    return out, dict(K=10)
+
+
+def case_naive(jd, jax, jnp):
+    """colliders/naive.py with clumps, two materials and bonds (valid_interaction_mask, colliders/__init__.py)."""
+    out = {}
+    for tag, dim, law in (("a", 3, "cundallstrack"), ("b", 2, "hertz")):
+        inp = make_inputs(70, dim, seed=5, dtype=F64, phi=0.6, poly=1.3, clumps=True, nmat=2)
+        n = 70
+        bond = np.full((n, 1), -1, dtype=np.int64)
+        bond[::3, 0] = (np.arange(n)[::3] + 1) % n
+        st0, _ = build_reference(jd, jnp, inp, domain="periodic", law=law, lin="verlet", rot="verletspiral", dt=1e-3,
+                                 nmat=2, collider="naive")
+        kw = {k: jnp.asarray(inp[k]) for k in ("vel", "ang_vel", "rad", "mass", "clump_id", "pos_p", "q", "inertia",
+                                               "mat_id")}
+        st = jd.State.create(jnp.asarray(inp["pos"]), bond_id=jnp.asarray(bond), **kw)
+        _, sy = build_reference(jd, jnp, inp, domain="periodic", law=law, lin="verlet", rot="verletspiral", dt=1e-3,
+                                nmat=2, collider="naive")
+        st, sy = sy.collider.compute_force(st, sy)
+        e = sy.collider.compute_potential_energy(st, sy)[2]
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out[f"{tag}_in_bond"] = bond
+        out[f"{tag}_bond_id"] = _np(st.bond_id)  # symmetrised and padded by State.create
+        out[f"{tag}_force"], out[f"{tag}_torque"], out[f"{tag}_energy"] = _np(st.force), _np(st.torque), _np(e)
+    return out, {}
+
+
+def case_nlist(jd, jax, jnp):
+    """colliders/neighbor_list.py:286-480,542-669: list at build, forces, then steps with a thin skin so the
+    list is rebuilt on the way (n_build_times)."""
+    inp = make_inputs(150, 3, seed=31, dtype=F64, phi=0.6, poly=1.5, nmat=2)
+    kw = dict(domain="periodic", law="hertz", lin="verlet", rot="verletspiral", dt=2e-3, nmat=2)
+    ckw = dict(cutoff=1.0, skin=0.04)
+    st, sy = build_reference(jd, jnp, inp, collider="neighborlist", collider_kw=ckw, **kw)
+    out = _inputs(inp)
+    out["max_neighbors"] = np.asarray(int(sy.collider.max_neighbors))
+    st, sy = sy.collider.compute_force(st, sy)
+    out.update(nl0=_np(sy.collider.neighbor_list), builds0=_np(sy.collider.n_build_times), force0=_np(st.force),
+               torque0=_np(st.torque), overflow0=_np(sy.collider.overflow))
+    out["energy0"] = _np(sy.collider.compute_potential_energy(st, sy)[2])
+    builds = []
+    for _ in range(6):
+        st, sy = jd.System.step(st, sy, n=5)
+        builds.append(int(sy.collider.n_build_times))
+    out["builds"] = np.asarray(builds)
+    out["nl_after"] = _np(sy.collider.neighbor_list)
+    out.update(_state_out(st, "after_"))
+    return out, dict(steps=30, **ckw)
+
+
+def case_multicell(jd, jax, jnp):
+    """colliders/multi_cell_list.py:46-73,142-254 on a strongly polydisperse packing."""
+    out = {}
+    for tag, dim, law, domain in (("a", 3, "spring", "periodic"), ("b", 2, "hertz", "reflect")):
+        inp = make_inputs(130, dim, seed=17, dtype=F64, phi=0.55, poly=3.0, nmat=2)
+        st, sy = build_reference(jd, jnp, inp, domain=domain, law=law, lin="verlet", rot="verletspiral", dt=1e-3,
+                                 nmat=2, collider="multicelllist")
+        st, sy = sy.collider.compute_force(st, sy)
+        e = sy.collider.compute_potential_energy(st, sy)[2]
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out[f"{tag}_force"], out[f"{tag}_torque"], out[f"{tag}_energy"] = _np(st.force), _np(st.torque), _np(e)
+        out[f"{tag}_cell_size"] = _np(sy.collider.cell_size)
+        st, sy = jd.System.step(st, sy, n=2)
+        out.update(_state_out(st, f"{tag}_after_"))
+    return out, {}
+
+
+def case_force_manager(jd, jax, jnp):
+    """forces/force_manager.py: gravity + external force on particles, at the clump COM, external torque, then
+    apply (the clump segment sums) inside two steps."""
+    inp = make_inputs(90, 3, seed=9, dtype=F64, phi=0.5, poly=1.3, clumps=True)
+    g = np.array([0.0, -2.0, -9.81])
+    st, sy = build_reference(jd, jnp, inp, domain="periodic", law="spring", lin="verlet", rot="verletspiral",
+                             dt=1e-3, nmat=1, gravity=jnp.asarray(g))
+    rng = np.random.default_rng(4)
+    fe, fc, te = rng.normal(size=(90, 3)), rng.normal(size=(90, 3)), rng.normal(size=(90, 3))
+    sy = sy.force_manager.add_force(st, sy, jnp.asarray(fe))
+    sy = sy.force_manager.add_force(st, sy, jnp.asarray(fc), is_com=True)
+    sy = sy.force_manager.add_torque(st, sy, jnp.asarray(te))
+    out = _inputs(inp)
+    out.update(in_gravity=g, in_fe=fe, in_fc=fc, in_te=te)
+    st, sy = jd.System.step(st, sy, n=1)
+    out.update(_state_out(st, "s1_"))
+    st, sy = jd.System.step(st, sy, n=1)  # external buffers were cleared by the first apply
+    out.update(_state_out(st, "s2_"))
+    return out, {}
+
+
+def case_reflect(jd, jax, jnp):
+    """domains/reflect.py with restitution 0.7: fast spheres and clumps crossing the walls over 12 steps."""
+    out = {}
+    for tag, clumps in (("a", False), ("b", True)):
+        inp = make_inputs(80, 3, seed=21, dtype=F64, phi=0.35, poly=1.3, clumps=clumps)
+        inp["vel"] = inp["vel"] * 40.0
+        from helpers import MATS
+        mats = [jd.Material.create("elasticfrict", **MATS[0])]
+        mt = jd.MaterialTable.from_materials(mats, matcher=jd.MaterialMatchmaker.create("harmonic"))
+        kw = {k: jnp.asarray(inp[k]) for k in ("vel", "ang_vel", "rad", "mass", "clump_id", "pos_p", "q", "inertia")
+              if k in inp}
+        st = jd.State.create(jnp.asarray(inp["pos"]), **kw)
+        sy = jd.System.create(st.shape, dt=2e-3, collider_type="celllist", collider_kw=dict(state=st),
+                              domain_type="reflect",
+                              domain_kw=dict(box_size=jnp.asarray(inp["box"]), restitution_coefficient=0.7),
+                              force_model_type="spring", mat_table=mt)
+        st, sy = jd.System.step(st, sy, n=12)
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out.update(_state_out(st, f"{tag}_"))
+    return out, dict(steps=12, dt=2e-3, restitution=0.7)
+
+
+def case_rollout(jd, jax, jnp):
+    """system.py:606-699 trajectory_rollout(n=3, stride=2): frames after 2, 4, 6 steps; final state = last frame."""
+    inp = make_inputs(80, 2, seed=2, dtype=F64, phi=0.6, poly=1.2)
+    st, sy = build_reference(jd, jnp, inp, domain="periodic", law="spring", lin="verlet", rot="verletspiral",
+                             dt=1e-3, nmat=1)
+    st, sy, (fst, fsy) = jd.System.trajectory_rollout(st, sy, n=3, stride=2)
+    out = _inputs(inp)
+    out.update(frames_pos_c=_np(fst.pos_c), frames_vel=_np(fst.vel), frames_time=_np(fsy.time),
+               frames_step_count=_np(fsy.step_count), final_pos_c=_np(st.pos_c), final_time=_np(sy.time))
+    return out, dict(n=3, stride=2)
+
+
+def case_batched(jd, jax, jnp):
+    """vmap(System.step) over B = 3 independent systems (system.py:701-748 under jax.vmap)."""
+    B = 3
+    inps = [make_inputs(70, 2, seed=40 + b, dtype=F64, phi=0.6, poly=1.3, box=9.0) for b in range(B)]
+    pairs = [build_reference(jd, jnp, i, domain="periodic", law="spring", lin="verlet", rot="verletspiral", dt=1e-3,
+                             nmat=1) for i in inps]
+    stb = jd.State.stack([p[0] for p in pairs])
+    syb = jax.tree.map(lambda *xs: jnp.stack(xs), *[p[1] for p in pairs])
+    stb, syb = jax.vmap(lambda s, y: jd.System.step(s, y, n=2))(stb, syb)
+    out = {}
+    for b, i in enumerate(inps):
+        out.update({f"b{b}_{k}": v for k, v in _inputs(i).items()})
+    out.update(_state_out(stb))
+    return out, dict(B=B, steps=2)
+
+
+CASES = dict(fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+             force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched)
+
+
+def main():
+    from _ref_import import import_reference
+    jd = import_reference()
+    import jax
+    import jax.numpy as jnp
+    os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    for name, fn in CASES.items():
+        if only and name not in only:
+            continue
+        t = time.time()
+        with np.errstate(all="ignore"):
+            data, meta = fn(jd, jax, jnp)
+        meta = dict(meta, source="reference sources on tests/golden/jaxshim", dtype="float64")
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **data, meta=np.array(repr(meta)))
+        print(name, f"{time.time() - t:.1f} s", len(data), "arrays", flush=True)
+
+
+if __name__ == "__main__":
+    main()

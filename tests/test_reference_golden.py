@@ -1,0 +1,335 @@
+"""Parity against outputs of the REFERENCE ITSELF (tests/golden/extras/*.npz, tests/golden/ref_*.npz).
+
+The fixtures are produced in the build container by tests/golden/make_reference_extras.py /
+make_reference_golden.py: the unmodified sources under /root/reference run through their public API on a numpy
+stand-in for JAX (tests/golden/jaxshim), float64.  Here
+  * the CPU tests pin the ORACLE on them (integers bit for bit, floats to a few ulp of the field scale), and
+  * the ``gpu`` tests compare the CUDA path, through the C ABI, with the same reference numbers
+for the rows beyond the plain cell-list step: FIRE (f1), NeighborList (f2), MultiCellList (f3),
+trajectory_rollout (f4), naive collider with clumps + bonds, ForceManager buffers on clumps, reflecting box with
+restitution, batched step.  Neither needs /root/reference at run time."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import colliders as ocol, minimizers as omin
+from helpers import MATS, build_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+F64 = np.float64
+
+
+def load(name):
+    z = np.load(os.path.join(HERE, "golden", "extras", name + ".npz"))
+    meta = eval(str(z["meta"]), {"__builtins__": {}}, {})
+    return {k: z[k] for k in z.files if k != "meta"}, meta
+
+
+def sub(z, tag):
+    """make_inputs-style dict of the arrays stored as ``<tag>_in_*``."""
+    p = f"{tag}_in_" if tag else "in_"
+    return {k[len(p):]: v for k, v in z.items() if k.startswith(p)}
+
+
+def close(got, want, name, tol=1e-12, scale=None):
+    """|got - want| <= tol * max(field scale, 1e-300); ``tol`` 1e-12 is the north-star f64 bound."""
+    if hasattr(got, "detach"):
+        got = got.detach().cpu().numpy()
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    s = float(np.abs(want).max()) if scale is None else scale
+    err = float(np.abs(got - want).max()) if got.size else 0.0
+    assert err <= tol * max(s, 1e-300), f"{name}: max err {err:.3e}, scale {s:.3e}, tol {tol:.1e}"
+
+
+def state_close(st, z, prefix, tol=1e-12, q=True, fscale=None):
+    get = (lambda f: getattr(st, f))
+    for f in ("pos_c", "vel", "force", "ang_vel"):
+        close(get(f), z[prefix + f], prefix + f, tol)
+    fs = float(np.abs(z[prefix + "force"]).max()) if fscale is None else fscale
+    close(get("torque"), z[prefix + "torque"], prefix + "torque", tol, scale=max(fs, float(np.abs(z[prefix + "torque"]).max())))
+    if q:
+        if hasattr(st, "q_w"):
+            qq = np.concatenate([st.q_w, st.q_xyz], axis=-1)
+        else:
+            import torch
+            qq = torch.cat([st.q.w, st.q.xyz], dim=-1)
+        close(qq, z[prefix + "q"], prefix + "q", tol, scale=1.0)
+
+
+# ------------------------------------------------------------------------------------------- CPU: the oracle
+def test_oracle_fire_matches_reference():
+    z, meta = load("fire")
+    for tag, law in (("a", "spring"), ("b", "hertz")):
+        inp = sub(z, tag)
+        ost, osy = build_oracle(inp, dtype=F64, law=law, dt=1e-2, nmat=2 if law != "spring" else 1)
+        steps, pe, _ = omin.minimize(ost, osy, omin.FireConfig(1e-2), max_steps=meta["K"], pe_tol=0.0,
+                                     pe_diff_tol=0.0, force_tol=-1.0)
+        assert steps == int(z[f"{tag}_steps"]) == meta["K"]
+        assert abs(pe - float(z[f"{tag}_pe"])) <= 1e-12 * abs(float(z[f"{tag}_pe"]))
+        for f in ("pos_c", "force", "torque"):
+            close(getattr(ost, f), z[f"{tag}_{f}"], f, 1e-11, scale=float(np.abs(z[f"{tag}_force"]).max()) if f == "torque" else None)
+        close(np.concatenate([ost.q_w, ost.q_xyz], axis=1), z[f"{tag}_q"], "q", 1e-11, scale=1.0)
+        close(ost._pos_p_rot, z[f"{tag}_pos_p_rot"], "_pos_p_rot", 1e-11, scale=1.0)
+    ost, osy = _jam_oracle(z)
+    steps, pe, _ = omin.minimize(ost, osy, omin.FireConfig(1e-2), max_steps=5000)
+    assert steps == int(z["c_steps"]) and 10 < steps < 5000
+    assert pe <= 1e-16 and float(z["c_pe"]) <= 1e-16
+    close(ost.pos_c, z["c_pos_c"], "pos_c", 1e-9)
+
+
+def _jam_oracle(z):
+    N = len(z["c_in_rad"])
+    ost = oracle.create_state(z["c_in_pos"], rad=z["c_in_rad"], mass=np.ones(N))
+    mt = oracle.make_material_table([dict(young=1.0, poisson=0.5, density=1.0)], "harmonic")
+    osy = oracle.create_system(ost, dt=1e-2, collider_type="celllist", collider_kw=dict(state=ost),
+                               domain_type="periodic", domain_kw=dict(box_size=z["c_in_box"]), mat_table=mt)
+    return ost, osy
+
+
+def test_oracle_naive_matches_reference():
+    z, _ = load("naive")
+    for tag, law in (("a", "cundallstrack"), ("b", "hertz")):
+        inp = sub(z, tag)
+        inp["bond_id"] = inp.pop("bond")
+        ost, osy = build_oracle(inp, dtype=F64, law=law, collider="naive", nmat=2)
+        assert np.array_equal(ost.bond_id, z[f"{tag}_bond_id"])  # State.create's symmetrisation + padding
+        ocol.naive_compute_force(ost, osy)
+        close(ost.force, z[f"{tag}_force"], "force")
+        close(ost.torque, z[f"{tag}_torque"], "torque", scale=float(np.abs(z[f"{tag}_force"]).max()))
+        e = ocol.naive_compute_potential_energy(ost, osy)
+        close(np.asarray(e), z[f"{tag}_energy"], "energy")
+
+
+def test_oracle_neighborlist_matches_reference():
+    z, meta = load("nlist")
+    inp = sub(z, "")
+    ost, osy = build_oracle(inp, dtype=F64, law="hertz", collider="neighborlist", nmat=2, dt=2e-3,
+                            collider_kw=dict(cutoff=meta["cutoff"], skin=meta["skin"]))
+    assert osy.collider.max_neighbors == int(z["max_neighbors"])
+    ocol.compute_force(ost, osy)
+    assert np.array_equal(osy.collider.neighbor_list, z["nl0"]) and osy.collider.n_build_times == int(z["builds0"])
+    assert bool(osy.collider.overflow) == bool(z["overflow0"])
+    close(ost.force, z["force0"], "force0")
+    close(ost.torque, z["torque0"], "torque0", scale=float(np.abs(z["force0"]).max()))
+    close(np.asarray(ocol.compute_potential_energy(ost, osy)), z["energy0"], "energy0")
+    builds = []
+    for _ in range(6):
+        oracle.step(ost, osy, 5)
+        builds.append(int(osy.collider.n_build_times))
+    assert builds == list(z["builds"]) and builds[-1] > 2  # the thin skin forced rebuilds on the way
+    assert np.array_equal(osy.collider.neighbor_list, z["nl_after"])
+    state_close(ost, z, "after_", 1e-11)
+
+
+def test_oracle_multicelllist_matches_reference():
+    z, _ = load("multicell")
+    for tag, law, domain in (("a", "spring", "periodic"), ("b", "hertz", "reflect")):
+        ost, osy = build_oracle(sub(z, tag), dtype=F64, law=law, domain=domain, collider="multicelllist", nmat=2)
+        close(np.asarray(osy.collider.cell_size), z[f"{tag}_cell_size"], "cell_size", 1e-15)
+        ocol.compute_force(ost, osy)
+        close(ost.force, z[f"{tag}_force"], "force")
+        close(np.asarray(ocol.compute_potential_energy(ost, osy)), z[f"{tag}_energy"], "energy")
+        oracle.step(ost, osy, 2)
+        state_close(ost, z, f"{tag}_after_", 1e-11)
+
+
+def _member_count(clump_id):
+    cid = np.unique(np.asarray(clump_id), return_inverse=True)[1]
+    return np.bincount(cid)[cid].astype(np.float64)
+
+
+def test_oracle_force_manager_matches_reference():
+    z, _ = load("force_manager")
+    inp = sub(z, "")
+    g, fe, fc, te = (inp.pop(k) for k in ("gravity", "fe", "fc", "te"))
+    ost, osy = build_oracle(inp, dtype=F64, law="spring", gravity=g)
+    cnt = _member_count(inp["clump_id"])[:, None]
+    fm = osy.force_manager  # ForceManager.add_force / add_torque (force_manager.py:196-303): COM shares
+    fm.external_force = fm.external_force + fe
+    fm.external_force_com = fm.external_force_com + fc / cnt
+    fm.external_torque = fm.external_torque + te / cnt
+    oracle.step(ost, osy, 1)
+    state_close(ost, z, "s1_", 1e-12)
+    oracle.step(ost, osy, 1)
+    state_close(ost, z, "s2_", 1e-11)
+
+
+def test_oracle_reflect_restitution_matches_reference():
+    z, meta = load("reflect")
+    for tag in ("a", "b"):
+        ost, osy = build_oracle(sub(z, tag), dtype=F64, law="spring", domain="reflect", dt=meta["dt"],
+                                restitution=meta["restitution"])
+        oracle.step(ost, osy, meta["steps"])
+        state_close(ost, z, f"{tag}_", 1e-10)
+
+
+def test_oracle_rollout_frames_match_reference():
+    z, meta = load("rollout")
+    ost, osy = build_oracle(sub(z, ""), dtype=F64, law="spring")
+    for k in range(meta["n"]):  # a frame is saved AFTER its `stride` steps; the initial state is not a frame
+        oracle.step(ost, osy, meta["stride"])
+        close(ost.pos_c, z["frames_pos_c"][k], f"frame {k} pos_c")
+        close(ost.vel, z["frames_vel"][k], f"frame {k} vel")
+        assert int(z["frames_step_count"][k]) == (k + 1) * meta["stride"] == osy.step_count
+        assert abs(float(z["frames_time"][k]) - float(osy.time)) <= 1e-15
+    close(ost.pos_c, z["final_pos_c"], "final")
+
+
+def test_oracle_batched_step_matches_reference():
+    z, meta = load("batched")
+    for b in range(meta["B"]):
+        ost, osy = build_oracle(sub(z, f"b{b}"), dtype=F64, law="spring")
+        oracle.step(ost, osy, meta["steps"])
+        for f in ("pos_c", "vel", "force", "ang_vel"):
+            close(getattr(ost, f), z[f][b], f"{f}[{b}]")
+
+
+# ------------------------------------------------------------------------------------------- GPU: the CUDA path
+gpu = pytest.mark.gpu
+
+
+def _gpu(inp, **kw):
+    from helpers import build_gpu
+    return build_gpu(inp, dtype=F64, **kw)
+
+
+@gpu
+def test_cuda_fire_matches_reference():
+    import jaxdem_b200 as jd
+    import torch
+    z, meta = load("fire")
+    for tag, law in (("a", "spring"), ("b", "hertz")):
+        gst, gsy = _gpu(sub(z, tag), law=law, dt=1e-2, nmat=2 if law != "spring" else 1, collider="CellList")
+        gst, gsy, steps, pe = jd.minimizers.minimize(gst, gsy, max_steps=meta["K"], pe_tol=0.0, pe_diff_tol=0.0,
+                                                     force_tol=-1.0)
+        assert int(steps) == int(z[f"{tag}_steps"])
+        assert abs(float(pe) - float(z[f"{tag}_pe"])) <= 1e-10 * abs(float(z[f"{tag}_pe"]))
+        fs = float(np.abs(z[f"{tag}_force"]).max())
+        close(gst.pos_c, z[f"{tag}_pos_c"], "pos_c", 1e-10)
+        close(gst.force, z[f"{tag}_force"], "force", 1e-9)
+        close(gst.torque, z[f"{tag}_torque"], "torque", 1e-9, scale=fs)
+        close(torch.cat([gst.q.w, gst.q.xyz], dim=-1), z[f"{tag}_q"], "q", 1e-10, scale=1.0)
+    N = len(z["c_in_rad"])
+    L = [float(v) for v in z["c_in_box"]]
+    gst = jd.State.create(z["c_in_pos"], rad=z["c_in_rad"], mass=np.ones(N), dtype=torch.float64)
+    gsy = jd.System.create(gst.shape, dt=1e-2, minimizer=jd.minimizers.fire, minimizer_kw=dict(dt=1e-2),
+                           collider_type="CellList", collider_kw=dict(state=gst), domain_type="periodic",
+                           domain_kw=dict(box_size=L), force_model_type="spring",
+                           mat_table=jd.MaterialTable.from_materials(
+                               [jd.Material.create("elastic", young=1.0, poisson=0.5, density=1.0)]),
+                           dtype=torch.float64)
+    gst, gsy, steps, pe = jd.System.minimize(gst, gsy, max_steps=5000)
+    assert abs(int(steps) - int(z["c_steps"])) <= 2 and float(pe) <= 1e-16  # the reference's own stop iteration
+
+
+@gpu
+def test_cuda_naive_matches_reference():
+    z, _ = load("naive")
+    for tag, law in (("a", "cundallstrack"), ("b", "hertz")):
+        inp = sub(z, tag)
+        inp["bond_id"] = inp.pop("bond")
+        gst, gsy = _gpu(inp, law=law, collider="naive", nmat=2)
+        assert np.array_equal(gst.bond_id.cpu().numpy(), z[f"{tag}_bond_id"])
+        gsy.collider.compute_force(gst, gsy)
+        fs = float(np.abs(z[f"{tag}_force"]).max())
+        close(gst.force, z[f"{tag}_force"], "force", 1e-11)
+        close(gst.torque, z[f"{tag}_torque"], "torque", 1e-11, scale=fs)
+        _, _, e = gsy.collider.compute_potential_energy(gst, gsy)
+        close(e.cpu().numpy().reshape(()), z[f"{tag}_energy"], "energy", 1e-11)
+
+
+@gpu
+def test_cuda_neighborlist_matches_reference():
+    import jaxdem_b200 as jd
+    z, meta = load("nlist")
+    gst, gsy = _gpu(sub(z, ""), law="hertz", collider="NeighborList", nmat=2, dt=2e-3,
+                    collider_kw=dict(cutoff=meta["cutoff"], skin=meta["skin"]))
+    assert gsy.collider.max_neighbors == int(z["max_neighbors"])
+    gsy.collider.compute_force(gst, gsy)
+    assert np.array_equal(gsy.collider.neighbor_list.cpu().numpy(), z["nl0"])
+    assert int(gsy.collider.n_build_times) == int(z["builds0"])
+    close(gst.force, z["force0"], "force0", 1e-11)
+    _, _, e = gsy.collider.compute_potential_energy(gst, gsy)
+    close(e.cpu().numpy().reshape(()), z["energy0"], "energy0", 1e-11)
+    builds = []
+    for _ in range(6):
+        jd.System.step(gst, gsy, n=5)
+        builds.append(int(gsy.collider.n_build_times))
+    assert builds == list(z["builds"])  # the device-side rebuild gate fires on the reference's steps
+    assert np.array_equal(gsy.collider.neighbor_list.cpu().numpy(), z["nl_after"])
+    state_close(gst, z, "after_", 1e-9)
+
+
+@gpu
+def test_cuda_multicelllist_matches_reference():
+    import jaxdem_b200 as jd
+    z, _ = load("multicell")
+    for tag, law, domain in (("a", "spring", "periodic"), ("b", "hertz", "reflect")):
+        gst, gsy = _gpu(sub(z, tag), law=law, domain=domain, collider="MultiCellList", nmat=2)
+        gsy.collider.compute_force(gst, gsy)
+        close(gst.force, z[f"{tag}_force"], "force", 1e-11)
+        _, _, e = gsy.collider.compute_potential_energy(gst, gsy)
+        close(e.cpu().numpy().reshape(()), z[f"{tag}_energy"], "energy", 1e-11)
+        jd.System.step(gst, gsy, n=2)
+        state_close(gst, z, f"{tag}_after_", 1e-10)
+
+
+@gpu
+def test_cuda_force_manager_matches_reference():
+    import jaxdem_b200 as jd
+    z, _ = load("force_manager")
+    inp = sub(z, "")
+    g, fe, fc, te = (inp.pop(k) for k in ("gravity", "fe", "fc", "te"))
+    gst, gsy = _gpu(inp, law="spring", gravity=g)
+    gsy = gsy.force_manager.add_force(gst, gsy, fe)
+    gsy = gsy.force_manager.add_force(gst, gsy, fc, is_com=True)
+    gsy = gsy.force_manager.add_torque(gst, gsy, te)
+    jd.System.step(gst, gsy, n=1)
+    state_close(gst, z, "s1_", 1e-11)
+    jd.System.step(gst, gsy, n=1)
+    state_close(gst, z, "s2_", 1e-10)
+
+
+@gpu
+def test_cuda_reflect_restitution_matches_reference():
+    import jaxdem_b200 as jd
+    z, meta = load("reflect")
+    for tag in ("a", "b"):
+        gst, gsy = _gpu(sub(z, tag), law="spring", domain="reflect", dt=meta["dt"], restitution=meta["restitution"])
+        jd.System.step(gst, gsy, n=meta["steps"])
+        state_close(gst, z, f"{tag}_", 1e-9)
+
+
+@gpu
+def test_cuda_rollout_frames_match_reference():
+    import jaxdem_b200 as jd
+    z, meta = load("rollout")
+    gst, gsy = _gpu(sub(z, ""), law="spring")
+    gst, gsy, (fst, fsy) = jd.System.trajectory_rollout(gst, gsy, n=meta["n"], stride=meta["stride"])
+    close(fst.pos_c, z["frames_pos_c"], "frames pos_c", 1e-11)
+    close(fst.vel, z["frames_vel"], "frames vel", 1e-11)
+    assert [int(v) for v in fsy.step_count.reshape(-1)] == [int(v) for v in z["frames_step_count"]]
+    close(fsy.time.reshape(-1), z["frames_time"], "frames time", 1e-13)
+    close(gst.pos_c, z["final_pos_c"], "final", 1e-11)
+
+
+@gpu
+def test_cuda_batched_step_matches_reference():
+    import jaxdem_b200 as jd
+    import torch
+    z, meta = load("batched")
+    B = meta["B"]
+    singles = [_gpu(sub(z, f"b{b}"), law="spring") for b in range(B)]
+    stb = jd.State.stack([s for s, _ in singles])
+    box = [[float(v) for v in z[f"b{b}_in_box"]] for b in range(B)]
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **MATS[0])],
+                                         matcher=jd.MaterialMatchmaker.create("harmonic"))
+    syb = jd.System.create(stb.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=singles[0][0]),
+                           domain_type="periodic", domain_kw=dict(box_size=box), force_model_type="spring",
+                           mat_table=mt, dtype=torch.float64, device="cuda")
+    jd.System.step(stb, syb, n=meta["steps"])
+    for f in ("pos_c", "vel", "force", "ang_vel"):
+        close(getattr(stb, f), z[f], f, 1e-11)
