@@ -8,7 +8,9 @@ vendored, not installed here).  Two optax functions are on the path and are rest
 definitions: ``optax.apply_updates(params, updates) = params + updates`` and
 ``optax.safe_norm(x, min_norm, axis=-1, keepdims=True)`` = ``where(norm <= min_norm, min_norm,
 norm(where(norm <= min_norm, 1, x)))`` — i.e. the row norm, floored at ``min_norm``.  The reference holds no test
-for ``minimizers/``, so this restatement is anchored on its call sites only: parity unpinned.
+for ``minimizers/``; this restatement is pinned on outputs of the reference's own ``minimize`` / ``fire``
+run on the numpy stand-in for JAX (tests/golden/extras/fire.npz, tests/test_reference_golden.py): iterates after K
+iterations, energy, and the stop iteration of a run to convergence, float64.
 """
 
 from __future__ import annotations

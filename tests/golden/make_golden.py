@@ -1,13 +1,14 @@
 """Regenerate tests/golden/*.npz:  python tests/golden/make_golden.py
 
-What these fixtures are — and are not.  The reference (cdelv/JaxDEM) is pure JAX, JAX is not installed in the
-build image or on the GPU box and there is no network, so NO fixture here comes from running the reference
-(parity is unpinned beyond the reference's closed-form test values, which
-tests/test_oracle_pins.py holds).  They are produced by the CPU oracle (oracle/*.py, the line-by-line
-restatement of the reference path) on small seeded inputs and committed so that
+What these fixtures are — and are not.  The six files this script writes (c2_like_f32 ... hertz_free_f32) are
+ORACLE outputs (oracle/*.py, the line-by-line restatement of the reference path) on small seeded inputs, in the
+dtypes of the BASELINE configurations (float32 included).  They are committed so that
   * the oracle itself cannot drift unnoticed (tests/test_host_cpu.py::test_oracle_matches_golden, CPU), and
   * the CUDA path is compared with stored numbers as well as with a live oracle run
     (tests/test_gpu_parity.py::test_cuda_matches_golden, GPU).
+REFERENCE outputs live next to them as ref_*.npz and extras/*.npz (make_reference_golden.py /
+make_reference_extras.py: the unmodified reference sources on a numpy stand-in for JAX, float64); both tests above
+run over those files too, which is what pins the oracle and the CUDA path on the reference itself.
 Every case stores its inputs and its outputs; integer results are compared bit for bit, floats to rel 1e-12
 (f64) / 1e-5 (f32) of the field scale."""
 import os

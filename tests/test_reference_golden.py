@@ -308,11 +308,11 @@ def test_cuda_rollout_frames_match_reference():
     import jaxdem_b200 as jd
     z, meta = load("rollout")
     gst, gsy = _gpu(sub(z, ""), law="spring")
-    gst, gsy, (fst, fsy) = jd.System.trajectory_rollout(gst, gsy, n=meta["n"], stride=meta["stride"])
-    close(fst.pos_c, z["frames_pos_c"], "frames pos_c", 1e-11)
-    close(fst.vel, z["frames_vel"], "frames vel", 1e-11)
-    assert [int(v) for v in fsy.step_count.reshape(-1)] == [int(v) for v in z["frames_step_count"]]
-    close(fsy.time.reshape(-1), z["frames_time"], "frames time", 1e-13)
+    gst, gsy, traj = jd.System.trajectory_rollout(gst, gsy, n=meta["n"], stride=meta["stride"])
+    close(traj["pos_c"], z["frames_pos_c"], "frames pos_c", 1e-11)
+    close(traj["vel"], z["frames_vel"], "frames vel", 1e-11)
+    assert [int(v) for v in traj.step_count.reshape(-1).tolist()] == [int(v) for v in z["frames_step_count"]]
+    close(traj.time.reshape(-1), z["frames_time"], "frames time", 1e-13)
     close(gst.pos_c, z["final_pos_c"], "final", 1e-11)
 
 
@@ -324,11 +324,12 @@ def test_cuda_batched_step_matches_reference():
     B = meta["B"]
     singles = [_gpu(sub(z, f"b{b}"), law="spring") for b in range(B)]
     stb = jd.State.stack([s for s, _ in singles])
+    big = max(singles, key=lambda p: float(p[0].rad.max()))[0]  # one cell size that serves every system
     box = [[float(v) for v in z[f"b{b}_in_box"]] for b in range(B)]
     mt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **MATS[0])],
                                          matcher=jd.MaterialMatchmaker.create("harmonic"))
-    syb = jd.System.create(stb.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=singles[0][0]),
-                           domain_type="periodic", domain_kw=dict(box_size=box), force_model_type="spring",
+    syb = jd.System.create(stb.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=big),
+                           domain_type="periodic", domain_kw=dict(box_size=np.asarray(box)), force_model_type="spring",
                            mat_table=mt, dtype=torch.float64, device="cuda")
     jd.System.step(stb, syb, n=meta["steps"])
     for f in ("pos_c", "vel", "force", "ang_vel"):
