@@ -11,8 +11,8 @@ class _Config:
     jax_enable_x64 = True
 
     def update(self, key, value):
-        if key == "jax_enable_x64" and not value:
-            raise NotImplementedError("the numpy stand-in emulates jax_enable_x64=True only")
+        if key == "jax_enable_x64":
+            _core.set_x64(value)
         setattr(self, key, value)
 
 

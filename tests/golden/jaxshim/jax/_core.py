@@ -15,6 +15,45 @@ import functools
 
 import numpy as np
 
+# ----------------------------------------------------------------------------- 32-bit mode
+# jax_enable_x64=False (JAX's default): 64-bit dtypes do not exist, every array is truncated to its 32-bit
+# counterpart.  The stand-in applies that after EVERY operation (``canon`` in ``wrap`` / ``__array_wrap__``), so
+# no float64 / int64 array ever reaches the next operation.  Where numpy's promotion differs from JAX's
+# (int32 op float32 -> float64 in numpy, float32 in JAX) the operation runs in float64 on operands that are
+# exactly representable and is rounded once more to float32; for + - * / sqrt that equals the float32
+# operation bit for bit (53 >= 2 * 24 + 2: the double rounding is innocuous).  Python scalars are weak in both
+# (NEP 50).
+X64 = True
+_TRUNC = {np.dtype(np.float64): np.float32, np.dtype(np.int64): np.int32, np.dtype(np.uint64): np.uint32,
+          np.dtype(np.complex128): np.complex64}
+
+
+def set_x64(on):
+    global X64
+    X64 = bool(on)
+
+
+def canon_dtype(dtype):
+    """dtype request -> the dtype JAX would give in the current mode (None stays None)."""
+    if dtype is None:
+        return None
+    if dtype is int:
+        dtype = np.int64
+    elif dtype is float:
+        dtype = np.float64
+    elif dtype is bool:
+        dtype = np.bool_
+    dt = np.dtype(dtype)
+    if not X64 and dt in _TRUNC:
+        return np.dtype(_TRUNC[dt])
+    return dt
+
+
+def canon(a):
+    if not X64 and a.dtype in _TRUNC:
+        return a.astype(_TRUNC[a.dtype])
+    return a
+
 
 # ----------------------------------------------------------------------------- arrays
 def _is_int_index(k):
@@ -122,7 +161,7 @@ class Arr(np.ndarray):
         raise TypeError("jax arrays are immutable; use .at[...].set()")
 
     def __array_wrap__(self, obj, context=None, return_scalar=False):
-        return np.asarray(obj).view(Arr)
+        return canon(np.asarray(obj)).view(Arr)
 
     def __hash__(self):
         raise TypeError("unhashable type: Arr")
@@ -151,6 +190,10 @@ class Arr(np.ndarray):
         base = getattr(np.ndarray, name)
 
         def f(self, *a, **k):
+            if name == "astype":
+                a = (canon_dtype(a[0]),) + a[1:] if a else a
+                if "dtype" in k:
+                    k["dtype"] = canon_dtype(k["dtype"])
             return wrap(base(np.asarray(self), *a, **k))
         f.__name__ = name
         return f
@@ -170,9 +213,9 @@ def wrap(x):
     if isinstance(x, Arr):
         return x
     if isinstance(x, np.ndarray):
-        return x.view(Arr)
+        return canon(x).view(Arr)
     if isinstance(x, (np.generic,)):
-        return np.asarray(x).view(Arr)
+        return canon(np.asarray(x)).view(Arr)
     if isinstance(x, tuple) and not hasattr(x, "_fields"):
         return tuple(wrap(v) for v in x)
     if isinstance(x, list):
@@ -181,15 +224,10 @@ def wrap(x):
 
 
 def asarr(x, dtype=None):
-    if dtype is int:
-        dtype = np.int64
-    elif dtype is float:
-        dtype = np.float64
-    elif dtype is bool:
-        dtype = np.bool_
+    dtype = canon_dtype(dtype)
     if isinstance(x, Arr) and (dtype is None or x.dtype == dtype):
         return x
-    return np.array(x, dtype=dtype, copy=True).view(Arr)  # never alias caller-owned numpy memory
+    return canon(np.array(x, dtype=dtype, copy=True)).view(Arr)  # never alias caller-owned numpy memory
 
 
 # ----------------------------------------------------------------------------- pytrees

@@ -4,13 +4,13 @@ import types
 
 import numpy as _np
 
-from ._core import Arr, asarr, wrap
+from ._core import Arr, asarr, canon, canon_dtype, wrap
 
 ndarray = Arr
 pi, inf, nan, e, newaxis = _np.pi, _np.inf, _np.nan, _np.e, None
 
 _TYPES = ("float16", "float32", "float64", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64",
-          "bool_", "integer", "floating", "number", "inexact", "complex64", "complex128", "dtype", "iinfo", "finfo",
+          "bool_", "integer", "floating", "number", "inexact", "complex64", "complex128", "dtype",
           "issubdtype", "promote_types", "result_type", "can_cast", "shape", "ndim", "size", "isscalar",
           "signedinteger", "unsignedinteger", "generic")
 for _t in _TYPES:
@@ -18,7 +18,15 @@ for _t in _TYPES:
 
 
 def _dt(dtype):
-    return {int: _np.int64, float: _np.float64, bool: _np.bool_}.get(dtype, dtype)
+    return canon_dtype(dtype)
+
+
+def iinfo(dtype):
+    return _np.iinfo(canon_dtype(dtype))
+
+
+def finfo(dtype):
+    return _np.finfo(canon_dtype(dtype))
 
 
 def asarray(x, dtype=None, **kw):
@@ -26,44 +34,44 @@ def asarray(x, dtype=None, **kw):
 
 
 def array(x, dtype=None, copy=True, **kw):
-    return _np.array(x, dtype=_dt(dtype), copy=True).view(Arr)
+    return canon(_np.array(x, dtype=_dt(dtype), copy=True)).view(Arr)
 
 
 def zeros(shape, dtype=float, **kw):
-    return _np.zeros(shape, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.zeros(shape, dtype=_dt(dtype))).view(Arr)
 
 
 def ones(shape, dtype=float, **kw):
-    return _np.ones(shape, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.ones(shape, dtype=_dt(dtype))).view(Arr)
 
 
 def empty(shape, dtype=float, **kw):
-    return _np.zeros(shape, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.zeros(shape, dtype=_dt(dtype))).view(Arr)
 
 
 def full(shape, fill_value, dtype=None, **kw):
-    return _np.full(shape, fill_value, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.full(shape, fill_value, dtype=_dt(dtype))).view(Arr)
 
 
 def arange(*a, dtype=None, **kw):
-    return _np.arange(*[_np.asarray(v).item() if isinstance(v, _np.ndarray) else v for v in a],
-                      dtype=_dt(dtype)).view(Arr)
+    return canon(_np.arange(*[_np.asarray(v).item() if isinstance(v, _np.ndarray) else v for v in a],
+                            dtype=_dt(dtype))).view(Arr)
 
 
 def eye(n, m=None, k=0, dtype=float, **kw):
-    return _np.eye(n, m, k, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.eye(n, m, k, dtype=_dt(dtype))).view(Arr)
 
 
 def zeros_like(x, dtype=None, **kw):
-    return _np.zeros_like(_np.asarray(x), dtype=_dt(dtype)).view(Arr)
+    return canon(_np.zeros_like(_np.asarray(x), dtype=_dt(dtype))).view(Arr)
 
 
 def ones_like(x, dtype=None, **kw):
-    return _np.ones_like(_np.asarray(x), dtype=_dt(dtype)).view(Arr)
+    return canon(_np.ones_like(_np.asarray(x), dtype=_dt(dtype))).view(Arr)
 
 
 def full_like(x, v, dtype=None, **kw):
-    return _np.full_like(_np.asarray(x), v, dtype=_dt(dtype)).view(Arr)
+    return canon(_np.full_like(_np.asarray(x), v, dtype=_dt(dtype))).view(Arr)
 
 
 def bincount(x, weights=None, minlength=0, *, length=None):

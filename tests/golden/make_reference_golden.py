@@ -27,7 +27,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
-CASES = [  # name, n, dim, domain, law, rot, clumps
+CASES = [  # name (its suffix is the dtype), n, dim, domain, law, rot, clumps
+    ("ref_c2_like_f32", 160, 3, "periodic", "spring", "", False),
+    ("ref_c3_like_f32", 140, 3, "periodic", "cundallstrack", "verletspiral", False),
+    ("ref_c5_like_f32", 140, 3, "periodic", "cundallstrack", "verletspiral", True),
+    ("ref_hertz_free_f32", 140, 2, "free", "hertz", "spiral", False),
     ("ref_c2_like_f64", 160, 3, "periodic", "spring", "", False),
     ("ref_c3_like_f64", 140, 3, "periodic", "cundallstrack", "verletspiral", False),
     ("ref_c4_like_f64", 160, 2, "periodic", "spring", "verletspiral", False),
@@ -61,7 +65,8 @@ def run_case(jd, jax, jnp, name, n, dim, domain, law, rot, clumps):
     from helpers import make_inputs
     from jaxdem.colliders.cell_list import _get_spatial_partition
     from jaxdem.colliders.cell_list import _dedup_stencil_hashes
-    dtype = np.float64
+    dtype = np.float32 if name.endswith("_f32") else np.float64
+    jax.config.update("jax_enable_x64", dtype == np.float64)  # float32 = JAX's default mode: no 64-bit arrays at all
     nmat = 2 if law != "spring" else 1
     inp = make_inputs(n, dim, seed=sum(map(ord, name)), dtype=dtype, phi=0.55, clumps=clumps, poly=1.3, nmat=nmat)
     lin = "euler" if domain == "free" else "verlet"
@@ -82,7 +87,9 @@ def run_case(jd, jax, jnp, name, n, dim, domain, law, rot, clumps):
         out[f"{f}_after"] = getattr(st, f)
     out["q_after"] = np.concatenate([np.asarray(st.q.w), np.asarray(st.q.xyz)], axis=1)
     out = {k: np.array(np.asarray(v)) for k, v in out.items()}
-    meta = dict(n=n, dim=dim, domain=domain, law=law, lin=lin, rot=rot, clumps=clumps, dtype="float64",
+    assert all(v.dtype in (np.dtype(dtype), np.dtype(np.int32 if dtype == np.float32 else np.int64), np.dtype(bool))
+               for v in out.values()), {k: v.dtype for k, v in out.items()}
+    meta = dict(n=n, dim=dim, domain=domain, law=law, lin=lin, rot=rot, clumps=clumps, dtype=np.dtype(dtype).name,
                 steps=STEPS, nmat=nmat, source="reference sources on tests/golden/jaxshim")
     inputs = {f"in_{k}": np.asarray(v) for k, v in inp.items() if not isinstance(v, list)}
     return dict(**inputs, **out, meta=np.array(repr(meta)))
