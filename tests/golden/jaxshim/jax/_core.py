@@ -157,6 +157,11 @@ class Arr(np.ndarray):
             r = np.asarray(r).view(Arr)
         return r
 
+    def __iter__(self):  # by shape: the sequence protocol would never see an IndexError from the clamping gather
+        if self.ndim == 0:
+            raise TypeError("iteration over a 0-d array")
+        return (self[i] for i in range(self.shape[0]))
+
     def __setitem__(self, key, value):  # JAX arrays are immutable; the reference never does this
         raise TypeError("jax arrays are immutable; use .at[...].set()")
 

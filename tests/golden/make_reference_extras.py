@@ -22,7 +22,7 @@ OUT = os.path.join(HERE, "extras")
 from helpers import make_inputs  # noqa: E402
 from make_reference_golden import build_reference  # noqa: E402
 
-F64 = np.float64
+F64 = np.float64  # dtype of the case being generated (main() switches it for the *_f32 variants)
 
 
 def _np(x):
@@ -139,11 +139,11 @@ def case_force_manager(jd, jax, jnp):
     """forces/force_manager.py: gravity + external force on particles, at the clump COM, external torque, then
     apply (the clump segment sums) inside two steps."""
     inp = make_inputs(90, 3, seed=9, dtype=F64, phi=0.5, poly=1.3, clumps=True)
-    g = np.array([0.0, -2.0, -9.81])
+    g = np.array([0.0, -2.0, -9.81], dtype=F64)
     st, sy = build_reference(jd, jnp, inp, domain="periodic", law="spring", lin="verlet", rot="verletspiral",
                              dt=1e-3, nmat=1, gravity=jnp.asarray(g))
     rng = np.random.default_rng(4)
-    fe, fc, te = rng.normal(size=(90, 3)), rng.normal(size=(90, 3)), rng.normal(size=(90, 3))
+    fe, fc, te = (rng.normal(size=(90, 3)).astype(F64) for _ in range(3))
     sy = sy.force_manager.add_force(st, sy, jnp.asarray(fe))
     sy = sy.force_manager.add_force(st, sy, jnp.asarray(fc), is_com=True)
     sy = sy.force_manager.add_torque(st, sy, jnp.asarray(te))
@@ -207,7 +207,9 @@ def case_batched(jd, jax, jnp):
 
 
 CASES = dict(fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
-             force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched)
+             force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
+             nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
+             reflect_f32=case_reflect, batched_f32=case_batched)
 
 
 def main():
@@ -221,9 +223,15 @@ def main():
         if only and name not in only:
             continue
         t = time.time()
+        global F64
+        F64 = np.float32 if name.endswith("_f32") else np.float64
+        jax.config.update("jax_enable_x64", F64 == np.float64)  # float32 = JAX's default mode, no 64-bit arrays
         with np.errstate(all="ignore"):
             data, meta = fn(jd, jax, jnp)
-        meta = dict(meta, source="reference sources on tests/golden/jaxshim", dtype="float64")
+        bad = {k: v.dtype for k, v in data.items() if not k.startswith(("in_", "a_in", "b_in", "c_in", "b0_", "b1_", "b2_"))
+               and v.dtype.kind == "f" and v.dtype != np.dtype(F64)}
+        assert not bad, bad
+        meta = dict(meta, source="reference sources on tests/golden/jaxshim", dtype=np.dtype(F64).name)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **data, meta=np.array(repr(meta)))
         print(name, f"{time.time() - t:.1f} s", len(data), "arrays", flush=True)
 

@@ -21,9 +21,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 F64 = np.float64
 
 
+_DT = [F64]  # dtype of the fixture loaded last: float32 fixtures widen the f64 tolerances by 1e7 (<= 1e-4)
+BOTH = pytest.mark.parametrize("sfx", ["", "_f32"], ids=["f64", "f32"])
+
+
 def load(name):
     z = np.load(os.path.join(HERE, "golden", "extras", name + ".npz"))
     meta = eval(str(z["meta"]), {"__builtins__": {}}, {})
+    _DT[0] = np.dtype(meta["dtype"]).type
     return {k: z[k] for k in z.files if k != "meta"}, meta
 
 
@@ -41,6 +46,8 @@ def close(got, want, name, tol=1e-12, scale=None):
     assert got.shape == want.shape, (name, got.shape, want.shape)
     s = float(np.abs(want).max()) if scale is None else scale
     err = float(np.abs(got - want).max()) if got.size else 0.0
+    if _DT[0] == np.float32:
+        tol = min(1e-4, tol * 1e7)
     assert err <= tol * max(s, 1e-300), f"{name}: max err {err:.3e}, scale {s:.3e}, tol {tol:.1e}"
 
 
@@ -64,7 +71,7 @@ def test_oracle_fire_matches_reference():
     z, meta = load("fire")
     for tag, law in (("a", "spring"), ("b", "hertz")):
         inp = sub(z, tag)
-        ost, osy = build_oracle(inp, dtype=F64, law=law, dt=1e-2, nmat=2 if law != "spring" else 1)
+        ost, osy = build_oracle(inp, dtype=_DT[0], law=law, dt=1e-2, nmat=2 if law != "spring" else 1)
         steps, pe, _ = omin.minimize(ost, osy, omin.FireConfig(1e-2), max_steps=meta["K"], pe_tol=0.0,
                                      pe_diff_tol=0.0, force_tol=-1.0)
         assert steps == int(z[f"{tag}_steps"]) == meta["K"]
@@ -94,7 +101,7 @@ def test_oracle_naive_matches_reference():
     for tag, law in (("a", "cundallstrack"), ("b", "hertz")):
         inp = sub(z, tag)
         inp["bond_id"] = inp.pop("bond")
-        ost, osy = build_oracle(inp, dtype=F64, law=law, collider="naive", nmat=2)
+        ost, osy = build_oracle(inp, dtype=_DT[0], law=law, collider="naive", nmat=2)
         assert np.array_equal(ost.bond_id, z[f"{tag}_bond_id"])  # State.create's symmetrisation + padding
         ocol.naive_compute_force(ost, osy)
         close(ost.force, z[f"{tag}_force"], "force")
@@ -103,10 +110,11 @@ def test_oracle_naive_matches_reference():
         close(np.asarray(e), z[f"{tag}_energy"], "energy")
 
 
-def test_oracle_neighborlist_matches_reference():
-    z, meta = load("nlist")
+@BOTH
+def test_oracle_neighborlist_matches_reference(sfx):
+    z, meta = load("nlist" + sfx)
     inp = sub(z, "")
-    ost, osy = build_oracle(inp, dtype=F64, law="hertz", collider="neighborlist", nmat=2, dt=2e-3,
+    ost, osy = build_oracle(inp, dtype=_DT[0], law="hertz", collider="neighborlist", nmat=2, dt=2e-3,
                             collider_kw=dict(cutoff=meta["cutoff"], skin=meta["skin"]))
     assert osy.collider.max_neighbors == int(z["max_neighbors"])
     ocol.compute_force(ost, osy)
@@ -124,10 +132,11 @@ def test_oracle_neighborlist_matches_reference():
     state_close(ost, z, "after_", 1e-11)
 
 
-def test_oracle_multicelllist_matches_reference():
-    z, _ = load("multicell")
+@BOTH
+def test_oracle_multicelllist_matches_reference(sfx):
+    z, _ = load("multicell" + sfx)
     for tag, law, domain in (("a", "spring", "periodic"), ("b", "hertz", "reflect")):
-        ost, osy = build_oracle(sub(z, tag), dtype=F64, law=law, domain=domain, collider="multicelllist", nmat=2)
+        ost, osy = build_oracle(sub(z, tag), dtype=_DT[0], law=law, domain=domain, collider="multicelllist", nmat=2)
         close(np.asarray(osy.collider.cell_size), z[f"{tag}_cell_size"], "cell_size", 1e-15)
         ocol.compute_force(ost, osy)
         close(ost.force, z[f"{tag}_force"], "force")
@@ -141,12 +150,13 @@ def _member_count(clump_id):
     return np.bincount(cid)[cid].astype(np.float64)
 
 
-def test_oracle_force_manager_matches_reference():
-    z, _ = load("force_manager")
+@BOTH
+def test_oracle_force_manager_matches_reference(sfx):
+    z, _ = load("force_manager" + sfx)
     inp = sub(z, "")
     g, fe, fc, te = (inp.pop(k) for k in ("gravity", "fe", "fc", "te"))
-    ost, osy = build_oracle(inp, dtype=F64, law="spring", gravity=g)
-    cnt = _member_count(inp["clump_id"])[:, None]
+    ost, osy = build_oracle(inp, dtype=_DT[0], law="spring", gravity=g)
+    cnt = _member_count(inp["clump_id"]).astype(_DT[0])[:, None]
     fm = osy.force_manager  # ForceManager.add_force / add_torque (force_manager.py:196-303): COM shares
     fm.external_force = fm.external_force + fe
     fm.external_force_com = fm.external_force_com + fc / cnt
@@ -157,10 +167,11 @@ def test_oracle_force_manager_matches_reference():
     state_close(ost, z, "s2_", 1e-11)
 
 
-def test_oracle_reflect_restitution_matches_reference():
-    z, meta = load("reflect")
+@BOTH
+def test_oracle_reflect_restitution_matches_reference(sfx):
+    z, meta = load("reflect" + sfx)
     for tag in ("a", "b"):
-        ost, osy = build_oracle(sub(z, tag), dtype=F64, law="spring", domain="reflect", dt=meta["dt"],
+        ost, osy = build_oracle(sub(z, tag), dtype=_DT[0], law="spring", domain="reflect", dt=meta["dt"],
                                 restitution=meta["restitution"])
         oracle.step(ost, osy, meta["steps"])
         state_close(ost, z, f"{tag}_", 1e-10)
@@ -168,7 +179,7 @@ def test_oracle_reflect_restitution_matches_reference():
 
 def test_oracle_rollout_frames_match_reference():
     z, meta = load("rollout")
-    ost, osy = build_oracle(sub(z, ""), dtype=F64, law="spring")
+    ost, osy = build_oracle(sub(z, ""), dtype=_DT[0], law="spring")
     for k in range(meta["n"]):  # a frame is saved AFTER its `stride` steps; the initial state is not a frame
         oracle.step(ost, osy, meta["stride"])
         close(ost.pos_c, z["frames_pos_c"][k], f"frame {k} pos_c")
@@ -178,10 +189,11 @@ def test_oracle_rollout_frames_match_reference():
     close(ost.pos_c, z["final_pos_c"], "final")
 
 
-def test_oracle_batched_step_matches_reference():
-    z, meta = load("batched")
+@BOTH
+def test_oracle_batched_step_matches_reference(sfx):
+    z, meta = load("batched" + sfx)
     for b in range(meta["B"]):
-        ost, osy = build_oracle(sub(z, f"b{b}"), dtype=F64, law="spring")
+        ost, osy = build_oracle(sub(z, f"b{b}"), dtype=_DT[0], law="spring")
         oracle.step(ost, osy, meta["steps"])
         for f in ("pos_c", "vel", "force", "ang_vel"):
             close(getattr(ost, f), z[f][b], f"{f}[{b}]")
@@ -193,7 +205,7 @@ gpu = pytest.mark.gpu
 
 def _gpu(inp, **kw):
     from helpers import build_gpu
-    return build_gpu(inp, dtype=F64, **kw)
+    return build_gpu(inp, dtype=_DT[0], **kw)
 
 
 @gpu
@@ -242,9 +254,10 @@ def test_cuda_naive_matches_reference():
 
 
 @gpu
-def test_cuda_neighborlist_matches_reference():
+@BOTH
+def test_cuda_neighborlist_matches_reference(sfx):
     import jaxdem_b200 as jd
-    z, meta = load("nlist")
+    z, meta = load("nlist" + sfx)
     gst, gsy = _gpu(sub(z, ""), law="hertz", collider="NeighborList", nmat=2, dt=2e-3,
                     collider_kw=dict(cutoff=meta["cutoff"], skin=meta["skin"]))
     assert gsy.collider.max_neighbors == int(z["max_neighbors"])
@@ -264,9 +277,10 @@ def test_cuda_neighborlist_matches_reference():
 
 
 @gpu
-def test_cuda_multicelllist_matches_reference():
+@BOTH
+def test_cuda_multicelllist_matches_reference(sfx):
     import jaxdem_b200 as jd
-    z, _ = load("multicell")
+    z, _ = load("multicell" + sfx)
     for tag, law, domain in (("a", "spring", "periodic"), ("b", "hertz", "reflect")):
         gst, gsy = _gpu(sub(z, tag), law=law, domain=domain, collider="MultiCellList", nmat=2)
         gsy.collider.compute_force(gst, gsy)
@@ -278,9 +292,10 @@ def test_cuda_multicelllist_matches_reference():
 
 
 @gpu
-def test_cuda_force_manager_matches_reference():
+@BOTH
+def test_cuda_force_manager_matches_reference(sfx):
     import jaxdem_b200 as jd
-    z, _ = load("force_manager")
+    z, _ = load("force_manager" + sfx)
     inp = sub(z, "")
     g, fe, fc, te = (inp.pop(k) for k in ("gravity", "fe", "fc", "te"))
     gst, gsy = _gpu(inp, law="spring", gravity=g)
@@ -294,9 +309,10 @@ def test_cuda_force_manager_matches_reference():
 
 
 @gpu
-def test_cuda_reflect_restitution_matches_reference():
+@BOTH
+def test_cuda_reflect_restitution_matches_reference(sfx):
     import jaxdem_b200 as jd
-    z, meta = load("reflect")
+    z, meta = load("reflect" + sfx)
     for tag in ("a", "b"):
         gst, gsy = _gpu(sub(z, tag), law="spring", domain="reflect", dt=meta["dt"], restitution=meta["restitution"])
         jd.System.step(gst, gsy, n=meta["steps"])
@@ -317,10 +333,11 @@ def test_cuda_rollout_frames_match_reference():
 
 
 @gpu
-def test_cuda_batched_step_matches_reference():
+@BOTH
+def test_cuda_batched_step_matches_reference(sfx):
     import jaxdem_b200 as jd
     import torch
-    z, meta = load("batched")
+    z, meta = load("batched" + sfx)
     B = meta["B"]
     singles = [_gpu(sub(z, f"b{b}"), law="spring") for b in range(B)]
     stb = jd.State.stack([s for s, _ in singles])
@@ -330,7 +347,7 @@ def test_cuda_batched_step_matches_reference():
                                          matcher=jd.MaterialMatchmaker.create("harmonic"))
     syb = jd.System.create(stb.shape, dt=1e-3, collider_type="CellList", collider_kw=dict(state=big),
                            domain_type="periodic", domain_kw=dict(box_size=np.asarray(box)), force_model_type="spring",
-                           mat_table=mt, dtype=torch.float64, device="cuda")
+                           mat_table=mt, dtype=torch.float32 if _DT[0] == np.float32 else torch.float64, device="cuda")
     jd.System.step(stb, syb, n=meta["steps"])
     for f in ("pos_c", "vel", "force", "ang_vel"):
         close(getattr(stb, f), z[f], f, 1e-11)
