@@ -351,3 +351,59 @@ def test_cuda_batched_step_matches_reference(sfx):
     jd.System.step(stb, syb, n=meta["steps"])
     for f in ("pos_c", "vel", "force", "ang_vel"):
         close(getattr(stb, f), z[f], f, 1e-11)
+
+
+# ------------------------------------------------------------------------------------------- full size (2**20, f32)
+def _sha(a):
+    import hashlib
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _fullsize_ref():
+    import json
+    with open(os.path.join(HERE, "golden", "ref_fullsize_c2.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_fullsize_partition_matches_reference_digests():
+    """BASELINE config 2 at FULL size (bench.py's 2**20-sphere workload, float32): the numpy oracle's and the C
+    oracle's cell permutation, sorted hashes and stencil hashes hash to the digests of the reference's own
+    ``_get_spatial_partition`` output (tests/golden/make_reference_fullsize.py)."""
+    import bench
+    from oracle import c_oracle
+    ref = _fullsize_ref()
+    wl = bench.make_workload()
+    ost = oracle.create_state(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=np.float32)
+    osy = oracle.create_system(ost, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                               collider_type="celllist", domain_type="periodic", domain_kw=dict(box_size=wl["box"]),
+                               force_model_type="spring")
+    assert ost.N == ref["n"] and float(osy.collider.cell_size) == ref["cell_size"]
+    perm, sh, nh, ovf, _ = ocol.get_spatial_partition(ost.pos, osy, osy.collider.cell_size,
+                                                      osy.collider.neighbor_mask, ost.idtype)
+    assert perm.dtype == np.int32 and [int(v) for v in perm[:8]] == ref["perm_head"]
+    assert _sha(perm) == ref["perm_sha256"] and _sha(sh) == ref["sorted_hash_sha256"]
+    assert _sha(nh) == ref["nbr_hash_sha256"] and bool(ovf) == ref["hash_overflow"]
+    cperm, csh, _ = c_oracle.CStep(ost, osy).partition()
+    assert _sha(cperm.astype(np.int32)) == ref["perm_sha256"] and _sha(csh.astype(np.int32)) == ref["sorted_hash_sha256"]
+
+
+@gpu
+def test_cuda_fullsize_partition_matches_reference_digests():
+    """The CUDA partition of the full-size config-2 workload against the reference's digests: permutation, sorted
+    hashes and the 27 stencil hashes of every particle, bit for bit."""
+    import jaxdem_b200 as jd
+    import torch
+    import bench
+    ref = _fullsize_ref()
+    wl = bench.make_workload()
+    gst = jd.State.create(wl["pos"], vel=wl["vel"], rad=wl["rad"], mass=wl["mass"], dtype=torch.float32)
+    gsy = jd.System.create(gst.shape, dt=1e-3, linear_integrator_type="verlet", rotation_integrator_type="",
+                           collider_type="CellList", collider_kw=dict(state=gst), domain_type="periodic",
+                           domain_kw=dict(box_size=wl["box"]), force_model_type="spring", dtype=torch.float32)
+    perm, sh, nh, _ = gsy.collider.partition(gst, gsy)
+    assert gst.N == ref["n"]
+    assert _sha(perm.to(torch.int32)) == ref["perm_sha256"]
+    assert _sha(sh.to(torch.int32)) == ref["sorted_hash_sha256"]
+    assert _sha(nh.to(torch.int32)) == ref["nbr_hash_sha256"]
