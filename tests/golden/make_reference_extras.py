@@ -206,7 +206,27 @@ def case_batched(jd, jax, jnp):
     return out, dict(B=B, steps=2)
 
 
-CASES = dict(fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+def case_cross(jd, jax, jnp):
+    """colliders/cell_list.py:598-700 create_cross_neighbor_list: query points (some un-wrapped, some outside a
+    reflecting box's grid) against the state's positions; a roomy and a too-small max_neighbors (overflow flag)."""
+    out = {}
+    for tag, dim, domain in (("a", 3, "periodic"), ("b", 2, "reflect")):
+        inp = make_inputs(160, dim, seed=6, dtype=F64, phi=0.55, poly=1.3)
+        st, sy = build_reference(jd, jnp, inp, domain=domain, law="spring", lin="verlet", rot="verletspiral",
+                                 dt=1e-3, nmat=1)
+        rng = np.random.default_rng(12)
+        pos_a = (rng.uniform(0.0, 0.999, (90, dim)) * inp["box"]).astype(F64)
+        if domain == "periodic":
+            pos_a[::5] += inp["box"].astype(F64)
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out[f"{tag}_in_pos_a"] = pos_a
+        for K in (40, 4):
+            nl, ovf = sy.collider.create_cross_neighbor_list(jnp.asarray(pos_a), st.pos, sy, 1.2, K)
+            out[f"{tag}_nl{K}"], out[f"{tag}_ovf{K}"] = _np(nl), _np(ovf)
+    return out, dict(cutoff=1.2)
+
+
+CASES = dict(cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

@@ -199,6 +199,19 @@ def test_oracle_batched_step_matches_reference(sfx):
             close(getattr(ost, f), z[f][b], f"{f}[{b}]")
 
 
+@BOTH
+def test_oracle_cross_neighbor_list_matches_reference(sfx):
+    z, meta = load("cross" + sfx)
+    for tag, domain in (("a", "periodic"), ("b", "reflect")):
+        inp = sub(z, tag)
+        pos_a = inp.pop("pos_a")
+        ost, osy = build_oracle(inp, dtype=_DT[0], law="spring", domain=domain)
+        for K in (40, 4):
+            nl, ovf = ocol.celllist_create_cross_neighbor_list(pos_a, ost.pos, osy, meta["cutoff"], K)
+            assert np.array_equal(nl, z[f"{tag}_nl{K}"]) and nl.dtype == z[f"{tag}_nl{K}"].dtype, (tag, K)
+            assert bool(ovf) == bool(z[f"{tag}_ovf{K}"]) == (K == 4)
+
+
 # ------------------------------------------------------------------------------------------- GPU: the CUDA path
 gpu = pytest.mark.gpu
 
@@ -351,6 +364,22 @@ def test_cuda_batched_step_matches_reference(sfx):
     jd.System.step(stb, syb, n=meta["steps"])
     for f in ("pos_c", "vel", "force", "ang_vel"):
         close(getattr(stb, f), z[f], f, 1e-11)
+
+
+@gpu
+@BOTH
+def test_cuda_cross_neighbor_list_matches_reference(sfx):
+    import torch
+    z, meta = load("cross" + sfx)
+    for tag, domain in (("a", "periodic"), ("b", "reflect")):
+        inp = sub(z, tag)
+        pos_a = inp.pop("pos_a")
+        gst, gsy = _gpu(inp, law="spring", domain=domain)
+        for K in (40, 4):
+            nl, ovf = gsy.collider.create_cross_neighbor_list(torch.as_tensor(pos_a, device="cuda"), gst.pos, gsy,
+                                                              meta["cutoff"], K)
+            assert np.array_equal(nl.cpu().numpy(), z[f"{tag}_nl{K}"]), (tag, K)
+            assert bool(ovf) == bool(z[f"{tag}_ovf{K}"])
 
 
 # ------------------------------------------------------------------------------------------- full size (2**20, f32)
