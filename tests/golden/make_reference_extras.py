@@ -226,7 +226,21 @@ def case_cross(jd, jax, jnp):
     return out, dict(cutoff=1.2)
 
 
-CASES = dict(cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+def case_materials(jd, jax, jnp):
+    """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
+    effective pair tables of three elastic-friction materials under both matchmakers."""
+    from helpers import MATS
+    out = {}
+    for matcher in ("harmonic", "linear"):
+        mats = [jd.Material.create("elasticfrict", **m) for m in MATS]
+        mt = jd.MaterialTable.from_materials(mats, matcher=jd.MaterialMatchmaker.create(matcher))
+        for k in ("young", "poisson", "density", "mu", "e", "mu_r"):
+            out[f"{matcher}_{k}"] = _np(getattr(mt, k))
+            out[f"{matcher}_{k}_eff"] = _np(getattr(mt, k + "_eff"))
+    return out, {}
+
+
+CASES = dict(materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

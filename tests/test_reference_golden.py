@@ -199,6 +199,22 @@ def test_oracle_batched_step_matches_reference(sfx):
             close(getattr(ost, f), z[f][b], f"{f}[{b}]")
 
 
+def test_material_tables_match_reference():
+    """MaterialTable.from_materials under the harmonic and the linear matchmaker: the oracle's tables AND the
+    product's host-side tables (jaxdem_b200/materials.py, plain torch on CPU) against the reference's."""
+    import jaxdem_b200 as jd
+    z, _ = load("materials")
+    for matcher in ("harmonic", "linear"):
+        omt = oracle.make_material_table(MATS, matcher)
+        pmt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **m) for m in MATS],
+                                              matcher=jd.MaterialMatchmaker.create(matcher))
+        for k in ("young", "poisson", "density", "mu", "e", "mu_r"):
+            for name in (k, k + "_eff"):
+                want = z[f"{matcher}_{name}"]
+                close(getattr(omt, name), want, f"oracle {matcher} {name}", 1e-15)
+                close(getattr(pmt, name), want, f"product {matcher} {name}", 1e-15)
+
+
 @BOTH
 def test_oracle_cross_neighbor_list_matches_reference(sfx):
     z, meta = load("cross" + sfx)
