@@ -13,7 +13,9 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally
 ``roofline`` (dominant kernel), ``step_roofline`` (whole step, 168 algorithmic bytes per
 particle-step), ``cpu_baseline``, ``kernels`` (per-kernel device time of one step) and
 ``parity`` (a small instance of the SAME configuration stepped on the GPU(s) and checked
-against the CPU oracle before anything is timed; the run fails if it does not agree).
+against the CPU oracle before anything is timed; the run fails if it does not agree;
+``parity.reference_golden``: the same CUDA path against stored outputs of the reference itself,
+tests/golden/ref_*.npz — permutation / hashes bit for bit, forces and a 3-step trajectory).
 
 Other workloads of BASELINE.json (``--config``; the default c2 is the headline):
     c3    config 3's physics: cundallstrack + velocity Verlet + verletspiral (352 B / particle-step);
@@ -237,6 +239,35 @@ def parity_check(jd, torch, cfg, dev, world=1, rank=0):
     ok = errs["pos_c"] <= 1e-4 and errs["vel"] <= 1e-4 and errs["force"] <= 1e-3
     return dict(parity_checked=bool(ok), against=f"{against}, {n} particles, {steps} steps", max_rel_err=errs,
                 bound={"pos_c": 1e-4, "vel": 1e-4, "force": 1e-3})
+
+
+def reference_golden_check(jd, torch, cfg):
+    """Next to the live oracle run: the CUDA path against STORED OUTPUTS OF THE REFERENCE ITSELF for this
+    configuration family (tests/golden/ref_*.npz — the unmodified reference sources run on the numpy stand-in for
+    JAX in the build container): cell permutation and sorted hashes bit for bit, contact forces and the
+    3-step trajectory within the float32 bounds of the tests.  A mismatch fails the run; a missing fixture is
+    reported as skipped."""
+    name = {"c2": "ref_c2_like_f32", "c2nl": "ref_c2_like_f32", "c3": "ref_c3_like_f32", "c5": "ref_c5_like_f32"}.get(cfg)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", f"{name}.npz")
+    if name is None or not os.path.exists(path):
+        return dict(checked=False, skipped=f"no stored reference output for {cfg}")
+    tdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests")
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    from helpers import build_gpu, load_golden
+    inp, kw, want, meta = load_golden(path)
+    st, sy = build_gpu(inp, **kw)
+    perm, sh, _, _ = sy.collider.partition(st, sy)
+    ints = bool(np.array_equal(perm.cpu().numpy(), want["perm"]) and np.array_equal(sh.cpu().numpy(), want["sorted_hash"]))
+    sy.collider.compute_force(st, sy)
+    errs = {"force0": _max_rel(st.force.cpu().numpy(), want["force0"])}
+    jd.System.step(st, sy, n=meta["steps"])
+    torch.cuda.synchronize()
+    for f in ("pos_c", "vel", "force"):
+        errs[f] = _max_rel(getattr(st, f).cpu().numpy(), want[f + "_after"])
+    ok = ints and errs["pos_c"] <= 1e-4 and errs["vel"] <= 1e-4 and errs["force0"] <= 1e-4 and errs["force"] <= 1e-3
+    return dict(checked=bool(ok), file=f"tests/golden/{name}.npz", permutation_and_hashes_bit_exact=ints,
+                max_rel_err=errs, steps=int(meta["steps"]))
 
 
 # ---------------------------------------------------------------------------
@@ -489,6 +520,10 @@ def run_cuda(args):
     parity = parity_check(jd, torch, cfg, dev) if not args.no_parity else {"parity_checked": False, "skipped": True}
     if not args.no_parity and not parity["parity_checked"]:
         raise RuntimeError(f"bench.py: the CUDA path does not agree with the CPU oracle: {parity}")
+    if not args.no_parity and rank == 0:
+        parity["reference_golden"] = reference_golden_check(jd, torch, cfg)
+        if world == 1 and not parity["reference_golden"]["checked"] and "skipped" not in parity["reference_golden"]:
+            raise RuntimeError(f"bench.py: the CUDA path does not agree with the stored reference outputs: {parity}")
     if cfg == "c4":
         return run_cuda_ensemble(args, world, rank, local, dev, parity)
     wl = workload_for(cfg, args.n_per_gpu, seed=1 + rank, packing=args.packing)
