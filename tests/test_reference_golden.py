@@ -452,3 +452,22 @@ def test_cuda_fullsize_partition_matches_reference_digests():
     assert _sha(perm.to(torch.int32)) == ref["perm_sha256"]
     assert _sha(sh.to(torch.int32)) == ref["sorted_hash_sha256"]
     assert _sha(nh.to(torch.int32)) == ref["nbr_hash_sha256"]
+
+
+@pytest.mark.parametrize("name", ["ref_c2_like_f32", "ref_c2_like_f64"])
+def test_c_oracle_matches_reference(name):
+    """oracle/c (the full-size checker and the timed CPU baseline) directly against the reference's outputs:
+    permutation / sorted hashes bit for bit, contact forces and the 3-step velocity-Verlet trajectory."""
+    from helpers import load_golden
+    from oracle import c_oracle
+    inp, kw, want, meta = load_golden(os.path.join(HERE, "golden", name + ".npz"))
+    _DT[0] = kw["dtype"]
+    ost, osy = build_oracle(inp, **kw)
+    cs = c_oracle.CStep(ost, osy)
+    perm, sh, _ = cs.partition()
+    assert np.array_equal(perm, want["perm"]) and np.array_equal(sh, want["sorted_hash"])
+    cs.compute_force()
+    close(ost.force, want["force0"], "force0", 1e-12)
+    cs.step(meta["steps"])
+    for f in ("pos_c", "vel", "force"):
+        close(getattr(ost, f), want[f + "_after"], f, 1e-11)
