@@ -226,6 +226,48 @@ def case_cross(jd, jax, jnp):
     return out, dict(cutoff=1.2)
 
 
+STATE_FIELDS = ("pos_c", "pos_p", "vel", "force", "ang_vel", "torque", "rad", "volume", "mass", "inertia", "clump_id",
+                "bond_id", "mat_id", "species_id", "fixed", "_pos_p_rot")
+
+
+def case_state_create(jd, jax, jnp):
+    """state.py:371-867 State.create defaults: a bare position array in 2-D and 3-D (unit radii / masses, solid
+    disc / sphere inertia, identity quaternions), masses from a material table's densities, and a clump system
+    with sparse clump ids (relabelled to dense ids), ragged bonds (symmetrised, padded) and given quaternions
+    (the ``_pos_p_rot`` cache)."""
+    from helpers import MATS
+    rng = np.random.default_rng(8)
+    out = {}
+
+    def put(tag, st):
+        for f in STATE_FIELDS:
+            out[f"{tag}_{f}"] = _np(getattr(st, f))
+        out[f"{tag}_q"] = np.concatenate([_np(st.q.w), _np(st.q.xyz)], axis=-1)
+
+    for tag, dim in (("a", 2), ("b", 3)):
+        pos = rng.uniform(0, 5, (7, dim))
+        out[f"{tag}_in_pos"] = pos
+        put(tag, jd.State.create(jnp.asarray(pos)))
+    pos, rad, mat_id = rng.uniform(0, 5, (9, 3)), rng.uniform(0.2, 0.6, 9), rng.integers(0, 3, 9)
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **m) for m in MATS],
+                                         matcher=jd.MaterialMatchmaker.create("harmonic"))
+    out.update(c_in_pos=pos, c_in_rad=rad, c_in_mat_id=mat_id)
+    put("c", jd.State.create(jnp.asarray(pos), rad=jnp.asarray(rad), mat_id=jnp.asarray(mat_id), mat_table=mt))
+    n = 10
+    pos, pos_p = rng.uniform(0, 5, (n, 3)), rng.normal(0, 0.3, (n, 3))
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    cid = np.array([40, 40, 7, 7, 7, 3, 99, 99, 12, 5])
+    bonds = np.full((n, 2), -1, dtype=np.int64)
+    bonds[0] = [3, 8]
+    bonds[4, 0] = 9
+    bonds[6, 0] = 0
+    out.update(d_in_pos=pos, d_in_pos_p=pos_p, d_in_q=q, d_in_clump_id=cid, d_in_bond=bonds)
+    put("d", jd.State.create(jnp.asarray(pos), pos_p=jnp.asarray(pos_p), q=jnp.asarray(q), clump_id=jnp.asarray(cid),
+                             bond_id=jnp.asarray(bonds)))
+    return out, {}
+
+
 def case_materials(jd, jax, jnp):
     """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
     effective pair tables of three elastic-friction materials under both matchmakers."""
@@ -240,7 +282,7 @@ def case_materials(jd, jax, jnp):
     return out, {}
 
 
-CASES = dict(materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+CASES = dict(state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

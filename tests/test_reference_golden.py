@@ -471,3 +471,36 @@ def test_c_oracle_matches_reference(name):
     cs.step(meta["steps"])
     for f in ("pos_c", "vel", "force"):
         close(getattr(ost, f), want[f + "_after"], f, 1e-11)
+
+
+def test_state_create_defaults_match_reference():
+    """State.create (a2): every field of the State the reference builds — defaults, material-table masses, dense
+    clump relabelling, bond symmetrisation + padding, the ``_pos_p_rot`` cache — from the oracle's create_state AND
+    from the product's host-side State.create (torch on the CPU; no kernel involved)."""
+    import torch
+    import jaxdem_b200 as jd
+    z, _ = load("state_create")
+    fields = ("pos_c", "pos_p", "vel", "force", "ang_vel", "torque", "rad", "volume", "mass", "inertia", "clump_id",
+              "bond_id", "mat_id", "species_id", "fixed", "_pos_p_rot")
+    omt = oracle.make_material_table(MATS, "harmonic")
+    pmt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **m) for m in MATS],
+                                          matcher=jd.MaterialMatchmaker.create("harmonic"))
+    cases = {
+        "a": (dict(), dict()), "b": (dict(), dict()),
+        "c": (dict(rad=z["c_in_rad"], mat_id=z["c_in_mat_id"], mat_table=omt),
+              dict(rad=z["c_in_rad"], mat_id=z["c_in_mat_id"], mat_table=pmt)),
+    }
+    dkw = dict(pos_p=z["d_in_pos_p"], q=z["d_in_q"], clump_id=z["d_in_clump_id"], bond_id=z["d_in_bond"])
+    cases["d"] = (dkw, dkw)
+    for tag, (okw, pkw) in cases.items():
+        ost = oracle.create_state(z[f"{tag}_in_pos"], dtype=F64, **okw)
+        pst = jd.State.create(z[f"{tag}_in_pos"], dtype=torch.float64, device="cpu", **pkw)
+        for f in fields:
+            want = z[f"{tag}_{f}"]
+            for who, got in (("oracle", getattr(ost, f)), ("product", getattr(pst, f).numpy())):
+                if want.dtype.kind in "iub":
+                    assert np.array_equal(np.asarray(got), want), (who, tag, f)
+                else:
+                    close(got, want, f"{who} {tag} {f}", 1e-15, scale=max(1.0, float(np.abs(want).max())))
+        close(np.concatenate([ost.q_w, ost.q_xyz], axis=1), z[f"{tag}_q"], "oracle q", 1e-15, scale=1.0)
+        close(torch.cat([pst.q.w, pst.q.xyz], dim=-1), z[f"{tag}_q"], "product q", 1e-15, scale=1.0)
