@@ -268,6 +268,31 @@ def case_state_create(jd, jax, jnp):
     return out, {}
 
 
+def case_collider_create(jd, jax, jnp):
+    """colliders/cell_list.py:375-433 CellList.Create (cell size and stencil from the radius spread, with and
+    without a box), multi_cell_list.py:324-370, neighbor_list.py:287-402 (skin, max_neighbors sizing)."""
+    rng = np.random.default_rng(0)
+    out = {}
+    for i, (poly, box, dim) in enumerate(((1.0, None, 3), (3.0, None, 3), (1.2, [2.5, 2.5, 2.5], 3), (6.0, None, 2))):
+        rad = rng.uniform(0.5 / poly, 0.5, 50)
+        pos = rng.uniform(0, 5, (50, dim))
+        st = jd.State.create(jnp.asarray(pos), rad=jnp.asarray(rad))
+        kw = {} if box is None else dict(box_size=jnp.asarray(box))
+        c = jd.Collider.create("celllist", state=st, **kw)
+        m = jd.Collider.create("multicelllist", state=st, **kw)
+        out.update({f"k{i}_in_pos": pos, f"k{i}_in_rad": rad, f"k{i}_in_box": np.asarray([] if box is None else box),
+                    f"k{i}_cell_size": _np(c.cell_size), f"k{i}_neighbor_mask": _np(c.neighbor_mask),
+                    f"k{i}_multi_cell_size": _np(m.cell_size), f"k{i}_multi_neighbor_mask": _np(m.neighbor_mask)})
+        for j, nkw in enumerate((dict(cutoff=1.0), dict(cutoff=1.0, skin=0.3), dict(cutoff=1.5, skin_fraction=0.2),
+                                 dict(cutoff=1.0, skin=0.1, max_neighbors=7),
+                                 dict(cutoff=1.2, skin=0.1, number_density=0.6, safety_factor=1.5))):
+            nl = jd.Collider.create("neighborlist", state=st, **nkw)
+            out[f"k{i}_nl{j}"] = np.asarray([float(np.asarray(nl.cutoff)), float(np.asarray(nl.skin)),
+                                             float(int(nl.max_neighbors)),
+                                             float(np.asarray(nl.secondary_collider.cell_size))])
+    return out, {}
+
+
 def case_materials(jd, jax, jnp):
     """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
     effective pair tables of three elastic-friction materials under both matchmakers."""
@@ -282,7 +307,7 @@ def case_materials(jd, jax, jnp):
     return out, {}
 
 
-CASES = dict(state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+CASES = dict(collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

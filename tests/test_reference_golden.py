@@ -504,3 +504,39 @@ def test_state_create_defaults_match_reference():
                     close(got, want, f"{who} {tag} {f}", 1e-15, scale=max(1.0, float(np.abs(want).max())))
         close(np.concatenate([ost.q_w, ost.q_xyz], axis=1), z[f"{tag}_q"], "oracle q", 1e-15, scale=1.0)
         close(torch.cat([pst.q.w, pst.q.xyz], dim=-1), z[f"{tag}_q"], "product q", 1e-15, scale=1.0)
+
+
+NL_KW = (dict(cutoff=1.0), dict(cutoff=1.0, skin=0.3), dict(cutoff=1.5, skin_fraction=0.2),
+         dict(cutoff=1.0, skin=0.1, max_neighbors=7), dict(cutoff=1.2, skin=0.1, number_density=0.6, safety_factor=1.5))
+
+
+def test_collider_create_matches_reference():
+    """Collider ``Create`` (a9, f2, f3): cell size and stencil of CellList / MultiCellList from the radius spread (with
+    and without a box), skin and max_neighbors sizing of NeighborList — the oracle's constructors AND the product's
+    host-side ones (torch on the CPU) against the reference's."""
+    import torch
+    import warnings
+    import jaxdem_b200 as jd
+    z, _ = load("collider_create")
+    for i in range(4):
+        pos, rad, box = z[f"k{i}_in_pos"], z[f"k{i}_in_rad"], z[f"k{i}_in_box"]
+        box = None if box.size == 0 else box
+        ost = oracle.create_state(pos, rad=rad, dtype=F64)
+        pst = jd.State.create(pos, rad=rad, dtype=torch.float64, device="cpu")
+        oc, om = ocol.celllist_create(ost, box_size=box), ocol.multicelllist_create(ost, box_size=box)
+        pc = jd.Collider.create("CellList", state=pst, box_size=box)
+        pm = jd.Collider.create("MultiCellList", state=pst, box_size=box)
+        for who, c, m in (("oracle", oc, om), ("product", pc, pm)):
+            assert float(c.cell_size) == float(z[f"k{i}_cell_size"]), (who, i)
+            assert float(m.cell_size) == float(z[f"k{i}_multi_cell_size"]), (who, i)
+            assert np.array_equal(np.asarray(c.neighbor_mask), z[f"k{i}_neighbor_mask"]), (who, i)
+            assert np.array_equal(np.asarray(m.neighbor_mask), z[f"k{i}_multi_neighbor_mask"]), (who, i)
+        for j, kw in enumerate(NL_KW):
+            want = z[f"k{i}_nl{j}"]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                on = ocol.neighborlist_create(ost, **kw)
+                pn = jd.Collider.create("NeighborList", state=pst, **kw)
+            for who, n in (("oracle", on), ("product", pn)):
+                got = [float(n.cutoff), float(n.skin), float(int(n.max_neighbors)), float(n.secondary_collider.cell_size)]
+                assert got == [float(v) for v in want], (who, i, j, got, want)
