@@ -293,6 +293,30 @@ def case_collider_create(jd, jax, jnp):
     return out, {}
 
 
+def case_pair_laws(jd, jax, jnp):
+    """forces/{spring,hertz,cundall_strack}.py: the per-pair plugin contract ``force(i, j, pos, state, system)`` /
+    ``energy(...)`` on touching pairs (nearest periodic neighbours), random pairs and self pairs, two materials."""
+    out = {}
+    for dim in (2, 3):
+        inp = make_inputs(120, dim, seed=5, dtype=F64, phi=0.7, nmat=2)
+        rng = np.random.default_rng(1)
+        d = inp["pos"][:, None, :] - inp["pos"][None, :, :]
+        d -= inp["box"] * np.round(d / inp["box"])
+        near = np.argsort((d**2).sum(-1), axis=1)[:, 1]
+        i = np.concatenate([np.arange(120), rng.integers(0, 120, 80), np.arange(5)])
+        j = np.concatenate([near, rng.integers(0, 120, 80), np.arange(5)])
+        out.update({f"d{dim}_{k}": v for k, v in _inputs(inp).items()})
+        out[f"d{dim}_i"], out[f"d{dim}_j"] = i, j
+        for law in ("spring", "hertz", "cundallstrack"):
+            st, sy = build_reference(jd, jnp, inp, domain="periodic", law=law, lin="verlet", rot="verletspiral",
+                                     dt=1e-3, nmat=2, collider="naive")
+            fm = sy.force_model
+            f, t = jax.vmap(lambda a, b: fm.force(a, b, st.pos, st, sy))(jnp.asarray(i), jnp.asarray(j))
+            e = jax.vmap(lambda a, b: fm.energy(a, b, st.pos, st, sy))(jnp.asarray(i), jnp.asarray(j))
+            out[f"d{dim}_{law}_f"], out[f"d{dim}_{law}_t"], out[f"d{dim}_{law}_e"] = _np(f), _np(t), _np(e)
+    return out, {}
+
+
 def case_materials(jd, jax, jnp):
     """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
     effective pair tables of three elastic-friction materials under both matchmakers."""
@@ -307,7 +331,7 @@ def case_materials(jd, jax, jnp):
     return out, {}
 
 
-CASES = dict(collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+CASES = dict(pair_laws=case_pair_laws, collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

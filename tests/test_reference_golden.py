@@ -540,3 +540,38 @@ def test_collider_create_matches_reference():
             for who, n in (("oracle", on), ("product", pn)):
                 got = [float(n.cutoff), float(n.skin), float(int(n.max_neighbors)), float(n.secondary_collider.cell_size)]
                 assert got == [float(v) for v in want], (who, i, j, got, want)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("law", ["spring", "hertz", "cundallstrack"])
+def test_pair_law_contract_matches_reference(dim, law):
+    """The per-pair plugin contract ``ForceModel.force / energy(i, j, pos, state, system)`` (forces/__init__.py:55-150):
+    the oracle's laws AND the product's torch implementation (jaxdem_b200/pair_laws.py, CPU tensors) against the
+    reference's own calls on touching, random and self pairs."""
+    import torch
+    import jaxdem_b200 as jd
+    from oracle import forces as oforces
+    z, _ = load("pair_laws")
+    inp = sub(z, f"d{dim}")
+    i, j = z[f"d{dim}_i"], z[f"d{dim}_j"]
+    wf, wt, we = (z[f"d{dim}_{law}_{k}"] for k in ("f", "t", "e"))
+    assert np.abs(wf).max() > 0 and (law != "cundallstrack" or np.abs(wt).max() > 0)
+    ost = oracle.create_state(inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"], mass=inp["mass"],
+                              mat_id=inp["mat_id"], dtype=F64)
+    osy = oracle.create_system(ost, domain_type="periodic", domain_kw=dict(box_size=inp["box"]), force_model_type=law,
+                               mat_table=oracle.make_material_table(MATS[:2], "harmonic"))
+    of, ot = getattr(oforces, law + "_force")(i, j, ost.pos, ost, osy)
+    oe = getattr(oforces, law + "_energy")(i, j, ost.pos, ost, osy)
+    st = jd.State.create(inp["pos"], vel=inp["vel"], ang_vel=inp["ang_vel"], rad=inp["rad"], mass=inp["mass"],
+                         mat_id=inp["mat_id"], dtype=torch.float64, device="cpu")
+    mt = jd.MaterialTable.from_materials([jd.Material.create("elasticfrict", **m) for m in MATS[:2]],
+                                         matcher=jd.MaterialMatchmaker.create("harmonic"))
+    sy = jd.System.create(st.shape, domain_type="periodic", domain_kw=dict(box_size=inp["box"]), force_model_type=law,
+                          mat_table=mt, collider_type="naive", dtype=torch.float64, device="cpu")
+    pf, pt = sy.force_model.force(torch.as_tensor(i), torch.as_tensor(j), st.pos, st, sy)
+    pe = sy.force_model.energy(torch.as_tensor(i), torch.as_tensor(j), st.pos, st, sy)
+    fs = float(np.abs(wf).max())
+    for who, (f, t, e) in (("oracle", (of, ot, oe)), ("product", (pf, pt, pe))):
+        close(f, wf, f"{who} force", 1e-13)
+        close(t, wt, f"{who} torque", 1e-13, scale=fs)
+        close(e, we, f"{who} energy", 1e-13)
