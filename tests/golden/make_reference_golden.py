@@ -38,6 +38,7 @@ CASES = [  # name (its suffix is the dtype), n, dim, domain, law, rot, clumps
     ("ref_c5_like_f64", 140, 3, "periodic", "cundallstrack", "verletspiral", True),
     ("ref_readme_like_f64", 120, 3, "reflect", "spring", "verletspiral", False),
     ("ref_hertz_free_f64", 140, 2, "free", "hertz", "spiral", False),
+    ("ref_spiral3d_free_f64", 120, 3, "free", "cundallstrack", "spiral", True),  # 3-D spiral + Euler on clumps, free box
 ]
 STEPS = 3
 
