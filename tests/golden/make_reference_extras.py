@@ -317,6 +317,25 @@ def case_pair_laws(jd, jax, jnp):
     return out, {}
 
 
+def case_energy(jd, jax, jnp):
+    """utils/thermal.py:83-177: translational / rotational kinetic energy, potential energy (collider + gravity) and
+    total energy of a clump system under gravity — the quantities the energy-drift tests integrate."""
+    from jaxdem.utils import thermal
+    out = {}
+    for tag, dim in (("a", 3), ("b", 2)):
+        inp = make_inputs(90, dim, seed=13, dtype=F64, phi=0.55, poly=1.3, clumps=True)
+        g = np.array([0.0, -9.81, 0.0][:dim] if dim == 3 else [0.0, -9.81], dtype=F64)
+        st, sy = build_reference(jd, jnp, inp, domain="periodic", law="hertz", lin="verlet", rot="verletspiral",
+                                 dt=1e-3, nmat=1, gravity=jnp.asarray(g))
+        out.update({f"{tag}_{k}": v for k, v in _inputs(inp).items()})
+        out[f"{tag}_in_gravity"] = g
+        out[f"{tag}_ke_t"] = _np(thermal.compute_translational_kinetic_energy(st))
+        out[f"{tag}_ke_r"] = _np(thermal.compute_rotational_kinetic_energy(st))
+        out[f"{tag}_pe"] = _np(thermal.compute_potential_energy(st, sy))
+        out[f"{tag}_e"] = _np(thermal.compute_energy(st, sy))
+    return out, {}
+
+
 def case_materials(jd, jax, jnp):
     """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
     effective pair tables of three elastic-friction materials under both matchmakers."""
@@ -331,7 +350,7 @@ def case_materials(jd, jax, jnp):
     return out, {}
 
 
-CASES = dict(pair_laws=case_pair_laws, collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+CASES = dict(energy=case_energy, pair_laws=case_pair_laws, collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

@@ -575,3 +575,19 @@ def test_pair_law_contract_matches_reference(dim, law):
         close(f, wf, f"{who} force", 1e-13)
         close(t, wt, f"{who} torque", 1e-13, scale=fs)
         close(e, we, f"{who} energy", 1e-13)
+
+
+def test_oracle_energy_helpers_match_reference():
+    """utils/thermal.py kinetic / potential / total energy of a clump system under gravity (what the energy-drift
+    tests of test_oracle_pins.py and tests/test_gpu_system.py integrate)."""
+    from oracle import force_manager as ofm, system as osys
+    z, _ = load("energy")
+    for tag in ("a", "b"):
+        inp = sub(z, tag)
+        g = inp.pop("gravity")
+        ost, osy = build_oracle(inp, dtype=F64, law="hertz", gravity=g)
+        ke = osys.kinetic_energy(ost)
+        close(np.asarray(ke), z[f"{tag}_ke_t"] + z[f"{tag}_ke_r"], "kinetic", 1e-13)
+        pe = ofm.compute_potential_energy(ost, osy) + ocol.compute_potential_energy(ost, osy)
+        close(np.asarray(pe), z[f"{tag}_pe"], "potential", 1e-12, scale=max(abs(float(z[f"{tag}_pe"])), abs(float(z[f"{tag}_e"]))))
+        close(np.asarray(osys.total_energy(ost, osy)), z[f"{tag}_e"], "total", 1e-12)
