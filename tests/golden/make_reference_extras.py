@@ -336,6 +336,31 @@ def case_energy(jd, jax, jnp):
     return out, {}
 
 
+def case_errors(jd, jax, jnp):
+    """Error behaviour of the factories / builders on the path (factory.py:240-320, system.py:474-540,
+    neighbor_list.py:330-340, system.py:684-690): exception type and message of seven invalid calls."""
+    st = jd.State.create(jnp.asarray(np.random.default_rng(0).uniform(0, 3, (6, 2))))
+    mt_el = jd.MaterialTable.from_materials([jd.Material.create("elastic", young=1.0, poisson=0.3, density=1.0)])
+    sy = jd.System.create(st.shape)
+    calls = dict(
+        missing_material_fields=lambda: jd.System.create(st.shape, force_model_type="cundallstrack", mat_table=mt_el),
+        skin_and_fraction=lambda: jd.Collider.create("neighborlist", state=st, cutoff=1.0, skin=0.1, skin_fraction=0.1),
+        unknown_collider=lambda: jd.Collider.create("nosuchcollider"),
+        rollout_without_n=lambda: jd.System.trajectory_rollout(st, sy),
+        unknown_material=lambda: jd.Material.create("nosuchmaterial"),
+        unknown_force_model=lambda: jd.ForceModel.create("nosuchlaw"),
+        unknown_domain=lambda: jd.Domain.create("nosuchdomain", dim=2),
+    )
+    out = {}
+    for name, f in calls.items():
+        try:
+            f()
+            out[name] = np.array(["", ""])
+        except Exception as e:  # noqa: BLE001 - the point is to record whatever the reference raises
+            out[name] = np.array([type(e).__name__, str(e)])
+    return out, {}
+
+
 def case_materials(jd, jax, jnp):
     """materials/material_table.py:87-140 + material_matchmakers/{harmonic,linear}.py: per-material arrays and the
     effective pair tables of three elastic-friction materials under both matchmakers."""
@@ -350,7 +375,7 @@ def case_materials(jd, jax, jnp):
     return out, {}
 
 
-CASES = dict(energy=case_energy, pair_laws=case_pair_laws, collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
+CASES = dict(errors=case_errors, energy=case_energy, pair_laws=case_pair_laws, collider_create=case_collider_create, state_create=case_state_create, materials=case_materials, cross=case_cross, cross_f32=case_cross, fire=case_fire, naive=case_naive, nlist=case_nlist, multicell=case_multicell,
              force_manager=case_force_manager, reflect=case_reflect, rollout=case_rollout, batched=case_batched,
              nlist_f32=case_nlist, multicell_f32=case_multicell, force_manager_f32=case_force_manager,
              reflect_f32=case_reflect, batched_f32=case_batched)

@@ -591,3 +591,36 @@ def test_oracle_energy_helpers_match_reference():
         pe = ofm.compute_potential_energy(ost, osy) + ocol.compute_potential_energy(ost, osy)
         close(np.asarray(pe), z[f"{tag}_pe"], "potential", 1e-12, scale=max(abs(float(z[f"{tag}_pe"])), abs(float(z[f"{tag}_e"]))))
         close(np.asarray(osys.total_energy(ost, osy)), z[f"{tag}_e"], "total", 1e-12)
+
+
+def test_error_behaviour_matches_reference():
+    """Invalid calls raise what the reference raises (type and message; for the factories' "Unknown X" errors the
+    message up to the list of registered keys, which differs by scope): recorded from the reference in
+    tests/golden/extras/errors.npz."""
+    import torch
+    import jaxdem_b200 as jd
+    z, _ = load("errors")
+    st = jd.State.create(np.random.default_rng(0).uniform(0, 3, (6, 2)), dtype=torch.float64, device="cpu")
+    mt_el = jd.MaterialTable.from_materials([jd.Material.create("elastic", young=1.0, poisson=0.3, density=1.0)])
+    sy = jd.System.create(st.shape, device="cpu")
+    calls = dict(
+        missing_material_fields=lambda: jd.System.create(st.shape, force_model_type="cundallstrack", mat_table=mt_el,
+                                                         device="cpu"),
+        skin_and_fraction=lambda: jd.Collider.create("neighborlist", state=st, cutoff=1.0, skin=0.1, skin_fraction=0.1),
+        unknown_collider=lambda: jd.Collider.create("nosuchcollider"),
+        rollout_without_n=lambda: jd.System.trajectory_rollout(st, sy),
+        unknown_material=lambda: jd.Material.create("nosuchmaterial"),
+        unknown_force_model=lambda: jd.ForceModel.create("nosuchlaw"),
+        unknown_domain=lambda: jd.Domain.create("nosuchdomain", dim=2),
+    )
+    for name, f in calls.items():
+        want_type, want_msg = (str(v) for v in z[name])
+        assert want_type, name  # the reference did raise
+        with pytest.raises(Exception) as ei:
+            f()
+        assert type(ei.value).__name__ == want_type, (name, type(ei.value).__name__, want_type)
+        got = str(ei.value)
+        if name.startswith("unknown_"):
+            assert got.split("Available:")[0] == want_msg.split("Available:")[0], (name, got, want_msg)
+        else:
+            assert got == want_msg, (name, got, want_msg)
